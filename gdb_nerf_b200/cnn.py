@@ -1,0 +1,172 @@
+"""The convolutional networks that stay in PyTorch / cuDNN (out of scope of the
+hand-written path): 2-D feature pyramid, the two 3-D
+cost-regularisation U-Nets and the residual-dense up-sampling decoder.
+
+They are re-declared here only so that checkpoints of the reference load with
+``strict=True``: parameter names, shapes and arithmetic follow
+networks/gdb_nerf/{feature_net.py:12-64, cost_reg_net.py:8-117,
+decoder_rdn.py:7-82, modules.py:5-57}.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _cbr(conv: nn.Module, norm: nn.Module) -> nn.Sequential:
+    # conv -> batch-norm -> ReLU, indices 0/1/2 as in the reference's block builders
+    return nn.Sequential(conv, norm, nn.ReLU(inplace=True))
+
+
+def _c2(cin: int, cout: int, k: int, stride: int = 1) -> nn.Sequential:
+    return _cbr(nn.Conv2d(cin, cout, k, stride, k // 2, bias=False), nn.BatchNorm2d(cout))
+
+
+def _c3(cin: int, cout: int, stride: int = 1) -> nn.Sequential:
+    return _cbr(nn.Conv3d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm3d(cout))
+
+
+def _d3(cin: int, cout: int) -> nn.Sequential:
+    return _cbr(nn.ConvTranspose3d(cin, cout, 3, 2, 1, 1, bias=False), nn.BatchNorm3d(cout))
+
+
+class FeatureNet(nn.Module):
+    """Three-level FPN; returns [1/4 res, 1/2 res, full res] feature maps."""
+
+    def __init__(self, base_channels: int = 8, out_channels: Sequence[int] = (32, 16, 8)) -> None:
+        super().__init__()
+        c = base_channels
+        self.conv0 = nn.Sequential(_c2(3, c, 3), _c2(c, c, 3))
+        self.conv1 = nn.Sequential(_c2(c, 2 * c, 5, 2), _c2(2 * c, 2 * c, 3))
+        self.conv2 = nn.Sequential(_c2(2 * c, 4 * c, 5, 2), _c2(4 * c, 4 * c, 3))
+        self.out0 = nn.Conv2d(4 * c, out_channels[0], 1)
+        self.inner1 = nn.Conv2d(2 * c, 4 * c, 1)
+        self.inner2 = nn.Conv2d(c, 4 * c, 1)
+        self.out1 = nn.Conv2d(4 * c, out_channels[1], 3, padding=1, bias=False)
+        self.out2 = nn.Conv2d(4 * c, out_channels[2], 3, padding=1, bias=False)
+
+    def forward(self, x: torch.Tensor, levels: int = 3) -> List[torch.Tensor]:
+        """``levels`` < 3 skips the finer lateral branches nobody consumes
+        (the full-resolution level is never read on the rendering path)."""
+        f0 = self.conv0(x)
+        f1 = self.conv1(f0)
+        f2 = self.conv2(f1)
+        outs = [self.out0(f2)]
+        if levels >= 2:
+            top = F.interpolate(f2, size=f1.shape[-2:], mode="nearest") + self.inner1(f1)
+            outs.append(self.out1(top))
+            if levels >= 3:
+                top = F.interpolate(top, size=f0.shape[-2:], mode="nearest") + self.inner2(f0)
+                outs.append(self.out2(top))
+        return outs
+
+
+class _CostReg(nn.Module):
+    def _heads(self, c: int, cout: int) -> None:
+        self.feat_head = nn.Conv3d(c, cout, 3, padding=1, bias=False)
+        self.prob_head = nn.Conv3d(c, 1, 3, padding=1, bias=False)
+
+    def _finish(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.feat_head(x), torch.softmax(self.prob_head(x).squeeze(1), dim=1)
+
+
+class CostRegNetSmall(_CostReg):
+    """Two-level 3-D U-Net (stage 0)."""
+
+    def __init__(self, cin: int, cout: int, c: int) -> None:
+        super().__init__()
+        self.conv0 = _c3(cin, c)
+        self.conv1 = _c3(c, 2 * c, 2)
+        self.conv2 = _c3(2 * c, 2 * c)
+        self.conv3 = _c3(2 * c, 4 * c, 2)
+        self.conv4 = _c3(4 * c, 4 * c)
+        self.conv5 = _d3(4 * c, 2 * c)
+        self.conv6 = _d3(2 * c, c)
+        self._heads(c, cout)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        s0 = self.conv0(x)
+        s1 = self.conv2(self.conv1(s0))
+        y = self.conv4(self.conv3(s1))
+        y = s1 + self.conv5(y)
+        y = s0 + self.conv6(y)
+        return self._finish(y)
+
+
+class CostRegNet(_CostReg):
+    """Three-level 3-D U-Net (later stages)."""
+
+    def __init__(self, cin: int, cout: int, c: int) -> None:
+        super().__init__()
+        self.conv0 = _c3(cin, c)
+        self.conv1 = _c3(c, 2 * c, 2)
+        self.conv2 = _c3(2 * c, 2 * c)
+        self.conv3 = _c3(2 * c, 4 * c, 2)
+        self.conv4 = _c3(4 * c, 4 * c)
+        self.conv5 = _c3(4 * c, 8 * c, 2)
+        self.conv6 = _c3(8 * c, 8 * c)
+        self.conv7 = _d3(8 * c, 4 * c)
+        self.conv8 = _d3(4 * c, 2 * c)
+        self.conv9 = _d3(2 * c, c)
+        self._heads(c, cout)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        s0 = self.conv0(x)
+        s1 = self.conv2(self.conv1(s0))
+        s2 = self.conv4(self.conv3(s1))
+        y = self.conv6(self.conv5(s2))
+        y = s2 + self.conv7(y)
+        y = s1 + self.conv8(y)
+        y = s0 + self.conv9(y)
+        return self._finish(y)
+
+
+class _SqueezeExcite(nn.Module):
+    def __init__(self, channels: int, reduction: int = 16) -> None:
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(channels, channels // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(channels // reduction, channels, bias=False), nn.Sigmoid())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        gate = self.fc(self.avg_pool(x).flatten(1))
+        return x * gate[:, :, None, None]
+
+
+class _DenseBlock(nn.Module):
+    def __init__(self, channels: int, growth: int = 32) -> None:
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, growth, 3, padding=1, bias=False)
+        self.conv2 = nn.Conv2d(channels + growth, growth, 3, padding=1, bias=False)
+        self.conv3 = nn.Conv2d(channels + 2 * growth, channels, 3, padding=1, bias=False)
+        self.se = _SqueezeExcite(channels)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        a = F.relu(self.conv1(x))
+        b = F.relu(self.conv2(torch.cat((x, a), 1)))
+        return x + self.se(self.conv3(torch.cat((x, a, b), 1)))
+
+
+class Decoder(nn.Module):
+    """Residual-dense network + pixel-shuffle up-sampler (x upscale_factor)."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_feats: int, num_layers: int, upscale_factor: int) -> None:
+        super().__init__()
+        if upscale_factor <= 0 or upscale_factor & (upscale_factor - 1):
+            raise ValueError("`upscale_factor` must be a power of 2.")
+        self.upscale_factor = upscale_factor
+        self.in_conv = nn.Conv2d(in_channels, num_feats, 3, padding=1)
+        self.blocks = nn.Sequential(*(_DenseBlock(num_feats) for _ in range(num_layers)))
+        ups: List[nn.Module] = []
+        for _ in range(int(round(math.log2(upscale_factor)))):
+            ups += [nn.Conv2d(num_feats, 4 * num_feats, 3, padding=1), nn.PixelShuffle(2)]
+        self.up = nn.Sequential(*ups)
+        self.out_conv = nn.Conv2d(num_feats, out_channels, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.in_conv(x)
+        return self.out_conv(self.up(y + self.blocks(y)))

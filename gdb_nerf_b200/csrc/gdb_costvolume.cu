@@ -1,0 +1,365 @@
+// Cost-volume side of the path: homography matrices, depth hypotheses,
+// fused homography-warp + variance (K1) and depth regression (K2).
+// Reference: networks/gdb_nerf/depth_net.py:399-514.
+#include "gdb_common.cuh"
+
+namespace gdb {
+
+// ---------------------------------------------------------------------------
+// small dense inverses in double (device): plumbing for camera matrices
+// ---------------------------------------------------------------------------
+__device__ inline void inv4x4(const double* a, double* out) {
+  double m[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      m[i][j] = a[i * 4 + j];
+      m[i][j + 4] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    double best = fabs(m[c][c]);
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
+    if (piv != c)
+      for (int j = 0; j < 8; ++j) { double t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+    double inv = 1.0 / m[c][c];
+    for (int j = 0; j < 8; ++j) m[c][j] *= inv;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        double f = m[r][c];
+        for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
+      }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = m[i][j + 4];
+}
+
+// ---------------------------------------------------------------------------
+// homography matrices  (depth_net.py:453-457 with the scaling of :159-162)
+// ---------------------------------------------------------------------------
+__global__ void homography_kernel(const float* __restrict__ src_exts, const float* __restrict__ src_ints,
+                                  const float* __restrict__ tar_exts, const float* __restrict__ tar_ints,
+                                  float src_scale, float tar_scale, int B, int V, float* __restrict__ proj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * V) return;
+  int b = i / V;
+  double Ks[9], Kt[9];
+  for (int k = 0; k < 9; ++k) {
+    // the reference scales rows 0-1 in float32 (in-place multiply) before anything else
+    float s = src_ints[i * 9 + k], t = tar_ints[b * 9 + k];
+    Ks[k] = (k < 6) ? (double)fmul(s, src_scale) : (double)s;
+    Kt[k] = (k < 6) ? (double)fmul(t, tar_scale) : (double)t;
+  }
+  const float* Es = src_exts + (size_t)i * 16;
+  const float* Et = tar_exts + (size_t)b * 16;
+  double Ps[12], Pt[16], Pti[16];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double a = 0.0, t = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        a += Ks[r * 3 + k] * (double)Es[k * 4 + c];
+        t += Kt[r * 3 + k] * (double)Et[k * 4 + c];
+      }
+      Ps[r * 4 + c] = a;
+      Pt[r * 4 + c] = t;
+    }
+  Pt[12] = Pt[13] = Pt[14] = 0.0;
+  Pt[15] = 1.0;
+  inv4x4(Pt, Pti);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 4; ++k) a += Ps[r * 4 + k] * Pti[k * 4 + c];
+      proj[(size_t)i * 12 + r * 4 + c] = (float)a;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// depth hypotheses (depth_net.py:399-421)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float hypothesis(float near_, float far_, int d, int D, int inv_depth) {
+  if (inv_depth) {
+    near_ = fdiv(1.f, near_);
+    far_ = fdiv(1.f, far_);
+  }
+  return fadd(near_, fmul(fsub(far_, near_), linspace01(d, D)));
+}
+
+__global__ void depth_values_kernel(const float* __restrict__ range, int rh, int rw, int B, int D, int Ht, int Wt,
+                                    int inv_depth, float* __restrict__ out) {
+  size_t n = (size_t)B * D * Ht * Wt;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int x = i % Wt;
+    int y = (i / Wt) % Ht;
+    int d = (i / ((size_t)Wt * Ht)) % D;
+    int b = i / ((size_t)Wt * Ht * D);
+    int ry = rh == 1 ? 0 : y, rx = rw == 1 ? 0 : x;
+    float near_ = range[((size_t)(b * 2 + 0) * rh + ry) * rw + rx];
+    float far_ = range[((size_t)(b * 2 + 1) * rh + ry) * rw + rx];
+    out[i] = hypothesis(near_, far_, d, D, inv_depth);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: homography warp + variance over views (depth_net.py:459-474)
+//
+// Thread = (target pixel, 4-channel slice).  C/4 adjacent lanes read one source
+// texel (C*4 bytes, channels-last) as consecutive float4s, so every warp-level
+// LDG.128 covers whole 128-byte lines.  A CTA owns PIX consecutive target
+// pixels and DCH depth planes; the 4-channel results are transposed through
+// shared memory so that the NCDHW variance volume is written in 128-byte
+// (or longer) runs per channel plane.
+// ---------------------------------------------------------------------------
+template <int C, int V>
+__global__ void __launch_bounds__(256)
+warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
+                     int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
+                     float* __restrict__ out) {
+  constexpr int LPP = C / 4;          // lanes per pixel
+  constexpr int PIX = 256 / LPP;      // pixels per CTA
+  constexpr int PAD = (C == 32) ? 1 : (C == 16 ? 2 : 4);
+  constexpr int ROW = PIX + PAD;
+  __shared__ float tile[2][C * ROW];
+  __shared__ float sproj[V * 12];
+
+  const int b = blockIdx.z;
+  const int HW = Ht * Wt;
+  const int q = threadIdx.x % LPP;
+  const int pl = threadIdx.x / LPP;
+  const int pix = blockIdx.x * PIX + pl;
+  const bool live = pix < HW;
+  const int px = live ? pix % Wt : 0, py = live ? pix / Wt : 0;
+
+  if (threadIdx.x < V * 12) sproj[threadIdx.x] = proj[(size_t)b * V * 12 + threadIdx.x];
+  __syncthreads();
+
+  // rotation part applied to the pixel centre, once per view
+  float rx[V], ry[V], rz[V];
+  const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float* P = sproj + v * 12;
+    rx[v] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
+    ry[v] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
+    rz[v] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
+  }
+  const int ryi = rh == 1 ? 0 : py, rxi = rw == 1 ? 0 : px;
+  const float near_ = range[((size_t)(b * 2 + 0) * rh + ryi) * rw + rxi];
+  const float far_ = range[((size_t)(b * 2 + 1) * rh + ryi) * rw + rxi];
+  const float fWs = (float)Ws, fHs = (float)Hs;
+  const size_t view_stride = (size_t)Hs * Ws * C;
+  const float* fbase = feat + (size_t)b * V * view_stride + q * 4;
+
+  const int d0 = blockIdx.y * DCH;
+  const int d1 = min(d0 + DCH, D);
+  int buf = 0;
+  for (int d = d0; d < d1; ++d, buf ^= 1) {
+    float dv = hypothesis(near_, far_, d, D, inv_depth);
+    float depth = inv_depth ? fdiv(1.f, dv) : dv;
+    float4 val[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float* P = sproj + v * 12;
+      float X = fmaf(rx[v], depth, P[3]);
+      float Y = fmaf(ry[v], depth, P[7]);
+      float Z = fmaxf(fmaf(rz[v], depth, P[11]), 1e-6f);
+      // same normalise -> un-normalise sequence as the reference + grid_sample
+      float gx = 2.f * (X / Z) / fWs - 1.f;
+      float gy = 2.f * (Y / Z) / fHs - 1.f;
+      float ix = ((gx + 1.f) * fWs - 1.f) * 0.5f;
+      float iy = ((gy + 1.f) * fHs - 1.f) * 0.5f;
+      float x0f = floorf(ix), y0f = floorf(iy);
+      float tx = ix - x0f, ty = iy - y0f;
+      // keep the integer conversion safe for wild coordinates
+      x0f = fminf(fmaxf(x0f, -2.f), fWs + 1.f);
+      y0f = fminf(fmaxf(y0f, -2.f), fHs + 1.f);
+      int x0 = (int)x0f, y0 = (int)y0f;
+      bool vx0 = x0 >= 0 && x0 < Ws, vx1 = x0 + 1 >= 0 && x0 + 1 < Ws;
+      bool vy0 = y0 >= 0 && y0 < Hs, vy1 = y0 + 1 >= 0 && y0 + 1 < Hs;
+      const float* vb = fbase + v * view_stride;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t00 = acc, t10 = acc, t01 = acc, t11 = acc;
+      if (live) {
+        if (vx0 && vy0) t00 = ldg4(vb + ((size_t)y0 * Ws + x0) * C);
+        if (vx1 && vy0) t10 = ldg4(vb + ((size_t)y0 * Ws + x0 + 1) * C);
+        if (vx0 && vy1) t01 = ldg4(vb + ((size_t)(y0 + 1) * Ws + x0) * C);
+        if (vx1 && vy1) t11 = ldg4(vb + ((size_t)(y0 + 1) * Ws + x0 + 1) * C);
+      }
+      acc = f4_scale_add(acc, t00, (1.f - tx) * (1.f - ty));
+      acc = f4_scale_add(acc, t10, tx * (1.f - ty));
+      acc = f4_scale_add(acc, t01, (1.f - tx) * ty);
+      acc = f4_scale_add(acc, t11, tx * ty);
+      val[v] = acc;
+    }
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < V; ++v) { mean.x += val[v].x; mean.y += val[v].y; mean.z += val[v].z; mean.w += val[v].w; }
+    const float invV = 1.f / (float)V;
+    mean.x *= invV; mean.y *= invV; mean.z *= invV; mean.w *= invV;
+    float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float a = val[v].x - mean.x, bb = val[v].y - mean.y, c = val[v].z - mean.z, e = val[v].w - mean.w;
+      var.x = fmaf(a, a, var.x); var.y = fmaf(bb, bb, var.y); var.z = fmaf(c, c, var.z); var.w = fmaf(e, e, var.w);
+    }
+    float* t = tile[buf];
+    t[(q * 4 + 0) * ROW + pl] = var.x * invV;
+    t[(q * 4 + 1) * ROW + pl] = var.y * invV;
+    t[(q * 4 + 2) * ROW + pl] = var.z * invV;
+    t[(q * 4 + 3) * ROW + pl] = var.w * invV;
+    __syncthreads();
+    // coalesced plane writes: C rows of PIX floats
+    float* obase = out + (((size_t)b * C) * D + d) * HW + (size_t)blockIdx.x * PIX;
+#pragma unroll
+    for (int i = 0; i < (C * PIX) / 256; ++i) {
+      int idx = i * 256 + threadIdx.x;
+      int c = idx / PIX, p = idx % PIX;
+      if (blockIdx.x * PIX + p < HW) __stcs(obase + (size_t)c * D * HW + p, t[c * ROW + p]);
+    }
+    // the other buffer is written next; its readers finished before the barrier above
+  }
+}
+
+template <int C, int V>
+static int launch_warp_variance(const float* feat, const float* proj, const float* range, int rh, int rw, int B, int Hs,
+                                int Ws, int D, int Ht, int Wt, int inv_depth, float* out, cudaStream_t st) {
+  constexpr int PIX = 256 / (C / 4);
+  int tiles = (Ht * Wt + PIX - 1) / PIX;
+  // depth chunk: enough CTAs for >= 4 waves of 148 SMs x 4 resident CTAs, but keep planes together for L1 reuse
+  int DCH = D;
+  while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
+  dim3 grid(tiles, (D + DCH - 1) / DCH, B);
+  warp_variance_kernel<C, V><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+  return cuda_check("gdb_warp_variance_fwd");
+}
+
+// ---------------------------------------------------------------------------
+// K2: depth regression -> confidence interval (depth_net.py:479-514)
+// ---------------------------------------------------------------------------
+__global__ void depth_range_kernel(const float* __restrict__ range, int rh, int rw, const float* __restrict__ prob,
+                                   int B, int D, int h, int w, float ci_scale, int inv_depth,
+                                   float* __restrict__ depth, float* __restrict__ ci, float* __restrict__ vol_range) {
+  int hw = h * w;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * hw) return;
+  int b = i / hw, p = i % hw;
+  int y = p / w, x = p % w;
+  int ry = rh == 1 ? 0 : y, rx = rw == 1 ? 0 : x;
+  float near_ = range[((size_t)(b * 2 + 0) * rh + ry) * rw + rx];
+  float far_ = range[((size_t)(b * 2 + 1) * rh + ry) * rw + rx];
+  const float* pp = prob + (size_t)b * D * hw + p;
+  float mean = 0.f;
+  for (int d = 0; d < D; ++d) mean = fadd(mean, fmul(pp[(size_t)d * hw], hypothesis(near_, far_, d, D, inv_depth)));
+  float var = 0.f;
+  for (int d = 0; d < D; ++d) {
+    float t = fsub(hypothesis(near_, far_, d, D, inv_depth), mean);
+    var = fadd(var, fmul(pp[(size_t)d * hw], fmul(t, t)));
+  }
+  float half = fmul(ci_scale, sqrtf(fmaxf(var, 1e-12f)));
+  float first = hypothesis(near_, far_, 0, D, inv_depth), last = hypothesis(near_, far_, D - 1, D, inv_depth);
+  float lo, hi, dep;
+  if (inv_depth) {
+    lo = fdiv(1.f, fminf(fadd(mean, half), first));
+    hi = fdiv(1.f, fmaxf(fsub(mean, half), last));
+    dep = fdiv(1.f, mean);
+  } else {
+    lo = fmaxf(fsub(mean, half), first);
+    hi = fminf(fadd(mean, half), last);
+    dep = mean;
+  }
+  depth[i] = dep;
+  ci[(size_t)(b * 2 + 0) * hw + p] = lo;
+  ci[(size_t)(b * 2 + 1) * hw + p] = hi;
+  if (vol_range) {
+    vol_range[(size_t)(b * 2 + 0) * hw + p] = first;
+    vol_range[(size_t)(b * 2 + 1) * hw + p] = last;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// planar -> channels-last
+// ---------------------------------------------------------------------------
+template <int CP>
+__global__ void planar_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t S, int64_t NS) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NS; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i / S, s = i % S;
+    const float* sp = src + n * C * S + s;
+    float v[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) v[c] = c < C ? __ldg(sp + (int64_t)c * S) : 0.f;
+    float4* dp = reinterpret_cast<float4*>(dst + i * CP);
+#pragma unroll
+    for (int c = 0; c < CP; c += 4) dp[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+}
+
+}  // namespace gdb
+
+using namespace gdb;
+
+extern "C" int gdb_planar_to_channels_last(const float* src, float* dst, int N, int C, int64_t S, int Cpad, void* stream) {
+  GDB_REQUIRE(src && dst && N > 0 && C > 0 && S > 0, GDB_E_BADARG, "gdb_planar_to_channels_last: bad argument");
+  GDB_REQUIRE(Cpad >= C && Cpad % 4 == 0, GDB_E_BADARG, "gdb_planar_to_channels_last: Cpad must be >= C and a multiple of 4");
+  GDB_REQUIRE(aligned16(dst), GDB_E_ALIGN, "gdb_planar_to_channels_last: dst not 16-byte aligned");
+  int64_t NS = (int64_t)N * S;
+  int blocks = (int)std::min<int64_t>((NS + 255) / 256, (int64_t)sm_count() * 16);
+  cudaStream_t st = as_stream(stream);
+  switch (Cpad) {
+    case 4: planar_to_cl_kernel<4><<<blocks, 256, 0, st>>>(src, dst, C, S, NS); break;
+    case 8: planar_to_cl_kernel<8><<<blocks, 256, 0, st>>>(src, dst, C, S, NS); break;
+    case 16: planar_to_cl_kernel<16><<<blocks, 256, 0, st>>>(src, dst, C, S, NS); break;
+    case 32: planar_to_cl_kernel<32><<<blocks, 256, 0, st>>>(src, dst, C, S, NS); break;
+    default: return fail(GDB_E_UNSUPPORTED, "gdb_planar_to_channels_last: Cpad=%d not in {4,8,16,32}", Cpad);
+  }
+  return cuda_check("gdb_planar_to_channels_last");
+}
+
+extern "C" int gdb_homography_mats(const float* src_exts, const float* src_ints, const float* tar_exts,
+                                   const float* tar_ints, float src_scale, float tar_scale, int B, int V, float* proj,
+                                   void* stream) {
+  GDB_REQUIRE(src_exts && src_ints && tar_exts && tar_ints && proj && B > 0 && V > 0, GDB_E_BADARG,
+              "gdb_homography_mats: bad argument");
+  homography_kernel<<<(B * V + 63) / 64, 64, 0, as_stream(stream)>>>(src_exts, src_ints, tar_exts, tar_ints, src_scale,
+                                                                    tar_scale, B, V, proj);
+  return cuda_check("gdb_homography_mats");
+}
+
+extern "C" int gdb_depth_values(const float* depth_range, int rh, int rw, int B, int D, int Ht, int Wt, int inv_depth,
+                                float* out, void* stream) {
+  GDB_REQUIRE(depth_range && out && B > 0 && D > 0 && Ht > 0 && Wt > 0, GDB_E_BADARG, "gdb_depth_values: bad argument");
+  GDB_REQUIRE((rh == 1 && rw == 1) || (rh == Ht && rw == Wt), GDB_E_BADARG,
+              "gdb_depth_values: depth_range must be 1x1 or %dx%d, got %dx%d", Ht, Wt, rh, rw);
+  size_t n = (size_t)B * D * Ht * Wt;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
+  depth_values_kernel<<<blocks, 256, 0, as_stream(stream)>>>(depth_range, rh, rw, B, D, Ht, Wt, inv_depth, out);
+  return cuda_check("gdb_depth_values");
+}
+
+extern "C" int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw,
+                                     int B, int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth,
+                                     float* variance, void* stream) {
+  GDB_REQUIRE(feat_cl && proj && depth_range && variance, GDB_E_BADARG, "gdb_warp_variance_fwd: null pointer");
+  GDB_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && D > 0 && Ht > 0 && Wt > 0, GDB_E_BADARG, "gdb_warp_variance_fwd: bad size");
+  GDB_REQUIRE((rh == 1 && rw == 1) || (rh == Ht && rw == Wt), GDB_E_BADARG,
+              "gdb_warp_variance_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", Ht, Wt, rh, rw);
+  GDB_REQUIRE(aligned16(feat_cl), GDB_E_ALIGN, "gdb_warp_variance_fwd: feat_cl not 16-byte aligned");
+  GDB_REQUIRE(B <= 65535, GDB_E_UNSUPPORTED, "gdb_warp_variance_fwd: B > 65535");
+  cudaStream_t st = as_stream(stream);
+#define GDB_WV(CC, VV) \
+  if (C == CC && V == VV) return launch_warp_variance<CC, VV>(feat_cl, proj, depth_range, rh, rw, B, Hs, Ws, D, Ht, Wt, inv_depth, variance, st);
+  GDB_WV(32, 2) GDB_WV(32, 3) GDB_WV(32, 4) GDB_WV(16, 2) GDB_WV(16, 3) GDB_WV(16, 4) GDB_WV(8, 2) GDB_WV(8, 3) GDB_WV(8, 4)
+#undef GDB_WV
+  return fail(GDB_E_UNSUPPORTED, "gdb_warp_variance_fwd: C=%d V=%d not instantiated (C in {8,16,32}, V in {2,3,4})", C, V);
+}
+
+extern "C" int gdb_depth_range_fwd(const float* depth_range, int rh, int rw, const float* prob, int B, int D, int h, int w,
+                                   float ci_scale, int inv_depth, float* depth, float* ci, float* vol_range, void* stream) {
+  GDB_REQUIRE(depth_range && prob && depth && ci && B > 0 && D > 0 && h > 0 && w > 0, GDB_E_BADARG,
+              "gdb_depth_range_fwd: bad argument");
+  GDB_REQUIRE((rh == 1 && rw == 1) || (rh == h && rw == w), GDB_E_BADARG,
+              "gdb_depth_range_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", h, w, rh, rw);
+  int n = B * h * w;
+  depth_range_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(depth_range, rh, rw, prob, B, D, h, w, ci_scale,
+                                                                    inv_depth, depth, ci, vol_range);
+  return cuda_check("gdb_depth_range_fwd");
+}

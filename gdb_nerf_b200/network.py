@@ -1,0 +1,171 @@
+"""Drop-in ``Network`` for the reference's plugin loader.
+
+The reference selects its model with ``cfg.network_module`` and instantiates
+``Network(cfg)`` from that file (networks/make_network.py:5-9); callers then use
+``forward(batch) -> (ret, mvs_depths, blend_rgbs)`` (networks/gdb_nerf/network.py:93-189).
+This class keeps that contract - constructor keys, batch-dict layout, return
+structure and ``state_dict`` names/shapes (strict checkpoint loading) - and runs
+the star-marked path of SURVEY.md section 8 on hand-written sm_100a kernels:
+
+    FPN (cuDNN) -> [K1 warp+variance -> CostReg (cuDNN) -> K2 depth range] x stages
+                -> source preparation (texture pyramid, RGBA) -> K3 fused render
+                -> decoder (cuDNN) -> output assembly kernel
+
+There is no CPU path: ``forward`` needs CUDA tensors and the built C-ABI library.
+"""
+from __future__ import annotations
+
+from operator import itemgetter
+from types import SimpleNamespace
+from typing import Any, Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet
+from .nerf import CoarseNeRF, NeRF
+from .sampler import BundleSampler
+
+
+def _as_tuple(x):
+    return tuple(x) if isinstance(x, (list, tuple)) else (x,)
+
+
+class DepthNet(nn.Module):
+    """Cascade cost-volume depth estimator (networks/gdb_nerf/depth_net.py:10-198):
+    owns the cost-regularisation CNNs; warp/variance and depth regression are kernels."""
+
+    def __init__(self, config: SimpleNamespace) -> None:
+        super().__init__()
+        base = config.fpn.base_channels
+        self.vol_levels = list(config.mvs.vol_levels)
+        self.vol_scales = list(config.mvs.vol_scales)
+        self.num_stages = len(self.vol_levels)
+        self.feat_scales = _as_tuple(itemgetter(*self.vol_levels)(config.fpn.feat_scales))
+        self.feat_dims = _as_tuple(itemgetter(*self.vol_levels)(config.fpn.feat_dims))
+        self.ci_scales = list(config.mvs.ci_scales)
+        self.num_depth = list(config.mvs.num_depth)
+        self.inv_depth = list(config.mvs.inv_depth)
+        voxel_dim = config.mvs.voxel_dim
+        # NB: the reference indexes feat_dims (already gathered by level) with vol_levels again (depth_net.py:32,36)
+        self.cost_regs = nn.ModuleList([CostRegNetSmall(self.feat_dims[self.vol_levels[0]], voxel_dim, base)])
+        for i in range(1, self.num_stages):
+            self.cost_regs.append(CostRegNet(self.feat_dims[self.vol_levels[i]], voxel_dim, base))
+        # coarse NeRFs exist in every reference checkpoint (module is in training mode at construction, :40-47)
+        self.num_samples = list(config.mvs.num_samples)
+        self.nerfs = nn.ModuleList([
+            CoarseNeRF(config.nerf.nerf_hidden_dims, voxel_dim, self.feat_dims[i], config.nerf.viewdir_agg)
+            for i in range(self.num_stages - 1)])
+
+    def forward(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far):
+        B, V, _, H, W = src_images.shape
+        mvs_depths: List[torch.Tensor] = []
+        range_list: List[torch.Tensor] = []
+        vol_list: List[torch.Tensor] = []
+        volume_list: List[torch.Tensor] = []
+        depth_range = near_far[..., None, None].contiguous()                  # (B,2,1,1)
+        for s in range(self.num_stages):
+            feats = ms_feats[self.vol_levels[s]]                              # (B,V,C,Hs,Ws)
+            Hi, Wi = int(H * self.vol_scales[s]), int(W * self.vol_scales[s])
+            proj = ops.homography_mats(src_exts, src_ints, tar_exts, tar_ints, self.feat_scales[s], self.vol_scales[s])
+            feat_cl = ops.to_channels_last(feats.flatten(0, 1)).unflatten(0, (B, V))
+            variance = ops.warp_variance(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s])
+            volume, prob = self.cost_regs[s](variance)
+            depth, ci, vol_range = ops.depth_range_from_prob(depth_range, prob, self.ci_scales[s], self.inv_depth[s])
+            mvs_depths.append(depth.squeeze(1))
+            range_list.append(ci)
+            vol_list.append(vol_range)
+            volume_list.append(volume)
+            depth_range = ci
+            if s < self.num_stages - 1:
+                up = self.vol_scales[s + 1] / self.vol_scales[s]
+                depth_range = F.interpolate(ci, scale_factor=up, mode="bilinear", align_corners=False)
+        return mvs_depths, range_list, vol_list, volume_list, []
+
+
+class Network(nn.Module):
+    def __init__(self, config: SimpleNamespace) -> None:
+        super().__init__()
+        self.feature_net = FeatureNet(config.fpn.base_channels, config.fpn.feat_dims)
+        self.voxel_dim = config.mvs.voxel_dim
+        self.depth_net = DepthNet(config)
+
+        self.max_num_samples = config.nerf.max_num_samples
+        self.b_size = config.nerf.bundle_size
+        if self.b_size <= 0 or (self.b_size & (self.b_size - 1)) != 0:
+            raise ValueError('`Bundle size` must be a power of 2.')
+        self.inv_depth = config.mvs.inv_depth[-1]
+        self.is_adaptive = config.nerf.is_adaptive
+        self.sampler = BundleSampler(config.nerf.global_num_depth, config.nerf.max_mipmap_level)
+
+        self.feat_level = 0
+        while self.feat_level < len(config.fpn.feat_scales) and config.fpn.feat_scales[self.feat_level] < 1. / self.b_size:
+            self.feat_level += 1
+        feat_dim = config.fpn.feat_dims[self.feat_level]
+        self.nerf_hidden_dims = config.nerf.nerf_hidden_dims
+        self.viewdir_agg = config.nerf.viewdir_agg
+        self.render_scale = 1.
+        self.nerf = NeRF(self.nerf_hidden_dims, feat_dim, self.voxel_dim, self.viewdir_agg)
+
+        self.dec_layers = config.nerf.dec_layers
+        self.upsampler = Decoder(feat_dim + 3 + self.voxel_dim, 3, num_feats=64, num_layers=self.dec_layers, upscale_factor=self.b_size)
+        self.reweighting = config.nerf.reweighting
+        self._fpn_levels = max(max(self.depth_net.vol_levels), self.feat_level) + 1
+
+    def forward(self, batch: Dict[str, Any]) -> Tuple[Dict[str, torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
+        if self.training:
+            raise NotImplementedError(
+                "gdb_nerf_b200.Network: the training path (coarse NeRF + backward kernels, SURVEY.md section 8 row a14/K4) "
+                "is not built yet; call .eval()")
+        src_views, tar_views = batch['src_views'], batch['tar_views']
+        near_far = batch['near_far']
+        src_images = src_views['rgb']
+        if not src_images.is_cuda:
+            raise ops._lib.GdbError("gdb_nerf_b200.Network.forward needs CUDA tensors (no CPU fallback exists)")
+        B, V, _, H, W = src_images.shape
+        src_exts = src_views['extrinsics']
+        src_ints = src_views['intrinsics'].clone()
+        tar_exts = tar_views['extrinsics']
+        tar_ints = tar_views['intrinsics'].clone()
+
+        if 'render_scale' in batch:
+            rs = batch['render_scale']
+            self.render_scale = rs[0].item() if torch.is_tensor(rs) else float(rs[0] if isinstance(rs, (list, tuple)) else rs)
+        if self.render_scale != 1.:
+            src_images = F.interpolate(src_images.flatten(0, 1), scale_factor=self.render_scale, mode='bilinear',
+                                       align_corners=False).unflatten(0, (B, V))
+            H, W = src_images.shape[-2:]
+            src_ints[..., :2, :] *= self.render_scale
+            tar_ints[:, :2, :] *= self.render_scale
+
+        ms_feats = [f.unflatten(0, (B, V)) for f in self.feature_net(src_images.flatten(0, 1), levels=self._fpn_levels)]
+        mvs_depths, range_list, vol_list, volume_list, blend_rgbs = self.depth_net(
+            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far)
+        depth_range, vol_range, feat_volume, mvs_depth = range_list[-1], vol_list[-1], volume_list[-1], mvs_depths[-1]
+
+        b = self.b_size
+        Hb, Wb = H // b, W // b
+        if depth_range.shape[2:] != (Hb, Wb):
+            depth_range = F.interpolate(depth_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
+            vol_range = F.interpolate(vol_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
+            mvs_depth = F.interpolate(mvs_depth.unsqueeze(1), size=(Hb, Wb), mode='nearest').squeeze(1)
+        if feat_volume.shape[-2:] != (Hb, Wb):
+            raise ValueError("feature volume resolution must equal the bundle map (true for every shipped recipe)")
+
+        img_feat = ms_feats[self.feat_level]
+        if img_feat.shape[-2:] != (Hb, Wb):
+            img_feat = F.interpolate(img_feat.flatten(0, 1), size=(Hb, Wb), mode='bilinear', align_corners=False).unflatten(0, (B, V))
+
+        self.sampler.build_rays(tar_exts, tar_ints, (H, W), near_far[:, 0], near_far[:, 1])
+        cam = self.sampler.camera_block(src_exts, src_ints, b, self.inv_depth)
+        sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
+        vol_cl = ops.to_channels_last(feat_volume, 8)
+        out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
+                               self.max_num_samples, self.inv_depth, self.is_adaptive)
+
+        rgb_c = self.upsampler(out['feat'][:, 3 * b * b:])
+        rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['feat'], rgb_c, out['depth'], out['opacity'], b, self.reweighting)
+        ret = {'rgb': rgb, 'nerf_depth': nerf_depth, 'mvs_depth': mvs_depth, 'opacity': nerf_opacity}
+        return ret, mvs_depths, blend_rgbs

@@ -1,0 +1,264 @@
+"""Host-side operators: thin wrappers that hand PyTorch-owned device memory and
+the current CUDA stream to the C-ABI kernels.  PyTorch is plumbing here
+(allocator + stream); all arithmetic of the path happens in the kernels.
+
+Every operator refuses CPU tensors: there is no fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .mlp_pack import pack_mlp  # noqa: F401  (re-export)
+
+Tensor = torch.Tensor
+CAM_HEAD = 32
+CAM_VIEW = 32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.GdbError("gdb_nerf_b200 operators need CUDA tensors (no CPU fallback exists)")
+
+
+def _f32(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def padded_feat(feat_dim: int) -> int:
+    return (feat_dim + 3 + 3) & ~3
+
+
+# ------------------------------------------------------------------ layout --
+def to_channels_last(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
+    """(N, C, *spatial) planar -> (N, *spatial, Cpad) channels-last."""
+    _dev(x)
+    x = _f32(x)
+    N, Cc = x.shape[:2]
+    spatial = x.shape[2:]
+    S = 1
+    for s in spatial:
+        S *= s
+    c_pad = c_pad or ((Cc + 3) & ~3)
+    out = torch.empty((N, *spatial, c_pad), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_planar_to_channels_last(x.data_ptr(), out.data_ptr(), N, Cc, S, c_pad, _stream()), "gdb_planar_to_channels_last")
+    return out
+
+
+# ------------------------------------------------------------- cost volume --
+def homography_mats(src_exts: Tensor, src_ints: Tensor, tar_exts: Tensor, tar_ints: Tensor, src_scale: float, tar_scale: float) -> Tensor:
+    _dev(src_exts, src_ints, tar_exts, tar_ints)
+    B, V = src_exts.shape[:2]
+    proj = torch.empty((B, V, 3, 4), device=src_exts.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_homography_mats(_f32(src_exts).data_ptr(), _f32(src_ints).data_ptr(), _f32(tar_exts).data_ptr(),
+                                       _f32(tar_ints).data_ptr(), float(src_scale), float(tar_scale), B, V, proj.data_ptr(), _stream()),
+               "gdb_homography_mats")
+    return proj
+
+
+def depth_values(depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_depth: bool) -> Tensor:
+    _dev(depth_range)
+    depth_range = _f32(depth_range)
+    B, _, rh, rw = depth_range.shape
+    out = torch.empty((B, num_depth, Ht, Wt), device=depth_range.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_depth_values(depth_range.data_ptr(), rh, rw, B, num_depth, Ht, Wt, int(inv_depth), out.data_ptr(), _stream()),
+               "gdb_depth_values")
+    return out
+
+
+def warp_variance(feat_cl: Tensor, proj: Tensor, depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_depth: bool) -> Tensor:
+    """feat_cl (B,V,Hs,Ws,C) channels-last -> variance volume (B,C,D,Ht,Wt)."""
+    _dev(feat_cl, proj, depth_range)
+    feat_cl, proj, depth_range = _f32(feat_cl), _f32(proj), _f32(depth_range)
+    B, V, Hs, Ws, Cc = feat_cl.shape
+    _, _, rh, rw = depth_range.shape
+    out = torch.empty((B, Cc, num_depth, Ht, Wt), device=feat_cl.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_warp_variance_fwd(feat_cl.data_ptr(), proj.data_ptr(), depth_range.data_ptr(), rh, rw, B, V, Cc, Hs, Ws,
+                                         num_depth, Ht, Wt, int(inv_depth), out.data_ptr(), _stream()), "gdb_warp_variance_fwd")
+    return out
+
+
+def depth_range_from_prob(depth_range: Tensor, prob: Tensor, ci_scale: float, inv_depth: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w)."""
+    _dev(depth_range, prob)
+    depth_range, prob = _f32(depth_range), _f32(prob)
+    B, D, h, w = prob.shape
+    _, _, rh, rw = depth_range.shape
+    depth = torch.empty((B, 1, h, w), device=prob.device, dtype=torch.float32)
+    ci = torch.empty((B, 2, h, w), device=prob.device, dtype=torch.float32)
+    vol = torch.empty((B, 2, h, w), device=prob.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_depth_range_fwd(depth_range.data_ptr(), rh, rw, prob.data_ptr(), B, D, h, w, float(ci_scale), int(inv_depth),
+                                       depth.data_ptr(), ci.data_ptr(), vol.data_ptr(), _stream()), "gdb_depth_range_fwd")
+    return depth, ci, vol
+
+
+# ---------------------------------------------------------------- sampling --
+def camera_block(tar_exts: Tensor, tar_ints: Tensor, src_exts: Tensor, src_ints: Tensor, near_far: Tensor, bundle_size: int,
+                 global_num_depth: int, inv_depth: bool) -> Tensor:
+    _dev(tar_exts, tar_ints, src_exts, src_ints, near_far)
+    B, V = src_exts.shape[:2]
+    cam = torch.empty((B, CAM_HEAD + CAM_VIEW * V), device=tar_exts.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_camera_block(_f32(tar_exts).data_ptr(), _f32(tar_ints).data_ptr(), _f32(src_exts).data_ptr(),
+                                    _f32(src_ints).data_ptr(), _f32(near_far).data_ptr(), B, V, bundle_size, global_num_depth,
+                                    int(inv_depth), cam.data_ptr(), _stream()), "gdb_camera_block")
+    return cam
+
+
+class SampleList(NamedTuple):
+    counts: Tensor       # (NB,) int32
+    offsets: Tensor      # (NB+1,) int32, offsets[NB] = S
+    total: int           # S (host value: one read-back)
+    indices: Optional[Tensor]
+    z_vals: Optional[Tensor]
+    uvd: Optional[Tensor]
+    ball_radii: Optional[Tensor]
+    rays_xyz: Optional[Tensor]
+
+
+def bundle_counts(depth_range: Tensor, cam: Tensor, max_samples: int, inv_depth: bool, adaptive: bool) -> Tuple[Tensor, Tensor]:
+    """-> counts (NB,) int32 and offsets (NB+1,) int32 (exclusive scan), no host sync."""
+    _dev(depth_range, cam)
+    depth_range = _f32(depth_range)
+    B, _, Hb, Wb = depth_range.shape
+    NB = B * Hb * Wb
+    counts = torch.empty(NB, device=cam.device, dtype=torch.int32)
+    offsets = torch.empty(NB + 1, device=cam.device, dtype=torch.int32)
+    block_sums = torch.empty((NB + 4095) // 4096, device=cam.device, dtype=torch.int32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_bundle_count(depth_range.data_ptr(), cam.data_ptr(), cam.shape[1], B, Hb, Wb, max_samples, int(inv_depth),
+                                    int(adaptive), counts.data_ptr(), block_sums.data_ptr(), _stream()), "gdb_bundle_count")
+    _lib.check(lib.gdb_bundle_scan(counts.data_ptr(), block_sums.data_ptr(), NB, offsets.data_ptr(), _stream()), "gdb_bundle_scan")
+    return counts, offsets
+
+
+def sample_bundles(depth_range: Tensor, vol_range: Tensor, cam: Tensor, bundle_size: int, max_samples: int, inv_depth: bool,
+                   adaptive: bool, want_rays: bool = True) -> SampleList:
+    """The reference's packed sample list (bundle_sampler.py:193-265).  Reads S
+    back to the host once to size the outputs (the fused render never needs it)."""
+    _dev(depth_range, vol_range, cam)
+    depth_range, vol_range = _f32(depth_range), _f32(vol_range)
+    B, _, Hb, Wb = depth_range.shape
+    counts, offsets = bundle_counts(depth_range, cam, max_samples, inv_depth, adaptive)
+    S = int(offsets[-1].item())
+    dev = cam.device
+    bb = bundle_size * bundle_size
+    indices = torch.empty(S, device=dev, dtype=torch.int64)
+    z_vals = torch.empty(S, device=dev, dtype=torch.float32)
+    uvd = torch.empty((S, 3), device=dev, dtype=torch.float32)
+    ball = torch.empty(S, device=dev, dtype=torch.float32)
+    rays = torch.empty((S, 3, bb), device=dev, dtype=torch.float32) if want_rays else None
+    lib = _lib.load()
+    _lib.check(lib.gdb_bundle_emit(depth_range.data_ptr(), vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], counts.data_ptr(),
+                                   offsets.data_ptr(), B, Hb, Wb, bundle_size, int(inv_depth), indices.data_ptr(), z_vals.data_ptr(),
+                                   uvd.data_ptr(), ball.data_ptr(), _p(rays), _stream()), "gdb_bundle_emit")
+    return SampleList(counts, offsets, S, indices, z_vals, uvd, ball, rays)
+
+
+# ----------------------------------------------------------------- sources --
+class Sources(NamedTuple):
+    tex: Tensor      # flat mip chain (floats)
+    rgba: Tensor     # (B*V, H, W, 4)
+    feat_dim: int
+    max_mip: int
+
+
+def prepare_sources(feat: Tensor, images: Tensor, bundle_size: int, max_mip: int) -> Sources:
+    """feat (B,V,Cf,Hb,Wb) planar FPN level, images (B,V,3,H,W)."""
+    _dev(feat, images)
+    feat, images = _f32(feat), _f32(images)
+    B, V, Cf, Hb, Wb = feat.shape
+    H, W = images.shape[-2:]
+    if (H, W) != (Hb * bundle_size, Wb * bundle_size):
+        raise ValueError(f"feature map {Hb}x{Wb} x bundle {bundle_size} != image {H}x{W}")
+    lib = _lib.load()
+    n = lib.gdb_texture_floats(B * V, Hb, Wb, Cf, max_mip)
+    tex = torch.empty(n, device=feat.device, dtype=torch.float32)
+    rgba = torch.empty((B * V, H, W, 4), device=feat.device, dtype=torch.float32)
+    _lib.check(lib.gdb_prepare_sources(feat.data_ptr(), images.data_ptr(), B * V, Cf, Hb, Wb, bundle_size, max_mip, tex.data_ptr(),
+                                       rgba.data_ptr(), _stream()), "gdb_prepare_sources")
+    return Sources(tex, rgba, Cf, max_mip)
+
+
+def texture_level(src: Sources, BV: int, Hb: int, Wb: int, level: int) -> Tensor:
+    """View of one mip level as (BV, h, w, FP)."""
+    FP = padded_feat(src.feat_dim)
+    off = 0
+    for k in range(level):
+        off += BV * (Hb >> k) * (Wb >> k) * FP
+    h, w = Hb >> level, Wb >> level
+    return src.tex[off: off + BV * h * w * FP].view(BV, h, w, FP)
+
+
+# ------------------------------------------------------------------ render --
+def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: Tensor, cam: Tensor, mlp: Tensor,
+                 B: int, V: int, H: int, W: int, bundle_size: int, max_samples: int, inv_depth: bool, adaptive: bool,
+                 taps: Optional[SampleList] = None, precision: int = 0) -> Dict[str, Tensor]:
+    """-> {'feat' (B,CT,Hb,Wb), 'depth' (B,Hb,Wb), 'opacity' (B,Hb,Wb)} and, when
+    ``taps`` (a SampleList) is given, the reference's packed intermediates."""
+    _dev(src.tex, src.rgba, vol_cl, depth_range, vol_range, cam, mlp)
+    depth_range, vol_range, vol_cl = _f32(depth_range), _f32(vol_range), _f32(vol_cl)
+    Hb, Wb = H // bundle_size, W // bundle_size
+    D = vol_cl.shape[1]
+    bb = bundle_size * bundle_size
+    F = src.feat_dim + 3
+    CT = 3 * bb + F + 8
+    dev = cam.device
+    out_feat = torch.empty((B, CT, Hb, Wb), device=dev, dtype=torch.float32)
+    out_depth = torch.empty((B, Hb, Wb), device=dev, dtype=torch.float32)
+    out_opac = torch.empty((B, Hb, Wb), device=dev, dtype=torch.float32)
+    res = {"feat": out_feat, "depth": out_depth, "opacity": out_opac}
+    tp = None
+    if taps is not None:
+        S = taps.total
+        res["rgbs_feat_dir"] = torch.zeros((V, S, 3 * bb + F + 4), device=dev, dtype=torch.float32)
+        res["vox_feat"] = torch.zeros((S, 8), device=dev, dtype=torch.float32)
+        res["sigma"] = torch.zeros(S, device=dev, dtype=torch.float32)
+        res["sample_feat"] = torch.zeros((S, CT), device=dev, dtype=torch.float32)
+        res["weights"] = torch.zeros(S, device=dev, dtype=torch.float32)
+        tp = _lib.RenderTaps(taps.offsets.data_ptr(), S, res["rgbs_feat_dir"].data_ptr(), res["vox_feat"].data_ptr(),
+                             res["sigma"].data_ptr(), res["sample_feat"].data_ptr(), res["weights"].data_ptr())
+    lib = _lib.load()
+    _lib.check(lib.gdb_render_fused_fwd(src.rgba.data_ptr(), src.tex.data_ptr(), vol_cl.data_ptr(), depth_range.data_ptr(),
+                                        vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], mlp.data_ptr(), B, V, H, W, bundle_size,
+                                        src.feat_dim, D, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
+                                        out_feat.data_ptr(), out_depth.data_ptr(), out_opac.data_ptr(),
+                                        C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
+    return res
+
+
+def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bundle_size: int, reweighting: bool):
+    """rgb = dec + pixel_shuffle(feat[:, :3b^2]) (network.py:175-182)."""
+    _dev(feat, dec, bdepth, bopac)
+    feat, dec, bdepth, bopac = _f32(feat), _f32(dec), _f32(bdepth), _f32(bopac)
+    B, CT, Hb, Wb = feat.shape
+    H, W = Hb * bundle_size, Wb * bundle_size
+    rgb = torch.empty((B, 3, H, W), device=feat.device, dtype=torch.float32)
+    depth = torch.empty((B, H, W), device=feat.device, dtype=torch.float32)
+    opac = torch.empty((B, H, W), device=feat.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_assemble_output(feat.data_ptr(), CT, dec.data_ptr(), bdepth.data_ptr(), bopac.data_ptr(), B, Hb, Wb, bundle_size,
+                                       int(reweighting), rgb.data_ptr(), depth.data_ptr(), opac.data_ptr(), _stream()),
+               "gdb_assemble_output")
+    return rgb, depth, opac

@@ -1,0 +1,159 @@
+/*
+ * gdb_nerf_b200 - C ABI of the B200-native GDB-NeRF rendering hot path.
+ *
+ * The reference (KLMAV-CUC/GDB-NeRF) is pure Python/PyTorch and has no FFI of
+ * its own; each entry point below replaces a Python function of the reference
+ * (cited as file:line into the reference tree) and is what a ctypes binding in
+ * networks/gdb_nerf/*.py would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; tensors are dense,
+ *     row-major, fp32 unless stated; indices are int64 where the reference's are.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *     on it: no allocation, no synchronisation, no host read-back.
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     GDB_E_* argument error.  gdb_last_error_string() describes the last
+ *     failure of the calling thread.
+ *   - "channels-last" (CL) means the channel index is innermost.
+ */
+#ifndef GDB_NERF_B200_H
+#define GDB_NERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDB_ABI_VERSION 1
+
+#define GDB_E_BADARG  (-1)   /* null pointer / non-positive size            */
+#define GDB_E_UNSUPPORTED (-2) /* parameter combination not instantiated     */
+#define GDB_E_ALIGN   (-3)   /* pointer not 16-byte aligned                  */
+
+#define GDB_MAX_VIEWS 4
+
+int gdb_abi_version(void);
+const char* gdb_last_error_string(void);
+
+/* number of floats in the packed MLP parameter block for a given 2-D feature
+ * width (feat_dim = 16 or 32) - layout documented in DESIGN.md / mlp_pack.py */
+int gdb_mlp_param_floats(int feat_dim);
+
+/* ---------------------------------------------------------------- layout -- */
+/* (N, C, S) planar -> (N, S, Cpad) channels-last, zero-filled pad channels.
+ * Used for FPN feature maps (C=16/32) and the cost-regularised feature volume
+ * (C=8).  C <= Cpad, Cpad % 4 == 0.                                          */
+int gdb_planar_to_channels_last(const float* src, float* dst, int N, int C, int64_t S, int Cpad, void* stream);
+
+/* --------------------------------------------------------- cost volume ---- */
+/* Homography matrices, replaces depth_net.py:453-457.
+ * src_exts (B,V,4,4) src_ints (B,V,3,3) tar_exts (B,4,4) tar_ints (B,3,3);
+ * intrinsic rows 0-1 are scaled by src_scale / tar_scale first
+ * (depth_net.py:159-162).  out proj (B,V,3,4).                               */
+int gdb_homography_mats(const float* src_exts, const float* src_ints, const float* tar_exts, const float* tar_ints,
+                        float src_scale, float tar_scale, int B, int V, float* proj, void* stream);
+
+/* Depth hypotheses, replaces get_depth_values depth_net.py:399-421.
+ * depth_range (B,2,rh,rw) with (rh,rw) == (1,1) or (Ht,Wt) -> out (B,D,Ht,Wt) */
+int gdb_depth_values(const float* depth_range, int rh, int rw, int B, int D, int Ht, int Wt, int inv_depth,
+                     float* out, void* stream);
+
+/* Homography warp + population variance over views, replaces
+ * build_feature_volume depth_net.py:424-476 fused with get_depth_values.
+ * feat_cl (B,V,Hs,Ws,C) channels-last, C in {8,16,32}; proj (B,V,3,4);
+ * depth_range as above -> variance (B,C,D,Ht,Wt) (NCDHW, what conv3d takes). */
+int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw,
+                          int B, int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth,
+                          float* variance, void* stream);
+
+/* Depth regression -> confidence interval, replaces depth_regression
+ * depth_net.py:479-514 (+ vol_range = depth_values[:, [0,-1]], :179).
+ * prob (B,D,h,w) -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w).      */
+int gdb_depth_range_fwd(const float* depth_range, int rh, int rw, const float* prob, int B, int D, int h, int w,
+                        float ci_scale, int inv_depth, float* depth, float* ci, float* vol_range, void* stream);
+
+/* --------------------------------------------------------- sampling ------- */
+/* Camera block for the sampling / render kernels: replaces
+ * BundleSampler.build_rays bundle_sampler.py:30-74 and the per-view constants
+ * of encode :303-313.  cam: (B, 32 + 32*V) floats (layout in DESIGN.md).     */
+int gdb_camera_block(const float* tar_exts, const float* tar_ints, const float* src_exts, const float* src_ints,
+                     const float* near_far, int B, int V, int bundle_size, int global_num_depth, int inv_depth,
+                     float* cam, void* stream);
+
+/* Samples per bundle, replaces bundle_sampler.py:152,179.
+ * depth_range (B,2,Hb,Wb); counts int32 (NB); block_sums int32
+ * (ceil(NB/4096)) partial sums for the scan.                                  */
+int gdb_bundle_count(const float* depth_range, const float* cam, int cam_stride, int B, int Hb, int Wb,
+                     int max_samples, int inv_depth, int adaptive, int32_t* counts, int32_t* block_sums, void* stream);
+
+/* Exclusive scan of counts -> offsets int32 (NB+1); offsets[NB] = S.
+ * The host may read offsets[NB] back once to size the packed outputs, or
+ * use the NB*max_samples upper bound and stay sync-free.                      */
+int gdb_bundle_scan(const int32_t* counts, int32_t* block_sums, int NB, int32_t* offsets, void* stream);
+
+/* Packed sample list, replaces BundleSampler.sample bundle_sampler.py:193-265.
+ * Any output pointer may be null.  indices int64 (S); z_vals (S); uvd (S,3);
+ * ball_radii (S); rays_xyz (S,3,b*b).                                         */
+int gdb_bundle_emit(const float* depth_range, const float* vol_range, const float* cam, int cam_stride,
+                    const int32_t* counts, const int32_t* offsets, int B, int Hb, int Wb, int bundle_size,
+                    int inv_depth, int64_t* indices, float* z_vals, float* uvd, float* ball_radii, float* rays_xyz,
+                    void* stream);
+
+/* --------------------------------------------------------- sources -------- */
+/* Gather sources for the render kernel, replaces network.py:159-164 and the
+ * mip construction nvdiffrast.torch.texture does internally
+ * (bundle_sampler.py:355-359): feature+rgb texture with its mip chain
+ * (channels-last, F=Cf+3 padded to FP=roundup4(F)) and RGBA-interleaved
+ * full-resolution images.
+ * feat (B,V,Cf,Hb,Wb) planar; images (B,V,3,H,W) planar, H=Hb*b, W=Wb*b.
+ * tex: levels 0..L concatenated, level k is (B*V, Hb>>k, Wb>>k, FP).
+ * rgba (B*V,H,W,4).  Hb, Wb divisible by 2^L.                                 */
+int64_t gdb_texture_floats(int BV, int Hb, int Wb, int feat_dim, int max_mip_level);
+int gdb_prepare_sources(const float* feat, const float* images, int BV, int Cf, int Hb, int Wb, int bundle_size,
+                        int max_mip_level, float* tex, float* rgba, void* stream);
+
+/* --------------------------------------------------------- render --------- */
+/* Fused per-bundle render, replaces BundleSampler.sample/encode
+ * (bundle_sampler.py:193-371), NeRF.forward (nerf.py:84-115),
+ * render_weight_from_density / accumulate_value_along_rays
+ * (utils.py:19-43,88-121) and Network.render_bundles (network.py:54-91).
+ *
+ * vol_cl (B,D,Hb,Wb,8) channels-last feature volume; tex/rgba from
+ * gdb_prepare_sources; depth_range, vol_range (B,2,Hb,Wb); mlp: packed
+ * parameter block.
+ * out_feat (B, 3b^2+F+8, Hb, Wb) planar; out_depth, out_opacity (B,Hb,Wb).
+ *
+ * Optional taps (any may be null; offsets required if any is non-null): the
+ * reference's intermediates in its packed sample order -
+ * rgbs_feat_dir (V,S,3b^2+F+4), vox_feat (S,8), sigma (S), feat (S,3b^2+F+8),
+ * weights (S).  S_total is the row count of those tensors.                    */
+typedef struct gdb_render_taps {
+  const int32_t* offsets;
+  int64_t S_total;
+  float* rgbs_feat_dir;
+  float* vox_feat;
+  float* sigma;
+  float* feat;
+  float* weights;
+} gdb_render_taps;
+
+int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
+                         const float* vol_range, const float* cam, int cam_stride, const float* mlp,
+                         int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int max_samples,
+                         int max_mip_level, int inv_depth, int adaptive, int precision /* 0 = fp32 */,
+                         float* out_feat, float* out_depth, float* out_opacity, const gdb_render_taps* taps,
+                         void* stream);
+
+/* Output assembly, replaces network.py:175-182 minus the decoder CNN:
+ * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
+ * and the bilinear xb up-sampling of depth and opacity.
+ * feat (B,Ctot,Hb,Wb), dec (B,3,H,W) -> rgb (B,3,H,W), depth/opacity (B,H,W). */
+int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
+                        int B, int Hb, int Wb, int bundle_size, int reweighting,
+                        float* rgb, float* depth, float* opacity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDB_NERF_B200_H */

@@ -1,0 +1,246 @@
+"""Parity of the CUDA kernels (called through the C ABI) against the CPU oracle
+and the golden vectors dumped from the reference.  Integer outputs bit-exact;
+floating point within the tolerances of BASELINE.json's north star, written in
+each assertion (fp32: 1e-4 absolute on rgb/depth-like quantities in normalised
+units; white-noise inputs get the reference's own fp32 noise floor instead)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASE_SPECS, load_golden
+from gdb_nerf_b200 import ops
+from gdb_nerf_b200.config import make_cfg
+from oracle import gdb_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _md(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def _cfg(g):
+    return make_cfg(CASE_SPECS[g.name]["recipe"])
+
+
+def _scales(cfg, s):
+    fs = cfg.fpn.feat_scales[cfg.mvs.vol_levels[s]]
+    return fs, cfg.mvs.vol_scales[s]
+
+
+# ------------------------------------------------------------------ K1 / a1 / a2
+def test_homography_and_depth_values(golden):
+    cfg = _cfg(golden)
+    se, si = golden.t("in_src_exts"), golden.t("in_src_ints")
+    te, ti = golden.t("in_tar_exts"), golden.t("in_tar_ints")
+    for s in range(2):
+        fs, vs = _scales(cfg, s)
+        proj = ops.homography_mats(se.to(DEV), si.to(DEV), te.to(DEV), ti.to(DEV), fs, vs)
+        ref = O.homography_matrices(se.double(), golden.t(f"s{s}_src_ints").double(), te.double(), golden.t(f"s{s}_tar_ints").double())
+        assert _md(proj, ref) <= 2e-6 * float(ref.abs().max())
+        rng = golden.t(f"s{s}_range_in")
+        dv_ref = golden.t(f"s{s}_depth_values")
+        Ht, Wt = dv_ref.shape[-2:]
+        dv = ops.depth_values(rng.to(DEV), cfg.mvs.num_depth[s], Ht, Wt, cfg.mvs.inv_depth[s])
+        # IEEE-exact restatement of linspace + affine map: identical to the CPU oracle bit for bit
+        want = O.depth_hypotheses(rng, cfg.mvs.num_depth[s], cfg.mvs.inv_depth[s]).expand_as(dv_ref)
+        assert torch.equal(dv.cpu(), want.contiguous())
+        assert _md(dv, dv_ref) <= 1e-6 * float(dv_ref.abs().max())
+
+
+def test_warp_variance(golden):
+    cfg = _cfg(golden)
+    se, te = golden.t("in_src_exts"), golden.t("in_tar_exts")
+    for s in range(2):
+        feat = golden.t(f"s{s}_src_feat")                                      # (B,V,C,Hs,Ws)
+        B, V = feat.shape[:2]
+        proj = O.homography_matrices(se, golden.t(f"s{s}_src_ints"), te, golden.t(f"s{s}_tar_ints"))
+        rng = golden.t(f"s{s}_range_in")
+        ref = golden.t(f"s{s}_variance")
+        D, Ht, Wt = ref.shape[2:]
+        feat_cl = ops.to_channels_last(feat.flatten(0, 1).to(DEV)).unflatten(0, (B, V))
+        assert torch.equal(feat_cl.cpu(), feat.permute(0, 1, 3, 4, 2).contiguous())
+        var = ops.warp_variance(feat_cl, proj.to(DEV), rng.to(DEV), D, Ht, Wt, cfg.mvs.inv_depth[s])
+        assert var.shape == ref.shape
+        truth = O.warp_variance(feat.double(), proj.double(), O.depth_hypotheses(rng.double(), D, cfg.mvs.inv_depth[s]).expand(B, D, Ht, Wt),
+                                cfg.mvs.inv_depth[s])
+        scale = max(1.0, float(ref.abs().max()))
+        ref_noise = _md(ref, truth)                                             # the reference's own fp32 error
+        assert _md(var, truth) <= max(1e-4 * scale, 2.0 * ref_noise)
+        assert _md(var, ref) <= 5e-4 * scale
+
+
+# ------------------------------------------------------------------ K2 / a3
+def test_depth_range(golden):
+    cfg = _cfg(golden)
+    for s in range(2):
+        rng, prob = golden.t(f"s{s}_range_in"), golden.t(f"s{s}_prob")
+        depth, ci, vol = ops.depth_range_from_prob(rng.to(DEV), prob.to(DEV), cfg.mvs.ci_scales[s], cfg.mvs.inv_depth[s])
+        scale = float(golden.t(f"s{s}_depth").abs().max())
+        assert _md(depth, golden.t(f"s{s}_depth")) <= 2e-5 * scale
+        assert _md(ci, golden.t(f"s{s}_ci")) <= 2e-5 * scale
+        dv = golden.t(f"s{s}_depth_values")
+        assert _md(vol, dv[:, [0, -1]]) <= 1e-6 * float(dv.abs().max())
+
+
+# ------------------------------------------------------------------ a4-a7 sampling
+def _cam(golden, cfg, V_src=True):
+    return ops.camera_block(golden.t("in_tar_exts").to(DEV), golden.t("in_tar_ints").to(DEV), golden.t("in_src_exts").to(DEV),
+                            golden.t("in_src_ints").to(DEV), golden.t("in_near_far").to(DEV), cfg.nerf.bundle_size,
+                            cfg.nerf.global_num_depth, cfg.mvs.inv_depth[-1])
+
+
+@pytest.mark.parametrize("prefix", ["", "inj_"])
+def test_sampling_bit_exact_indices(golden, prefix):
+    cfg = _cfg(golden)
+    adaptive = True if prefix else cfg.nerf.is_adaptive
+    cam = _cam(golden, cfg)
+    sl = ops.sample_bundles(golden.t(prefix + "depth_range").to(DEV), golden.t(prefix + "vol_range").to(DEV), cam,
+                            cfg.nerf.bundle_size, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive)
+    assert sl.indices.dtype == torch.int64
+    assert np.array_equal(sl.indices.cpu().numpy(), golden.np(prefix + "indices"))                  # bit-exact
+    assert np.array_equal(sl.counts.cpu().numpy().astype(np.int64), golden.np(prefix + "samples_per_bundle").astype(np.int64))
+    assert sl.total == golden.np(prefix + "indices").shape[0]
+    offs = sl.offsets.cpu().numpy()
+    assert offs[0] == 0 and np.array_equal(np.diff(offs), sl.counts.cpu().numpy())
+    zs = float(golden.t(prefix + "z_vals").abs().max())
+    assert _md(sl.z_vals, golden.t(prefix + "z_vals")) <= 1e-6 * zs
+    assert _md(sl.uvd, golden.t(prefix + "uvd")) <= 2e-5
+    assert _md(sl.rays_xyz, golden.t(prefix + "rays_xyz")) <= 2e-6 * float(golden.t(prefix + "rays_xyz").abs().max())
+    rb = golden.t(prefix + "ball_radii")
+    assert _md(sl.ball_radii, rb) <= 2e-5 * float(rb.abs().max())
+
+
+def test_sampler_mirror_api(golden):
+    """BundleSampler keeps the reference's call sequence, return tuple and dtypes."""
+    from gdb_nerf_b200.sampler import BundleSampler
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    smp = BundleSampler(cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level)
+    with pytest.raises(ValueError, match="build_rays"):
+        smp.sample(golden.t("inj_depth_range").to(DEV), golden.t("inj_vol_range").to(DEV), cfg.nerf.bundle_size, cfg.nerf.max_num_samples)
+    nf = golden.t("in_near_far").to(DEV)
+    smp.build_rays(golden.t("in_tar_exts").to(DEV), golden.t("in_tar_ints").to(DEV), (spec["H"], spec["W"]), nf[:, 0], nf[:, 1])
+    out = smp.sample(golden.t("inj_depth_range").to(DEV), golden.t("inj_vol_range").to(DEV), cfg.nerf.bundle_size,
+                     cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], True)
+    rays_xyz, uvd, z, ball, idx, per_batch, per_bundle = out
+    assert per_bundle.dtype == torch.float32 and per_batch.dtype == torch.float32     # adaptive mode dtypes of the reference
+    assert np.array_equal(per_batch.cpu().numpy(), golden.np("inj_samples_per_batch"))
+    assert np.array_equal(idx.cpu().numpy(), golden.np("inj_indices"))
+
+
+# ------------------------------------------------------------------ a8 sources
+def test_prepare_sources(golden):
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b, L = cfg.nerf.bundle_size, cfg.nerf.max_mipmap_level
+    tex_ref = golden.t("tex_nchw")                                             # (B,V,F,Hb,Wb)
+    B, V, F, Hb, Wb = tex_ref.shape
+    rgb = golden.t("in_rgb")
+    src = ops.prepare_sources(tex_ref[:, :, :F - 3].contiguous().to(DEV), rgb.to(DEV), b, L)
+    lvl0 = ops.texture_level(src, B * V, Hb, Wb, 0).cpu()
+    want = tex_ref.flatten(0, 1).permute(0, 2, 3, 1)
+    assert torch.equal(lvl0[..., :F], want.contiguous())                       # exact: pure data movement + exact 2x2 mean
+    assert float(lvl0[..., F:].abs().max()) == 0.0 if lvl0.shape[-1] > F else True
+    mips = O.build_mips(want.contiguous(), L)
+    for k in range(1, L + 1):
+        got = ops.texture_level(src, B * V, Hb, Wb, k).cpu()[..., :F]
+        assert torch.equal(got, mips[k])                                       # same association as nvdiffrast's box filter
+    assert torch.equal(src.rgba.cpu()[..., :3], rgb.flatten(0, 1).permute(0, 2, 3, 1).contiguous())
+
+
+# ------------------------------------------------------------------ K3 / a9-a12
+def _render(golden, prefix, adaptive):
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    tex_ref = golden.t("tex_nchw")
+    B, V, F, Hb, Wb = tex_ref.shape
+    feat_dim = F - 3
+    cam = _cam(golden, cfg)
+    dr, vr = golden.t(prefix + "depth_range").to(DEV), golden.t(prefix + "vol_range").to(DEV)
+    sl = ops.sample_bundles(dr, vr, cam, b, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive, want_rays=False)
+    src = ops.prepare_sources(tex_ref[:, :, :feat_dim].contiguous().to(DEV), golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(golden.t("feat_volume").to(DEV), 8)
+    mlp = ops.pack_mlp(golden.mlp(), feat_dim, device=DEV)
+    out = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples,
+                           cfg.mvs.inv_depth[-1], adaptive, taps=sl)
+    plain = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples,
+                             cfg.mvs.inv_depth[-1], adaptive)
+    for k in ("feat", "depth", "opacity"):
+        assert torch.equal(out[k], plain[k])                                   # taps do not change the result
+    return out, (B, Hb, Wb)
+
+
+@pytest.mark.parametrize("prefix", ["", "inj_"])
+def test_render_fused_against_reference(golden, prefix):
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    adaptive = True if prefix else cfg.nerf.is_adaptive
+    out, (B, Hb, Wb) = _render(golden, prefix, adaptive)
+    noise = 3e-4 if spec["images"] == "noise" else 1e-4
+    # gathered inputs of the MLP
+    rfd_ref = golden.t(prefix + "rgbs_feat_dir")
+    assert out["rgbs_feat_dir"].shape == rfd_ref.shape
+    assert _md(out["vox_feat"], golden.t(prefix + "vox_feat")) <= 1e-4
+    assert _md(out["rgbs_feat_dir"][..., :-4], rfd_ref[..., :-4]) <= noise
+    assert _md(out["rgbs_feat_dir"][..., -1], rfd_ref[..., -1]) <= 1e-5
+    assert _md(out["rgbs_feat_dir"][..., -4:-1], rfd_ref[..., -4:-1]) <= 2e-3   # unit difference of nearly parallel rays
+    # MLP outputs, weights, composited maps
+    assert _md(out["sigma"], golden.t(prefix + "sigma")) <= 1e-4
+    assert _md(out["sample_feat"], golden.t(prefix + "feat")) <= noise
+    assert _md(out["weights"], golden.t(prefix + "weights")) <= 1e-4
+    ref_feat = golden.t(prefix + "bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2)
+    assert _md(out["feat"], ref_feat) <= noise
+    zs = float(golden.t(prefix + "z_vals").abs().max())
+    assert _md(out["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 1e-4 * max(1.0, zs / (spec["far"] - spec["near"]))
+    assert _md(out["opacity"].reshape(-1), golden.t(prefix + "bundle_opacity")) <= 1e-5
+
+
+def test_render_fused_against_fp64_oracle(golden):
+    """CUDA fp32 vs the float64 oracle on identical inputs: error no larger than ~the reference's own fp32 error."""
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    out, (B, Hb, Wb) = _render(golden, "inj_", True)
+    tex = golden.t("tex_nchw", torch.float64)
+    truth = O.render_bundles(
+        golden.mlp(dtype=torch.float64), tex.shape[2] - 3, golden.t("in_rgb", torch.float64), tex[:, :, :-3], golden.t("feat_volume", torch.float64),
+        golden.t("inj_depth_range"), golden.t("inj_vol_range"), golden.t("in_src_exts"), golden.t("in_src_ints"),
+        golden.t("in_tar_exts"), golden.t("in_tar_ints"), golden.t("in_near_far"), cfg.nerf.bundle_size, cfg.nerf.max_num_samples,
+        cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, cfg.mvs.inv_depth[-1], True)
+    # NB: sampling runs in float32 in both (counts are only defined there); everything downstream in float64
+    ref_feat = golden.t("inj_bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2)
+    ref_err = _md(ref_feat, truth["bundle_feat"])
+    mine = _md(out["feat"], truth["bundle_feat"])
+    assert mine <= max(1e-4, 2.0 * ref_err), (mine, ref_err)
+
+
+def test_output_assembly(golden):
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    B, Hb, Wb = spec["B"], spec["H"] // b, spec["W"] // b
+    feat = golden.t("bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2).contiguous()
+    bd, bo = golden.t("bundle_depth").view(B, Hb, Wb), golden.t("bundle_opacity").view(B, Hb, Wb)
+    g = torch.Generator().manual_seed(5)
+    dec = torch.rand(B, 3, spec["H"], spec["W"], generator=g)
+    for rew in (False, True):
+        rgb, depth, opac = ops.assemble_output(feat.to(DEV), dec.to(DEV), bd.to(DEV), bo.to(DEV), b, rew)
+        fine = torch.nn.functional.pixel_shuffle(feat[:, :3 * b * b], b)
+        want = dec + fine
+        if rew:
+            want = 0.5 * (want + fine)
+        assert _md(rgb, want) <= 1e-6
+        assert _md(depth, torch.nn.functional.interpolate(bd[:, None], scale_factor=b, mode="bilinear", align_corners=False)[:, 0]) <= 1e-6 * float(bd.abs().max())
+        assert _md(opac, torch.nn.functional.interpolate(bo[:, None], scale_factor=b, mode="bilinear", align_corners=False)[:, 0]) <= 1e-6
+
+
+def test_c_abi_rejects_unsupported_combinations():
+    from gdb_nerf_b200 import _lib
+    lib = _lib.load()
+    z = torch.zeros(64, device=DEV)
+    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 1, 1, 5, 32, 2, 2, 4, 2, 2, 0, z.data_ptr(), None)
+    assert code == -2 and b"not instantiated" in lib.gdb_last_error_string()
+    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 3, 1, 1, 3, 32, 2, 2, 4, 2, 2, 0, z.data_ptr(), None)
+    assert code == -1
