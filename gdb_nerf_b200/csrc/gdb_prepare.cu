@@ -58,9 +58,8 @@ prepare_sources_kernel(const float* __restrict__ feat, const float* __restrict__
       for (int c = 0; c < 3; ++c) {
         const float* pl = ip + (size_t)c * H * W + (size_t)cy * W + cx;
         if (BS > 1) {
-          float top = 0.5f * __ldg(pl) + 0.5f * __ldg(pl + 1);
-          float bot = 0.5f * __ldg(pl + W) + 0.5f * __ldg(pl + W + 1);
-          sp[c] = 0.5f * top + 0.5f * bot;
+          // four taps of weight 1/4 summed in tap order, the association ATen's CPU kernel uses (bit-exact with it)
+          sp[c] = 0.25f * (((__ldg(pl) + __ldg(pl + 1)) + __ldg(pl + W)) + __ldg(pl + W + 1));
         } else {
           sp[c] = __ldg(pl);
         }

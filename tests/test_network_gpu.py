@@ -130,7 +130,7 @@ def test_full_size_render_against_oracle_and_view_symmetry():
     # property: aggregation over source views is symmetric
     perm = run([2, 0, 1])
     assert _md(out["feat"], perm["feat"]) <= 2e-5
-    assert _md(out["depth"], perm["depth"]) <= 1e-4
+    assert _md(out["depth"], perm["depth"]) <= 1e-4 * (w["far"] - w["near"])
     # property: weights are renormalised per bundle -> opacity == 1
     assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
     dr = data["depth_range"]
