@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: rays/s of ``Network.forward`` at DTU 512x640, 3 source views,
+batch of 8 target views per step per GPU (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload dtu|llff|nerf] [--views-per-step B]
+
+One JSON line on stdout (rank 0).  Timing rules: W >= 3 warm-up steps, every
+timed step bracketed by CUDA events on the launching stream, an L2 flush (256 MB
+memset) between timed steps outside the events, max over ranks, SM clocks and
+throttle reasons sampled with nvidia-smi during the timed region.
+
+``--impl reference`` times the CPU port of the reference's forward
+(oracle/gdb_oracle.py:network_forward - the reference itself is pure Python and
+cannot travel to the GPU box) on the host cores, one target view per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays/sec and ms/target-view at DTU 512x640, 3 src views"
+UNIT = "rays/s"
+
+# algorithmic bytes per target view (SURVEY.md section 8d / DESIGN.md): unique bytes the kernel must move
+K3_BYTES_PER_VIEW = {"dtu": 66.2e6, "llff": 124.1e6, "nerf": 65.6e6}
+K1_BYTES_PER_VIEW = {"dtu": 107.5e6, "llff": 167.1e6, "nerf": 153.6e6}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, wl, cfg):
+    """CPU arm: the oracle port of Network.forward on the host cores, one target view per step."""
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import workload_batch
+    from oracle import gdb_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = Network(cfg).eval()
+    batch = workload_batch(args.workload, B=1, V=3, seed=0)
+    H, W = batch["src_views"]["rgb"].shape[-2:]
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.network_forward(net, batch, cfg)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = args.steps * H * W / total
+    sample = f"{args.steps} steps x 1 target view ({H}x{W}, 3 source views) after {args.warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} {H}x{W} eval forward, 3 source views, 1 target view per step, CPU",
+                   "recipe": wl["recipe"], "views_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(args, cfg, wl):
+    """Bounded CPU sample for the `cpu_baseline` object of our own arm (rank 0, N=1)."""
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import workload_batch
+    from oracle import gdb_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = Network(cfg).eval()
+    batch = workload_batch(args.workload, B=1, V=3, seed=0)
+    H, W = batch["src_views"]["rgb"].shape[-2:]
+    times = []
+    with torch.no_grad():
+        for i in range(3):
+            t0 = time.perf_counter()
+            O.network_forward(net, batch, cfg)
+            times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {"value": H * W / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"CPU port of Network.forward (oracle/gdb_oracle.py), 1 target view {H}x{W}, best of 2 after 1 warm-up "
+                      f"({best:.2f} s/view)"}
+
+
+def run_ours(args, wl, cfg):
+    import torch.distributed as dist
+
+    from gdb_nerf_b200 import ops
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import batch_to, workload_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.views_per_step
+    torch.manual_seed(0)
+    net = Network(cfg).to(dev).eval()
+    # every rank renders its own target views (round-robin shard of the sweep): no data-path collective
+    host_batch = workload_batch(args.workload, B=B, V=3, seed=rank, view_offset=rank * B)
+    H, W = host_batch["src_views"]["rgb"].shape[-2:]
+
+    def pin(x):
+        return {k: pin(v) for k, v in x.items()} if isinstance(x, dict) else x.pin_memory()
+
+    pinned = pin(host_batch)
+    dev_batch = batch_to(host_batch, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    # ---- launch counter + per-kernel events (on torch's current stream, which is the one the kernels launch on)
+    counts = {"n": 0}
+    spans = {"gdb_render_fused_fwd": [], "gdb_warp_variance_fwd": []}
+    recording = {"on": False}
+    launches_per_call = {"to_channels_last": 1, "homography_mats": 1, "depth_values": 1, "warp_variance": 1, "depth_range_from_prob": 1,
+                         "camera_block": 1, "prepare_sources": 1, "render_fused": 1, "assemble_output": 1}
+
+    def wrap(name, key=None):
+        fn = getattr(ops, name)
+
+        def inner(*a, **k):
+            counts["n"] += launches_per_call[name]
+            if key and recording["on"]:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                out = fn(*a, **k)
+                e.record(stream)
+                spans[key].append((s, e))
+                return out
+            return fn(*a, **k)
+
+        setattr(ops, name, inner)
+
+    for nm in launches_per_call:
+        wrap(nm, {"render_fused": "gdb_render_fused_fwd", "warp_variance": "gdb_warp_variance_fwd"}.get(nm))
+
+    def step_device():
+        with torch.no_grad():
+            ret, _, _ = net(dev_batch)
+        return ret
+
+    def step_e2e():
+        with torch.no_grad():
+            ret, _, _ = net(batch_to(pinned, dev, non_blocking=True))
+            return ret["rgb"].to("cpu", non_blocking=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, record):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                   # L2 flush between timed iterations, outside the events
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            recording["on"] = record
+            s.record(stream)
+            fn()
+            e.record(stream)
+            recording["on"] = False
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)       # ms over exactly `steps` steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    counts["n"] = 0
+    ms_dev = timed(step_device, args.steps, True)
+    launches = counts["n"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public API with host buffers (pinned H2D inside, D2H of the image inside)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t_e2e = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    ms_e2e = 1e3 * sum(t_e2e)
+    barrier()
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        rays_per_step = world * B * H * W
+        value = rays_per_step * args.steps / (ms_dev * 1e-3)
+        e2e_value = rays_per_step * args.steps / (ms_e2e * 1e-3)
+        peak, how = _peaks()
+
+        def roof(key, bytes_per_view):
+            sp = spans[key]
+            if not sp:
+                return None
+            ms = sum(s.elapsed_time(e) for s, e in sp) / len(sp)
+            launches_per_step = len(sp) / args.steps
+            # the cost-volume kernel launches once per cascade stage; its per-view figure covers both stages
+            bytes_per_launch = bytes_per_view * B / launches_per_step
+            ach = bytes_per_launch / (ms * 1e-3) / 1e9
+            return {"kernel": key, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "avg_launch_ms": ms, "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "peak_source": how}
+
+        h2d = sum(v.numel() * v.element_size() for d in (host_batch["src_views"], host_batch["tar_views"]) for v in d.values())
+        h2d += host_batch["near_far"].numel() * 4
+        d2h = B * 3 * H * W * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "ms_per_target_view": ms_dev / args.steps / B,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} {H}x{W} eval forward, 3 source views, batch of {B} target views per GPU per step "
+                                   f"(BASELINE.json configs[1])", "recipe": wl["recipe"], "views_per_step_per_gpu": B,
+                       "parallelism": f"target views sharded over {world} GPU(s), no data-path collective",
+                       "l2": "256 MB memset between timed steps (outside the CUDA events)", "cnn_math": "cuDNN, PyTorch default (TF32 conv)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "what": "pinned host batch -> H2D -> Network.forward -> D2H of ret['rgb'], wall clock"},
+            "gpu_launches": launches,
+            "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload]),
+            "roofline_warp_variance": roof("gdb_warp_variance_fwd", K1_BYTES_PER_VIEW[args.workload]),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(args, cfg, wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["dtu", "llff", "nerf"], default="dtu")
+    ap.add_argument("--views-per-step", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from gdb_nerf_b200.config import make_cfg
+    from gdb_nerf_b200.synthetic import WORKLOADS
+    wl = WORKLOADS[args.workload]
+    cfg = make_cfg(wl["recipe"])
+    if args.impl == "reference":
+        if args.steps is None:
+            args.steps = 3
+        run_reference(args, wl, cfg)
+    else:
+        if args.steps is None:
+            args.steps = 20
+        run_ours(args, wl, cfg)
+
+
+if __name__ == "__main__":
+    main()

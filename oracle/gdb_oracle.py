@@ -541,3 +541,71 @@ def render_bundles(
         "bundle_feat": bfeat.view(B, Hb, Wb, -1).permute(0, 3, 1, 2).contiguous(),
         "bundle_depth": bdepth.view(B, Hb, Wb), "bundle_opacity": bopac.view(B, Hb, Wb),
     }
+
+
+# --------------------------------------------------------------------------
+# whole Network.forward on the CPU (network.py:93-189): the CPU baseline that
+# bench.py times (`cpu_baseline`, `--impl reference`).  The convolutional
+# networks are PyTorch modules in the reference as well; they are passed in.
+# --------------------------------------------------------------------------
+def network_forward(net, batch: Mapping, cfg) -> Tuple[Dict[str, Tensor], List[Tensor]]:
+    """``net``: any module exposing feature_net / depth_net.cost_regs / nerf /
+    upsampler with the reference's parameter names (the product's
+    ``gdb_nerf_b200.network.Network`` on the CPU qualifies; only its CNN
+    sub-modules and its parameter tensors are used here, never its forward)."""
+    import torch.nn.functional as Fn
+
+    src = batch["src_views"]
+    images, src_exts, src_ints = src["rgb"], src["extrinsics"], src["intrinsics"]
+    tar_exts, tar_ints = batch["tar_views"]["extrinsics"], batch["tar_views"]["intrinsics"]
+    near_far = batch["near_far"]
+    B, V, _, H, W = images.shape
+    b = cfg.nerf.bundle_size
+    feats = [f.unflatten(0, (B, V)) for f in net.feature_net(images.flatten(0, 1))]
+    depth_range = near_far[..., None, None]
+    mvs_depths = []
+    n_stage = len(cfg.mvs.vol_levels)
+    for s in range(n_stage):
+        lvl = cfg.mvs.vol_levels[s]
+        fs, vs = cfg.fpn.feat_scales[lvl], cfg.mvs.vol_scales[s]
+        Ks = src_ints.clone(); Ks[..., :2, :] *= fs
+        Kt = tar_ints.clone(); Kt[:, :2, :] *= vs
+        Hi, Wi = int(H * vs), int(W * vs)
+        dv = depth_hypotheses(depth_range, cfg.mvs.num_depth[s], cfg.mvs.inv_depth[s]).expand(B, -1, Hi, Wi)
+        proj = homography_matrices(src_exts, Ks, tar_exts, Kt)
+        variance = warp_variance(feats[lvl], proj, dv, cfg.mvs.inv_depth[s])
+        volume, prob = net.depth_net.cost_regs[s](variance)
+        depth, ci = depth_interval(dv, prob, cfg.mvs.ci_scales[s], cfg.mvs.inv_depth[s])
+        mvs_depths.append(depth.squeeze(1))
+        vol_range = dv[:, [0, -1]]
+        depth_range = ci
+        if s < n_stage - 1:
+            up = cfg.mvs.vol_scales[s + 1] / cfg.mvs.vol_scales[s]
+            depth_range = upsample_bilinear(ci, int(ci.shape[-2] * up), int(ci.shape[-1] * up))
+    Hb, Wb = H // b, W // b
+    mvs_depth = mvs_depths[-1]
+    if ci.shape[-2:] != (Hb, Wb):
+        ci = upsample_bilinear(ci, Hb, Wb)
+        vol_range = upsample_bilinear(vol_range, Hb, Wb)
+        mvs_depth = Fn.interpolate(mvs_depth.unsqueeze(1), size=(Hb, Wb), mode="nearest").squeeze(1)
+    lvl = 0
+    while cfg.fpn.feat_scales[lvl] < 1.0 / b:
+        lvl += 1
+    mlp = {k: v.detach() for k, v in net.nerf.state_dict().items()}
+    out = render_bundles(mlp, cfg.fpn.feat_dims[lvl], images, feats[lvl], volume, ci, vol_range, src_exts, src_ints, tar_exts,
+                         tar_ints, near_far, b, cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level,
+                         cfg.mvs.inv_depth[-1], cfg.nerf.is_adaptive)
+    bf = out["bundle_feat"]
+    R = 3 * b * b
+    coarse = net.upsampler(bf[:, R:])
+    fine = Fn.pixel_shuffle(bf[:, :R], b)
+    rgb = coarse + fine
+    if cfg.nerf.reweighting:
+        rgb = 0.5 * (rgb + fine)
+    ret = {
+        "rgb": rgb,
+        "nerf_depth": upsample_bilinear(out["bundle_depth"].unsqueeze(1), H, W).squeeze(1),
+        "opacity": upsample_bilinear(out["bundle_opacity"].unsqueeze(1), H, W).squeeze(1),
+        "mvs_depth": mvs_depth,
+    }
+    return ret, mvs_depths

@@ -174,3 +174,28 @@ def test_render_bundles_end_to_end(golden):
     assert _maxdiff(out["bundle_feat"], ref_feat) <= noise
     zs = float(golden.t("inj_z_vals").abs().max())
     assert _maxdiff(out["bundle_depth"].reshape(-1), golden.t("inj_bundle_depth")) <= 1e-5 * zs
+
+
+@pytest.mark.parametrize("case", ["dtu_b2", "nerf_b4"])
+def test_network_forward_port_matches_reference(case):
+    """The whole-forward CPU port that bench.py times as `cpu_baseline` reproduces the reference's outputs."""
+    from conftest import load_golden
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import make_batch, synth_state_dict
+    g = load_golden(case)
+    spec = CASE_SPECS[case]
+    cfg = make_cfg(spec["recipe"])
+    net = Network(cfg)
+    net.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=1), strict=True)
+    net.eval()
+    batch = make_batch(spec["B"], spec["V"], spec["H"], spec["W"], spec["near"], spec["far"], spec["focal"], seed=3,
+                       images=spec["images"], tilt=spec["tilt"])
+    with torch.no_grad():
+        ret, mvs = O.network_forward(net, batch, cfg)
+    scale = spec["far"] - spec["near"]
+    assert _maxdiff(ret["rgb"], g.t("ret_rgb")) <= 1e-5
+    assert _maxdiff(ret["opacity"], g.t("ret_opacity")) <= 1e-5
+    assert _maxdiff(ret["nerf_depth"], g.t("ret_nerf_depth")) <= 1e-5 * scale
+    assert _maxdiff(ret["mvs_depth"], g.t("ret_mvs_depth")) <= 1e-5 * scale
+    for i, d in enumerate(mvs):
+        assert _maxdiff(d, g.t(f"mvs_depth_{i}")) <= 1e-5 * scale
