@@ -38,17 +38,17 @@ SIGNATURES = {
     "gdb_planar_to_channels_last": (c_i, [c_f, c_f, c_i, c_i, c_i64, c_i, c_f]),
     "gdb_homography_mats": (c_i, [c_f, c_f, c_f, c_f, c_fl, c_fl, c_i, c_i, c_f, c_f]),
     "gdb_depth_values": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
-    "gdb_warp_variance_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
+    "gdb_warp_variance_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
     "gdb_depth_range_fwd": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f]),
     "gdb_camera_block": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
     "gdb_bundle_count": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f]),
     "gdb_bundle_scan": (c_i, [c_f, c_f, c_i, c_f, c_f]),
     "gdb_bundle_emit": (c_i, [c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
     "gdb_texture_floats": (c_i64, [c_i, c_i, c_i, c_i, c_i]),
-    "gdb_prepare_sources": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f]),
+    "gdb_prepare_sources": (c_i, [c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f]),
     "gdb_render_fused_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
-                                   c_i, c_i, c_f, c_f, c_f, C.POINTER(RenderTaps), c_f]),
-    "gdb_assemble_output": (c_i, [c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f]),
+                                   c_i, c_i, c_i, c_f, c_f, c_f, c_f, C.POINTER(RenderTaps), c_f]),
+    "gdb_assemble_output": (c_i, [c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f]),
 }
 
 _lock = threading.Lock()

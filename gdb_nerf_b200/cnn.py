@@ -17,6 +17,57 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# ---------------------------------------------------------------------------
+# Inference-time execution of a conv -> batch-norm -> ReLU block: the batch-norm
+# affine map is folded into the convolution (exact algebra, eval mode only) and
+# the block runs as ONE cuDNN call (conv + bias + ReLU) on channels-last data.
+# Host-side plumbing around library kernels; the arithmetic is still cuDNN's.
+# ---------------------------------------------------------------------------
+def _folded(block: nn.Sequential):
+    conv, bn = block[0], block[1]
+    key = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, bn.weight.data_ptr())
+    cache = getattr(block, "_gdb_fold", None)
+    if cache is not None and cache[0] == key:
+        return cache[1], cache[2]
+    with torch.no_grad():
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        shift = (bn.bias - bn.running_mean * scale).contiguous()
+        w = conv.weight
+        if isinstance(conv, (nn.ConvTranspose2d, nn.ConvTranspose3d)):
+            w = w * scale.view(1, -1, *([1] * (w.dim() - 2)))
+        else:
+            w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+        fmt = torch.channels_last if w.dim() == 4 else torch.channels_last_3d
+        w = w.contiguous(memory_format=fmt)
+    block._gdb_fold = (key, w, shift)
+    return w, shift
+
+
+def run_block(block: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """conv+BN+ReLU block in eval mode, BN folded, fused where cuDNN offers it."""
+    conv = block[0]
+    w, b = _folded(block)
+    if isinstance(conv, nn.ConvTranspose3d):
+        return F.conv_transpose3d(x, w, b, conv.stride, conv.padding, conv.output_padding).relu_()
+    global _FUSED_3D
+    if isinstance(conv, nn.Conv2d):
+        return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if _FUSED_3D is not False:
+        try:
+            y = torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+            _FUSED_3D = True
+            return y
+        except RuntimeError:
+            if _FUSED_3D is True:
+                raise
+            _FUSED_3D = False     # this cuDNN build has no fused 3-D conv+bias+ReLU: plain conv + in-place ReLU
+    return F.conv3d(x, w, b, conv.stride, conv.padding).relu_()
+
+
+_FUSED_3D = None
+
+
 def _cbr(conv: nn.Module, norm: nn.Module) -> nn.Sequential:
     # conv -> batch-norm -> ReLU, indices 0/1/2 as in the reference's block builders
     return nn.Sequential(conv, norm, nn.ReLU(inplace=True))
@@ -63,6 +114,39 @@ class FeatureNet(nn.Module):
                 top = F.interpolate(top, size=f0.shape[-2:], mode="nearest") + self.inner2(f0)
                 outs.append(self.out2(top))
         return outs
+
+
+def feature_net_fused(net: "FeatureNet", x: torch.Tensor, levels: int = 3) -> List[torch.Tensor]:
+    x = x.contiguous(memory_format=torch.channels_last)
+    f0 = run_block(net.conv0[1], run_block(net.conv0[0], x))
+    f1 = run_block(net.conv1[1], run_block(net.conv1[0], f0))
+    f2 = run_block(net.conv2[1], run_block(net.conv2[0], f1))
+    outs = [net.out0(f2)]
+    if levels >= 2:
+        top = F.interpolate(f2, size=f1.shape[-2:], mode="nearest") + net.inner1(f1)
+        outs.append(net.out1(top))
+        if levels >= 3:
+            top = F.interpolate(top, size=f0.shape[-2:], mode="nearest") + net.inner2(f0)
+            outs.append(net.out2(top))
+    return outs
+
+
+def cost_reg_fused(net: "_CostReg", x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same data flow as CostRegNet(Small).forward with folded blocks; x is NCDHW-shaped, channels_last_3d strides."""
+    r = run_block
+    s0 = r(net.conv0, x)
+    s1 = r(net.conv2, r(net.conv1, s0))
+    if isinstance(net, CostRegNetSmall):
+        y = r(net.conv4, r(net.conv3, s1))
+        y = s1 + r(net.conv5, y)
+        y = s0 + r(net.conv6, y)
+    else:
+        s2 = r(net.conv4, r(net.conv3, s1))
+        y = r(net.conv6, r(net.conv5, s2))
+        y = s2 + r(net.conv7, y)
+        y = s1 + r(net.conv8, y)
+        y = s0 + r(net.conv9, y)
+    return net.feat_head(y), torch.softmax(net.prob_head(y).squeeze(1), dim=1)
 
 
 class _CostReg(nn.Module):

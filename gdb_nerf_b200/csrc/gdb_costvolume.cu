@@ -105,12 +105,38 @@ __global__ void depth_values_kernel(const float* __restrict__ range, int rh, int
 //
 // Thread = (target pixel, 4-channel slice).  C/4 adjacent lanes read one source
 // texel (C*4 bytes, channels-last) as consecutive float4s, so every warp-level
-// LDG.128 covers whole 128-byte lines.  A CTA owns PIX consecutive target
-// pixels and DCH depth planes; the 4-channel results are transposed through
-// shared memory so that the NCDHW variance volume is written in 128-byte
-// (or longer) runs per channel plane.
+// LDG.128 covers whole 128-byte lines.  The projection of a pixel into a view
+// is computed by ONE lane of the pixel's lane group (lane q handles view q) and
+// broadcast with shuffles: the coordinate arithmetic is issued once per warp
+// instead of once per view.  A CTA owns PIX consecutive target pixels and DCH
+// depth planes.  Output either channels-last (B,D,Ht,Wt,C) - one coalesced
+// STG.128 per thread, what cuDNN's NDHWC kernels consume directly - or planar
+// NCDHW (the reference's layout) through a shared-memory transpose.
 // ---------------------------------------------------------------------------
-template <int C, int V>
+struct WarpTap {
+  int xy;        // (y0 + 2) << 16 | (x0 + 2), clamped so that the packing is safe
+  float tx, ty;
+};
+
+__device__ __forceinline__ WarpTap warp_tap(const float* __restrict__ P, float rx, float ry, float rz, float depth, float fWs,
+                                            float fHs) {
+  float X = fmaf(rx, depth, P[3]);
+  float Y = fmaf(ry, depth, P[7]);
+  float Z = fmaxf(fmaf(rz, depth, P[11]), 1e-6f);
+  float iz = 1.f / Z;
+  // pixel-space coordinate u = X/Z maps to texel space u - 0.5 (normalise + grid_sample un-normalise cancel)
+  float ix = fmaf(X, iz, -0.5f), iy = fmaf(Y, iz, -0.5f);
+  float x0f = floorf(ix), y0f = floorf(iy);
+  WarpTap t;
+  t.tx = ix - x0f;
+  t.ty = iy - y0f;
+  x0f = fminf(fmaxf(x0f, -2.f), fWs + 1.f);    // also maps NaN to -2 (fully outside)
+  y0f = fminf(fmaxf(y0f, -2.f), fHs + 1.f);
+  t.xy = (((int)y0f + 2) << 16) | ((int)x0f + 2);
+  return t;
+}
+
+template <int C, int V, bool OUT_CL>
 __global__ void __launch_bounds__(256)
 warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
                      int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
@@ -119,7 +145,8 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
   constexpr int PIX = 256 / LPP;      // pixels per CTA
   constexpr int PAD = (C == 32) ? 1 : (C == 16 ? 2 : 4);
   constexpr int ROW = PIX + PAD;
-  __shared__ float tile[2][C * ROW];
+  constexpr bool SHARE = LPP >= V;    // one lane per (pixel, view) does the projection
+  __shared__ float tile[OUT_CL ? 1 : 2][OUT_CL ? 1 : C * ROW];
   __shared__ float sproj[V * 12];
 
   const int b = blockIdx.z;
@@ -129,19 +156,21 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
   const int pix = blockIdx.x * PIX + pl;
   const bool live = pix < HW;
   const int px = live ? pix % Wt : 0, py = live ? pix / Wt : 0;
+  const int lane = threadIdx.x & 31;
+  const int group_base = lane - q;
 
   if (threadIdx.x < V * 12) sproj[threadIdx.x] = proj[(size_t)b * V * 12 + threadIdx.x];
   __syncthreads();
 
-  // rotation part applied to the pixel centre, once per view
-  float rx[V], ry[V], rz[V];
+  // rotation part applied to the pixel centre (for the view(s) this lane projects)
   const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+  float rx[SHARE ? 1 : V], ry[SHARE ? 1 : V], rz[SHARE ? 1 : V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const float* P = sproj + v * 12;
-    rx[v] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
-    ry[v] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
-    rz[v] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
+  for (int k = 0; k < (SHARE ? 1 : V); ++k) {
+    const float* P = sproj + (SHARE ? min(q, V - 1) : k) * 12;
+    rx[k] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
+    ry[k] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
+    rz[k] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
   }
   const int ryi = rh == 1 ? 0 : py, rxi = rw == 1 ? 0 : px;
   const float near_ = range[((size_t)(b * 2 + 0) * rh + ryi) * rw + rxi];
@@ -156,39 +185,37 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
   for (int d = d0; d < d1; ++d, buf ^= 1) {
     float dv = hypothesis(near_, far_, d, D, inv_depth);
     float depth = inv_depth ? fdiv(1.f, dv) : dv;
+    WarpTap mine;
+    if (SHARE) mine = warp_tap(sproj + min(q, V - 1) * 12, rx[0], ry[0], rz[0], depth, fWs, fHs);
     float4 val[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float* P = sproj + v * 12;
-      float X = fmaf(rx[v], depth, P[3]);
-      float Y = fmaf(ry[v], depth, P[7]);
-      float Z = fmaxf(fmaf(rz[v], depth, P[11]), 1e-6f);
-      // same normalise -> un-normalise sequence as the reference + grid_sample
-      float gx = 2.f * (X / Z) / fWs - 1.f;
-      float gy = 2.f * (Y / Z) / fHs - 1.f;
-      float ix = ((gx + 1.f) * fWs - 1.f) * 0.5f;
-      float iy = ((gy + 1.f) * fHs - 1.f) * 0.5f;
-      float x0f = floorf(ix), y0f = floorf(iy);
-      float tx = ix - x0f, ty = iy - y0f;
-      // keep the integer conversion safe for wild coordinates
-      x0f = fminf(fmaxf(x0f, -2.f), fWs + 1.f);
-      y0f = fminf(fmaxf(y0f, -2.f), fHs + 1.f);
-      int x0 = (int)x0f, y0 = (int)y0f;
-      bool vx0 = x0 >= 0 && x0 < Ws, vx1 = x0 + 1 >= 0 && x0 + 1 < Ws;
-      bool vy0 = y0 >= 0 && y0 < Hs, vy1 = y0 + 1 >= 0 && y0 + 1 < Hs;
-      const float* vb = fbase + v * view_stride;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 t00 = acc, t10 = acc, t01 = acc, t11 = acc;
-      if (live) {
-        if (vx0 && vy0) t00 = ldg4(vb + ((size_t)y0 * Ws + x0) * C);
-        if (vx1 && vy0) t10 = ldg4(vb + ((size_t)y0 * Ws + x0 + 1) * C);
-        if (vx0 && vy1) t01 = ldg4(vb + ((size_t)(y0 + 1) * Ws + x0) * C);
-        if (vx1 && vy1) t11 = ldg4(vb + ((size_t)(y0 + 1) * Ws + x0 + 1) * C);
+      WarpTap t;
+      if (SHARE) {
+        t.xy = __shfl_sync(0xffffffffu, mine.xy, group_base + v);
+        t.tx = __shfl_sync(0xffffffffu, mine.tx, group_base + v);
+        t.ty = __shfl_sync(0xffffffffu, mine.ty, group_base + v);
+      } else {
+        t = warp_tap(sproj + v * 12, rx[SHARE ? 0 : v], ry[SHARE ? 0 : v], rz[SHARE ? 0 : v], depth, fWs, fHs);
       }
-      acc = f4_scale_add(acc, t00, (1.f - tx) * (1.f - ty));
-      acc = f4_scale_add(acc, t10, tx * (1.f - ty));
-      acc = f4_scale_add(acc, t01, (1.f - tx) * ty);
-      acc = f4_scale_add(acc, t11, tx * ty);
+      const int x0 = (t.xy & 0xffff) - 2, y0 = (t.xy >> 16) - 2;
+      const bool vx0 = (unsigned)x0 < (unsigned)Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)Ws;
+      const bool vy0 = (unsigned)y0 < (unsigned)Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)Hs;
+      const float* vb = fbase + v * view_stride + ((ptrdiff_t)y0 * Ws + x0) * C;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t00 = zero, t10 = zero, t01 = zero, t11 = zero;
+      if (live) {
+        if (vx0 && vy0) t00 = ldg4(vb);
+        if (vx1 && vy0) t10 = ldg4(vb + C);
+        if (vx0 && vy1) t01 = ldg4(vb + (size_t)Ws * C);
+        if (vx1 && vy1) t11 = ldg4(vb + (size_t)Ws * C + C);
+      }
+      const float wx1 = t.tx, wx0 = 1.f - t.tx, wy1 = t.ty, wy0 = 1.f - t.ty;
+      float4 acc = zero;
+      acc = f4_scale_add(acc, t00, wx0 * wy0);
+      acc = f4_scale_add(acc, t10, wx1 * wy0);
+      acc = f4_scale_add(acc, t01, wx0 * wy1);
+      acc = f4_scale_add(acc, t11, wx1 * wy1);
       val[v] = acc;
     }
     float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -202,34 +229,42 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
       float a = val[v].x - mean.x, bb = val[v].y - mean.y, c = val[v].z - mean.z, e = val[v].w - mean.w;
       var.x = fmaf(a, a, var.x); var.y = fmaf(bb, bb, var.y); var.z = fmaf(c, c, var.z); var.w = fmaf(e, e, var.w);
     }
-    float* t = tile[buf];
-    t[(q * 4 + 0) * ROW + pl] = var.x * invV;
-    t[(q * 4 + 1) * ROW + pl] = var.y * invV;
-    t[(q * 4 + 2) * ROW + pl] = var.z * invV;
-    t[(q * 4 + 3) * ROW + pl] = var.w * invV;
-    __syncthreads();
-    // coalesced plane writes: C rows of PIX floats
-    float* obase = out + (((size_t)b * C) * D + d) * HW + (size_t)blockIdx.x * PIX;
+    var.x *= invV; var.y *= invV; var.z *= invV; var.w *= invV;
+    if (OUT_CL) {
+      if (live) __stcs(reinterpret_cast<float4*>(out + (((size_t)b * D + d) * HW + pix) * C + q * 4), var);
+    } else {
+      float* t = tile[buf];
+      t[(q * 4 + 0) * ROW + pl] = var.x;
+      t[(q * 4 + 1) * ROW + pl] = var.y;
+      t[(q * 4 + 2) * ROW + pl] = var.z;
+      t[(q * 4 + 3) * ROW + pl] = var.w;
+      __syncthreads();
+      // coalesced plane writes: C rows of PIX floats
+      float* obase = out + (((size_t)b * C) * D + d) * HW + (size_t)blockIdx.x * PIX;
 #pragma unroll
-    for (int i = 0; i < (C * PIX) / 256; ++i) {
-      int idx = i * 256 + threadIdx.x;
-      int c = idx / PIX, p = idx % PIX;
-      if (blockIdx.x * PIX + p < HW) __stcs(obase + (size_t)c * D * HW + p, t[c * ROW + p]);
+      for (int i = 0; i < (C * PIX) / 256; ++i) {
+        int idx = i * 256 + threadIdx.x;
+        int c = idx / PIX, p = idx % PIX;
+        if (blockIdx.x * PIX + p < HW) __stcs(obase + (size_t)c * D * HW + p, t[c * ROW + p]);
+      }
+      // the other buffer is written next; its readers finished before the barrier above
     }
-    // the other buffer is written next; its readers finished before the barrier above
   }
 }
 
 template <int C, int V>
 static int launch_warp_variance(const float* feat, const float* proj, const float* range, int rh, int rw, int B, int Hs,
-                                int Ws, int D, int Ht, int Wt, int inv_depth, float* out, cudaStream_t st) {
+                                int Ws, int D, int Ht, int Wt, int inv_depth, int out_cl, float* out, cudaStream_t st) {
   constexpr int PIX = 256 / (C / 4);
   int tiles = (Ht * Wt + PIX - 1) / PIX;
   // depth chunk: enough CTAs for >= 4 waves of 148 SMs x 4 resident CTAs, but keep planes together for L1 reuse
   int DCH = D;
   while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
   dim3 grid(tiles, (D + DCH - 1) / DCH, B);
-  warp_variance_kernel<C, V><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+  if (out_cl)
+    warp_variance_kernel<C, V, true><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+  else
+    warp_variance_kernel<C, V, false><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
   return cuda_check("gdb_warp_variance_fwd");
 }
 
@@ -337,16 +372,18 @@ extern "C" int gdb_depth_values(const float* depth_range, int rh, int rw, int B,
 
 extern "C" int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw,
                                      int B, int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth,
-                                     float* variance, void* stream) {
+                                     int out_channels_last, float* variance, void* stream) {
   GDB_REQUIRE(feat_cl && proj && depth_range && variance, GDB_E_BADARG, "gdb_warp_variance_fwd: null pointer");
   GDB_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && D > 0 && Ht > 0 && Wt > 0, GDB_E_BADARG, "gdb_warp_variance_fwd: bad size");
   GDB_REQUIRE((rh == 1 && rw == 1) || (rh == Ht && rw == Wt), GDB_E_BADARG,
               "gdb_warp_variance_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", Ht, Wt, rh, rw);
-  GDB_REQUIRE(aligned16(feat_cl), GDB_E_ALIGN, "gdb_warp_variance_fwd: feat_cl not 16-byte aligned");
+  GDB_REQUIRE(aligned16(feat_cl) && (!out_channels_last || aligned16(variance)), GDB_E_ALIGN,
+              "gdb_warp_variance_fwd: feat_cl / channels-last output not 16-byte aligned");
+  GDB_REQUIRE(Hs < 32000 && Ws < 32000, GDB_E_UNSUPPORTED, "gdb_warp_variance_fwd: source map larger than 32000 px");
   GDB_REQUIRE(B <= 65535, GDB_E_UNSUPPORTED, "gdb_warp_variance_fwd: B > 65535");
   cudaStream_t st = as_stream(stream);
 #define GDB_WV(CC, VV) \
-  if (C == CC && V == VV) return launch_warp_variance<CC, VV>(feat_cl, proj, depth_range, rh, rw, B, Hs, Ws, D, Ht, Wt, inv_depth, variance, st);
+  if (C == CC && V == VV) return launch_warp_variance<CC, VV>(feat_cl, proj, depth_range, rh, rw, B, Hs, Ws, D, Ht, Wt, inv_depth, out_channels_last, variance, st);
   GDB_WV(32, 2) GDB_WV(32, 3) GDB_WV(32, 4) GDB_WV(16, 2) GDB_WV(16, 3) GDB_WV(16, 4) GDB_WV(8, 2) GDB_WV(8, 3) GDB_WV(8, 4)
 #undef GDB_WV
   return fail(GDB_E_UNSUPPORTED, "gdb_warp_variance_fwd: C=%d V=%d not instantiated (C in {8,16,32}, V in {2,3,4})", C, V);

@@ -17,8 +17,8 @@ constexpr int TILE_H = 8, TILE_W = 32;
 //     0.25*((a00+a10)+(a01+a11)) and writes them.
 template <int FP>
 __global__ void __launch_bounds__(256)
-prepare_sources_kernel(const float* __restrict__ feat, const float* __restrict__ images, int Cf, int Hb, int Wb, int BS,
-                       int L, int64_t lvl1, int64_t lvl2, int64_t lvl3, float* __restrict__ tex, float* __restrict__ rgba) {
+prepare_sources_kernel(const float* __restrict__ feat, const float* __restrict__ images, int Cf, int feat_cl, int Hb, int Wb,
+                       int BS, int L, int64_t lvl1, int64_t lvl2, int64_t lvl3, float* __restrict__ tex, float* __restrict__ rgba) {
   __shared__ __align__(16) float s0[TILE_H * TILE_W * FP];
   __shared__ __align__(16) float s1[(TILE_H / 2) * (TILE_W / 2) * FP];
   __shared__ __align__(16) float s2[(TILE_H / 4) * (TILE_W / 4) * FP];
@@ -35,9 +35,17 @@ prepare_sources_kernel(const float* __restrict__ feat, const float* __restrict__
 
   // -- features: coalesced plane reads, channels-last in shared memory
   {
-    const float* fp = feat + (size_t)bv * Cf * Hb * Wb + (size_t)(ty0 + row) * Wb + tx0 + col;
     float* sp = s0 + (row * TILE_W + col) * FP;
-    for (int c = 0; c < Cf; ++c) sp[c] = in_tile ? __ldg(fp + (size_t)c * Hb * Wb) : 0.f;
+    if (feat_cl) {      // (BV, Hb, Wb, Cf): one texel is Cf contiguous floats
+      const float* fp = feat + (((size_t)bv * Hb + ty0 + row) * Wb + tx0 + col) * Cf;
+      for (int c = 0; c < Cf; c += 4) {
+        float4 v = in_tile ? ldg4(fp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sp[c] = v.x; sp[c + 1] = v.y; sp[c + 2] = v.z; sp[c + 3] = v.w;
+      }
+    } else {            // (BV, Cf, Hb, Wb): coalesced plane reads
+      const float* fp = feat + (size_t)bv * Cf * Hb * Wb + (size_t)(ty0 + row) * Wb + tx0 + col;
+      for (int c = 0; c < Cf; ++c) sp[c] = in_tile ? __ldg(fp + (size_t)c * Hb * Wb) : 0.f;
+    }
     for (int c = F; c < FP; ++c) sp[c] = 0.f;
   }
   // -- full-resolution pixels of the tile -> RGBA
@@ -113,8 +121,9 @@ __device__ __forceinline__ void up_axis(int o, int n_in, float inv_scale, int& i
 
 __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot, const float* __restrict__ dec,
                                        const float* __restrict__ bdepth, const float* __restrict__ bopac, int B, int Hb,
-                                       int Wb, int BS, int reweighting, float* __restrict__ rgb, float* __restrict__ depth,
-                                       float* __restrict__ opacity) {
+                                       int Wb, int BS, int reweighting, int layout, float* __restrict__ rgb,
+                                       float* __restrict__ depth, float* __restrict__ opacity) {
+  const bool feat_cl = layout & 1, dec_cl = layout & 2;
   const int H = Hb * BS, W = Wb * BS;
   const size_t HW = (size_t)H * W, hw = (size_t)Hb * Wb;
   size_t n = (size_t)B * HW;
@@ -124,8 +133,9 @@ __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot,
     int yb = y / BS, xb = x / BS, j = (y % BS) * BS + (x % BS);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float fine = feat[((size_t)b * Ctot + c * BS * BS + j) * hw + (size_t)yb * Wb + xb];
-      float v = dec[((size_t)b * 3 + c) * HW + (size_t)y * W + x] + fine;
+      float fine = feat_cl ? feat[((size_t)b * hw + (size_t)yb * Wb + xb) * Ctot + c * BS * BS + j]
+                           : feat[((size_t)b * Ctot + c * BS * BS + j) * hw + (size_t)yb * Wb + xb];
+      float v = (dec_cl ? dec[((size_t)b * HW + (size_t)y * W + x) * 3 + c] : dec[((size_t)b * 3 + c) * HW + (size_t)y * W + x]) + fine;
       if (reweighting) v = 0.5f * (v + fine);
       rgb[((size_t)b * 3 + c) * HW + (size_t)y * W + x] = v;
     }
@@ -155,8 +165,8 @@ extern "C" int64_t gdb_texture_floats(int BV, int Hb, int Wb, int feat_dim, int 
   return n;
 }
 
-extern "C" int gdb_prepare_sources(const float* feat, const float* images, int BV, int Cf, int Hb, int Wb, int bundle_size,
-                                   int max_mip_level, float* tex, float* rgba, void* stream) {
+extern "C" int gdb_prepare_sources(const float* feat, int feat_channels_last, const float* images, int BV, int Cf, int Hb,
+                                   int Wb, int bundle_size, int max_mip_level, float* tex, float* rgba, void* stream) {
   GDB_REQUIRE(feat && images && tex && rgba && BV > 0 && Cf > 0 && Hb > 0 && Wb > 0, GDB_E_BADARG, "gdb_prepare_sources: bad argument");
   GDB_REQUIRE(max_mip_level >= 0 && max_mip_level <= 3, GDB_E_UNSUPPORTED, "gdb_prepare_sources: max_mip_level must be 0..3");
   GDB_REQUIRE(bundle_size >= 1 && (bundle_size & (bundle_size - 1)) == 0, GDB_E_BADARG, "gdb_prepare_sources: bundle_size must be a power of two");
@@ -164,6 +174,7 @@ extern "C" int gdb_prepare_sources(const float* feat, const float* images, int B
   GDB_REQUIRE(Hb % m == 0 && Wb % m == 0, GDB_E_BADARG,
               "gdb_prepare_sources: bundle map %dx%d must be divisible by 2^max_mip_level=%d (as nvdiffrast requires)", Hb, Wb, m);
   GDB_REQUIRE(aligned16(tex) && aligned16(rgba), GDB_E_ALIGN, "gdb_prepare_sources: outputs not 16-byte aligned");
+  GDB_REQUIRE(!feat_channels_last || (aligned16(feat) && Cf % 4 == 0), GDB_E_ALIGN, "gdb_prepare_sources: channels-last features need 16-byte alignment and Cf % 4 == 0");
   GDB_REQUIRE(BV <= 65535, GDB_E_UNSUPPORTED, "gdb_prepare_sources: B*V > 65535");
   const int FP = padded_feat(Cf);
   int64_t lvl[4] = {0, 0, 0, 0};
@@ -171,22 +182,22 @@ extern "C" int gdb_prepare_sources(const float* feat, const float* images, int B
   dim3 grid((Wb + TILE_W - 1) / TILE_W, (Hb + TILE_H - 1) / TILE_H, BV);
   cudaStream_t st = as_stream(stream);
   switch (FP) {
-    case 12: prepare_sources_kernel<12><<<grid, 256, 0, st>>>(feat, images, Cf, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
-    case 20: prepare_sources_kernel<20><<<grid, 256, 0, st>>>(feat, images, Cf, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
-    case 36: prepare_sources_kernel<36><<<grid, 256, 0, st>>>(feat, images, Cf, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
+    case 12: prepare_sources_kernel<12><<<grid, 256, 0, st>>>(feat, images, Cf, feat_channels_last, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
+    case 20: prepare_sources_kernel<20><<<grid, 256, 0, st>>>(feat, images, Cf, feat_channels_last, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
+    case 36: prepare_sources_kernel<36><<<grid, 256, 0, st>>>(feat, images, Cf, feat_channels_last, Hb, Wb, bundle_size, max_mip_level, lvl[1], lvl[2], lvl[3], tex, rgba); break;
     default: return fail(GDB_E_UNSUPPORTED, "gdb_prepare_sources: feature width %d not in {8,16,32}", Cf);
   }
   return cuda_check("gdb_prepare_sources");
 }
 
 extern "C" int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
-                                   int B, int Hb, int Wb, int bundle_size, int reweighting, float* rgb, float* depth,
-                                   float* opacity, void* stream) {
+                                   int B, int Hb, int Wb, int bundle_size, int reweighting, int layout, float* rgb,
+                                   float* depth, float* opacity, void* stream) {
   GDB_REQUIRE(feat && dec && bdepth && bopacity && rgb && depth && opacity, GDB_E_BADARG, "gdb_assemble_output: null pointer");
   GDB_REQUIRE(B > 0 && Hb > 0 && Wb > 0 && bundle_size > 0 && Ctot >= 3 * bundle_size * bundle_size, GDB_E_BADARG, "gdb_assemble_output: bad size");
   size_t n = (size_t)B * Hb * Wb * bundle_size * bundle_size;
   int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
   assemble_output_kernel<<<blocks, 256, 0, as_stream(stream)>>>(feat, Ctot, dec, bdepth, bopacity, B, Hb, Wb, bundle_size,
-                                                               reweighting, rgb, depth, opacity);
+                                                               reweighting, layout, rgb, depth, opacity);
   return cuda_check("gdb_assemble_output");
 }

@@ -26,7 +26,8 @@ struct RenderParams {
   const float* vol_range;
   const float* cam;
   const float* mlp;
-  float* out_feat;        // (B, CT, Hb, Wb)
+  float* out_feat;        // (B, CT, Hb, Wb) planar, or (B, Hb, Wb, R) when out_cl
+  float* out_dec;         // (B, Hb, Wb, F+8) when out_cl
   float* out_depth;
   float* out_opacity;
   // optional taps
@@ -39,7 +40,7 @@ struct RenderParams {
   float* tap_w;
   int64_t tex_level[4];
   int cam_stride;
-  int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive;
+  int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
 };
 
 template <int N>
@@ -463,7 +464,10 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
       return acc;
     };
     const bool writer = has_bundle && slot == 0;
-    float* of = p.out_feat + (size_t)b * CT * HW + pix;
+    // planar: channel c at of[c * ostr]; channels-last: fine colours in out_feat (R per bundle), the rest in out_dec
+    const size_t ostr = p.out_cl ? 1 : (size_t)HW;
+    float* of = p.out_cl ? p.out_feat + (size_t)bidx * R : p.out_feat + (size_t)b * CT * HW + pix;
+    float* od = p.out_cl ? p.out_dec + (size_t)bidx * (F + 8) - R : of;
     float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     // -- fine colours: project every ray of the bundle into every view, bilinear on the full-res image,
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
       if (tf) { tf[0 * BB + j] = cr; tf[1 * BB + j] = cg; tf[2 * BB + j] = cb; }
       float sr = seg_sum(wgt * cr), sg = seg_sum(wgt * cg), sb = seg_sum(wgt * cb);
       if (writer) {
-        of[(size_t)(0 * BB + j) * HW] = sr; of[(size_t)(1 * BB + j) * HW] = sg; of[(size_t)(2 * BB + j) * HW] = sb;
+        of[(size_t)(0 * BB + j) * ostr] = sr; of[(size_t)(1 * BB + j) * ostr] = sg; of[(size_t)(2 * BB + j) * ostr] = sb;
       }
     }
     // -- blended feature+rgb channels
@@ -513,14 +517,14 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
       for (int v = 0; v < V; ++v) a = fmaf(SM(C::R_FR + v * F + c), wv[v], a);
       if (tf) tf[R + c] = a;
       float s = seg_sum(wgt * a);
-      if (writer) of[(size_t)(R + c) * HW] = s;
+      if (writer) od[(size_t)(R + c) * ostr] = s;
     }
     // -- geometry head channels
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (tf) tf[R + F + k] = fh[k];
       float s = seg_sum(wgt * fh[k]);
-      if (writer) of[(size_t)(R + F + k) * HW] = s;
+      if (writer) od[(size_t)(R + F + k) * ostr] = s;
     }
     // -- depth and opacity (network.py:83-89)
     {
@@ -578,8 +582,9 @@ extern "C" int gdb_mlp_param_floats(int feat_dim) {
 extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
                                     const float* vol_range, const float* cam, int cam_stride, const float* mlp, int B,
                                     int V, int H, int W, int bundle_size, int feat_dim, int D, int max_samples,
-                                    int max_mip_level, int inv_depth, int adaptive, int precision, float* out_feat,
-                                    float* out_depth, float* out_opacity, const gdb_render_taps* taps, void* stream) {
+                                    int max_mip_level, int inv_depth, int adaptive, int precision, int out_channels_last,
+                                    float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
+                                    const gdb_render_taps* taps, void* stream) {
   GDB_REQUIRE(rgba && tex && vol_cl && depth_range && vol_range && cam && mlp && out_feat && out_depth && out_opacity,
               GDB_E_BADARG, "gdb_render_fused_fwd: null pointer");
   GDB_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, GDB_E_BADARG, "gdb_render_fused_fwd: bad size");
@@ -594,7 +599,8 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               CAM_HEAD + CAM_VIEW * V);
   RenderParams p{};
   p.rgba = rgba; p.tex = tex; p.vol = vol_cl; p.depth_range = depth_range; p.vol_range = vol_range; p.cam = cam; p.mlp = mlp;
-  p.out_feat = out_feat; p.out_depth = out_depth; p.out_opacity = out_opacity;
+  GDB_REQUIRE(!out_channels_last || out_dec, GDB_E_BADARG, "gdb_render_fused_fwd: channels-last output needs out_dec");
+  p.out_feat = out_feat; p.out_dec = out_dec; p.out_depth = out_depth; p.out_opacity = out_opacity; p.out_cl = out_channels_last ? 1 : 0;
   if (taps && (taps->rgbs_feat_dir || taps->vox_feat || taps->sigma || taps->feat || taps->weights)) {
     GDB_REQUIRE(taps->offsets && taps->S_total > 0, GDB_E_BADARG, "gdb_render_fused_fwd: taps need offsets and S_total");
     GDB_REQUIRE(!taps->vox_feat || aligned16(taps->vox_feat), GDB_E_ALIGN, "gdb_render_fused_fwd: vox tap not aligned");

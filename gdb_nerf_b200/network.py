@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet
+from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, feature_net_fused
 from .nerf import CoarseNeRF, NeRF
 from .sampler import BundleSampler
 
@@ -59,7 +59,7 @@ class DepthNet(nn.Module):
             CoarseNeRF(config.nerf.nerf_hidden_dims, voxel_dim, self.feat_dims[i], config.nerf.viewdir_agg)
             for i in range(self.num_stages - 1)])
 
-    def forward(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far):
+    def forward(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far, fused_cnn: bool = False):
         B, V, _, H, W = src_images.shape
         mvs_depths: List[torch.Tensor] = []
         range_list: List[torch.Tensor] = []
@@ -71,8 +71,9 @@ class DepthNet(nn.Module):
             Hi, Wi = int(H * self.vol_scales[s]), int(W * self.vol_scales[s])
             proj = ops.homography_mats(src_exts, src_ints, tar_exts, tar_ints, self.feat_scales[s], self.vol_scales[s])
             feat_cl = ops.to_channels_last(feats.flatten(0, 1)).unflatten(0, (B, V))
-            variance = ops.warp_variance(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s])
-            volume, prob = self.cost_regs[s](variance)
+            variance = ops.warp_variance(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s],
+                                         out_channels_last=fused_cnn)
+            volume, prob = cost_reg_fused(self.cost_regs[s], variance) if fused_cnn else self.cost_regs[s](variance)
             depth, ci, vol_range = ops.depth_range_from_prob(depth_range, prob, self.ci_scales[s], self.inv_depth[s])
             mvs_depths.append(depth.squeeze(1))
             range_list.append(ci)
@@ -113,6 +114,22 @@ class Network(nn.Module):
         self.upsampler = Decoder(feat_dim + 3 + self.voxel_dim, 3, num_feats=64, num_layers=self.dec_layers, upscale_factor=self.b_size)
         self.reweighting = config.nerf.reweighting
         self._fpn_levels = max(max(self.depth_net.vol_levels), self.feat_level) + 1
+        # "fused": eval-time execution of the cuDNN networks with batch-norm folded into the convolutions and
+        # channels-last tensors end to end (the kernels read/write those layouts directly);
+        # "modules": the plain nn.Module graph in the reference's NCHW layout.  Same arithmetic either way.
+        self.cnn_mode = "fused"
+        self._cl_ready = False
+
+    def _channels_last_params(self) -> None:
+        if not self._cl_ready:
+            self.feature_net.to(memory_format=torch.channels_last)
+            self.upsampler.to(memory_format=torch.channels_last)
+            self.depth_net.cost_regs.to(memory_format=torch.channels_last_3d)
+            self._cl_ready = True
+
+    def _apply(self, fn, *args, **kwargs):
+        self._cl_ready = False      # .to()/.cuda() may re-create parameter storage
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, batch: Dict[str, Any]) -> Tuple[Dict[str, torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
         if self.training:
@@ -140,9 +157,15 @@ class Network(nn.Module):
             src_ints[..., :2, :] *= self.render_scale
             tar_ints[:, :2, :] *= self.render_scale
 
-        ms_feats = [f.unflatten(0, (B, V)) for f in self.feature_net(src_images.flatten(0, 1), levels=self._fpn_levels)]
+        fused = self.cnn_mode == "fused"
+        if fused:
+            self._channels_last_params()
+            feats = feature_net_fused(self.feature_net, src_images.flatten(0, 1), levels=self._fpn_levels)
+        else:
+            feats = self.feature_net(src_images.flatten(0, 1), levels=self._fpn_levels)
+        ms_feats = [f.unflatten(0, (B, V)) for f in feats]
         mvs_depths, range_list, vol_list, volume_list, blend_rgbs = self.depth_net(
-            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far)
+            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far, fused_cnn=fused)
         depth_range, vol_range, feat_volume, mvs_depth = range_list[-1], vol_list[-1], volume_list[-1], mvs_depths[-1]
 
         b = self.b_size
@@ -163,9 +186,13 @@ class Network(nn.Module):
         sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
         vol_cl = ops.to_channels_last(feat_volume, 8)
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
-                               self.max_num_samples, self.inv_depth, self.is_adaptive)
-
-        rgb_c = self.upsampler(out['feat'][:, 3 * b * b:])
-        rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['feat'], rgb_c, out['depth'], out['opacity'], b, self.reweighting)
+                               self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused)
+        if fused:
+            rgb_c = self.upsampler(out['dec_in'].permute(0, 3, 1, 2))          # NCHW shape over channels-last memory
+            rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], rgb_c, out['depth'], out['opacity'], b,
+                                                                self.reweighting, feat_channels_last=True)
+        else:
+            rgb_c = self.upsampler(out['feat'][:, 3 * b * b:])
+            rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['feat'], rgb_c, out['depth'], out['opacity'], b, self.reweighting)
         ret = {'rgb': rgb, 'nerf_depth': nerf_depth, 'mvs_depth': mvs_depth, 'opacity': nerf_opacity}
         return ret, mvs_depths, blend_rgbs

@@ -49,9 +49,13 @@ def padded_feat(feat_dim: int) -> int:
 def to_channels_last(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
     """(N, C, *spatial) planar -> (N, *spatial, Cpad) channels-last."""
     _dev(x)
-    x = _f32(x)
     N, Cc = x.shape[:2]
     spatial = x.shape[2:]
+    if x.dtype == torch.float32 and (c_pad is None or c_pad == Cc) and Cc % 4 == 0:
+        perm = x.permute(0, *range(2, x.dim()), 1)
+        if perm.is_contiguous():          # already channels-last in memory (cuDNN NHWC / NDHWC output): zero-copy
+            return perm
+    x = _f32(x)
     S = 1
     for s in spatial:
         S *= s
@@ -85,17 +89,23 @@ def depth_values(depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_dept
     return out
 
 
-def warp_variance(feat_cl: Tensor, proj: Tensor, depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_depth: bool) -> Tensor:
-    """feat_cl (B,V,Hs,Ws,C) channels-last -> variance volume (B,C,D,Ht,Wt)."""
+def warp_variance(feat_cl: Tensor, proj: Tensor, depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_depth: bool,
+                  out_channels_last: bool = False) -> Tensor:
+    """feat_cl (B,V,Hs,Ws,C) channels-last -> variance volume of SHAPE (B,C,D,Ht,Wt); with ``out_channels_last``
+    the memory behind it is (B,D,Ht,Wt,C), i.e. torch.channels_last_3d strides."""
     _dev(feat_cl, proj, depth_range)
     feat_cl, proj, depth_range = _f32(feat_cl), _f32(proj), _f32(depth_range)
     B, V, Hs, Ws, Cc = feat_cl.shape
     _, _, rh, rw = depth_range.shape
-    out = torch.empty((B, Cc, num_depth, Ht, Wt), device=feat_cl.device, dtype=torch.float32)
+    if out_channels_last:
+        out = torch.empty((B, num_depth, Ht, Wt, Cc), device=feat_cl.device, dtype=torch.float32)
+    else:
+        out = torch.empty((B, Cc, num_depth, Ht, Wt), device=feat_cl.device, dtype=torch.float32)
     lib = _lib.load()
     _lib.check(lib.gdb_warp_variance_fwd(feat_cl.data_ptr(), proj.data_ptr(), depth_range.data_ptr(), rh, rw, B, V, Cc, Hs, Ws,
-                                         num_depth, Ht, Wt, int(inv_depth), out.data_ptr(), _stream()), "gdb_warp_variance_fwd")
-    return out
+                                         num_depth, Ht, Wt, int(inv_depth), int(out_channels_last), out.data_ptr(), _stream()),
+               "gdb_warp_variance_fwd")
+    return out.permute(0, 4, 1, 2, 3) if out_channels_last else out
 
 
 def depth_range_from_prob(depth_range: Tensor, prob: Tensor, ci_scale: float, inv_depth: bool) -> Tuple[Tensor, Tensor, Tensor]:
@@ -185,10 +195,13 @@ class Sources(NamedTuple):
 
 
 def prepare_sources(feat: Tensor, images: Tensor, bundle_size: int, max_mip: int) -> Sources:
-    """feat (B,V,Cf,Hb,Wb) planar FPN level, images (B,V,3,H,W)."""
+    """feat (B,V,Cf,Hb,Wb) FPN level (planar or channels-last memory), images (B,V,3,H,W)."""
     _dev(feat, images)
-    feat, images = _f32(feat), _f32(images)
     B, V, Cf, Hb, Wb = feat.shape
+    feat_cl = feat.dtype == torch.float32 and Cf % 4 == 0 and feat.permute(0, 1, 3, 4, 2).is_contiguous()
+    if not feat_cl:
+        feat = _f32(feat)
+    images = _f32(images)
     H, W = images.shape[-2:]
     if (H, W) != (Hb * bundle_size, Wb * bundle_size):
         raise ValueError(f"feature map {Hb}x{Wb} x bundle {bundle_size} != image {H}x{W}")
@@ -196,8 +209,8 @@ def prepare_sources(feat: Tensor, images: Tensor, bundle_size: int, max_mip: int
     n = lib.gdb_texture_floats(B * V, Hb, Wb, Cf, max_mip)
     tex = torch.empty(n, device=feat.device, dtype=torch.float32)
     rgba = torch.empty((B * V, H, W, 4), device=feat.device, dtype=torch.float32)
-    _lib.check(lib.gdb_prepare_sources(feat.data_ptr(), images.data_ptr(), B * V, Cf, Hb, Wb, bundle_size, max_mip, tex.data_ptr(),
-                                       rgba.data_ptr(), _stream()), "gdb_prepare_sources")
+    _lib.check(lib.gdb_prepare_sources(feat.data_ptr(), int(feat_cl), images.data_ptr(), B * V, Cf, Hb, Wb, bundle_size, max_mip,
+                                       tex.data_ptr(), rgba.data_ptr(), _stream()), "gdb_prepare_sources")
     return Sources(tex, rgba, Cf, max_mip)
 
 
@@ -214,9 +227,10 @@ def texture_level(src: Sources, BV: int, Hb: int, Wb: int, level: int) -> Tensor
 # ------------------------------------------------------------------ render --
 def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: Tensor, cam: Tensor, mlp: Tensor,
                  B: int, V: int, H: int, W: int, bundle_size: int, max_samples: int, inv_depth: bool, adaptive: bool,
-                 taps: Optional[SampleList] = None, precision: int = 0) -> Dict[str, Tensor]:
+                 taps: Optional[SampleList] = None, precision: int = 0, out_channels_last: bool = False) -> Dict[str, Tensor]:
     """-> {'feat' (B,CT,Hb,Wb), 'depth' (B,Hb,Wb), 'opacity' (B,Hb,Wb)} and, when
-    ``taps`` (a SampleList) is given, the reference's packed intermediates."""
+    ``taps`` (a SampleList) is given, the reference's packed intermediates.
+    With ``out_channels_last``: {'fine' (B,Hb,Wb,3b^2), 'dec_in' (B,Hb,Wb,F+8), 'depth', 'opacity'}."""
     _dev(src.tex, src.rgba, vol_cl, depth_range, vol_range, cam, mlp)
     depth_range, vol_range, vol_cl = _f32(depth_range), _f32(vol_range), _f32(vol_cl)
     Hb, Wb = H // bundle_size, W // bundle_size
@@ -225,10 +239,16 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     F = src.feat_dim + 3
     CT = 3 * bb + F + 8
     dev = cam.device
-    out_feat = torch.empty((B, CT, Hb, Wb), device=dev, dtype=torch.float32)
     out_depth = torch.empty((B, Hb, Wb), device=dev, dtype=torch.float32)
     out_opac = torch.empty((B, Hb, Wb), device=dev, dtype=torch.float32)
-    res = {"feat": out_feat, "depth": out_depth, "opacity": out_opac}
+    if out_channels_last:
+        out_feat = torch.empty((B, Hb, Wb, 3 * bb), device=dev, dtype=torch.float32)
+        out_dec = torch.empty((B, Hb, Wb, F + 8), device=dev, dtype=torch.float32)
+        res = {"fine": out_feat, "dec_in": out_dec, "depth": out_depth, "opacity": out_opac}
+    else:
+        out_feat = torch.empty((B, CT, Hb, Wb), device=dev, dtype=torch.float32)
+        out_dec = None
+        res = {"feat": out_feat, "depth": out_depth, "opacity": out_opac}
     tp = None
     if taps is not None:
         S = taps.total
@@ -243,22 +263,33 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     _lib.check(lib.gdb_render_fused_fwd(src.rgba.data_ptr(), src.tex.data_ptr(), vol_cl.data_ptr(), depth_range.data_ptr(),
                                         vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], mlp.data_ptr(), B, V, H, W, bundle_size,
                                         src.feat_dim, D, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
-                                        out_feat.data_ptr(), out_depth.data_ptr(), out_opac.data_ptr(),
+                                        int(out_channels_last), out_feat.data_ptr(), _p(out_dec), out_depth.data_ptr(), out_opac.data_ptr(),
                                         C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
     return res
 
 
-def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bundle_size: int, reweighting: bool):
-    """rgb = dec + pixel_shuffle(feat[:, :3b^2]) (network.py:175-182)."""
+def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bundle_size: int, reweighting: bool,
+                    feat_channels_last: bool = False):
+    """rgb = dec + pixel_shuffle(feat[:, :3b^2]) (network.py:175-182).  ``feat`` is (B,CT,Hb,Wb) planar or, with
+    ``feat_channels_last``, (B,Hb,Wb,C) holding at least the 3b^2 fine-colour channels; ``dec`` (B,3,H,W) in either
+    memory format."""
     _dev(feat, dec, bdepth, bopac)
-    feat, dec, bdepth, bopac = _f32(feat), _f32(dec), _f32(bdepth), _f32(bopac)
-    B, CT, Hb, Wb = feat.shape
+    layout = 1 if feat_channels_last else 0
+    if dec.dtype == torch.float32 and not dec.is_contiguous() and dec.permute(0, 2, 3, 1).is_contiguous():
+        layout |= 2
+    else:
+        dec = _f32(dec)
+    feat, bdepth, bopac = _f32(feat), _f32(bdepth), _f32(bopac)
+    if feat_channels_last:
+        B, Hb, Wb, CT = feat.shape
+    else:
+        B, CT, Hb, Wb = feat.shape
     H, W = Hb * bundle_size, Wb * bundle_size
     rgb = torch.empty((B, 3, H, W), device=feat.device, dtype=torch.float32)
     depth = torch.empty((B, H, W), device=feat.device, dtype=torch.float32)
     opac = torch.empty((B, H, W), device=feat.device, dtype=torch.float32)
     lib = _lib.load()
     _lib.check(lib.gdb_assemble_output(feat.data_ptr(), CT, dec.data_ptr(), bdepth.data_ptr(), bopac.data_ptr(), B, Hb, Wb, bundle_size,
-                                       int(reweighting), rgb.data_ptr(), depth.data_ptr(), opac.data_ptr(), _stream()),
+                                       int(reweighting), layout, rgb.data_ptr(), depth.data_ptr(), opac.data_ptr(), _stream()),
                "gdb_assemble_output")
     return rgb, depth, opac

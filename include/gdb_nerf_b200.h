@@ -62,10 +62,12 @@ int gdb_depth_values(const float* depth_range, int rh, int rw, int B, int D, int
 /* Homography warp + population variance over views, replaces
  * build_feature_volume depth_net.py:424-476 fused with get_depth_values.
  * feat_cl (B,V,Hs,Ws,C) channels-last, C in {8,16,32}; proj (B,V,3,4);
- * depth_range as above -> variance (B,C,D,Ht,Wt) (NCDHW, what conv3d takes). */
+ * depth_range as above -> variance (B,C,D,Ht,Wt) (NCDHW, the reference's
+ * layout) or, with out_channels_last != 0, (B,D,Ht,Wt,C) (NDHWC: what cuDNN's
+ * channels-last 3-D convolutions consume without a layout conversion).        */
 int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw,
                           int B, int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth,
-                          float* variance, void* stream);
+                          int out_channels_last, float* variance, void* stream);
 
 /* Depth regression -> confidence interval, replaces depth_regression
  * depth_net.py:479-514 (+ vol_range = depth_values[:, [0,-1]], :179).
@@ -106,12 +108,13 @@ int gdb_bundle_emit(const float* depth_range, const float* vol_range, const floa
  * (bundle_sampler.py:355-359): feature+rgb texture with its mip chain
  * (channels-last, F=Cf+3 padded to FP=roundup4(F)) and RGBA-interleaved
  * full-resolution images.
- * feat (B,V,Cf,Hb,Wb) planar; images (B,V,3,H,W) planar, H=Hb*b, W=Wb*b.
+ * feat (B,V,Cf,Hb,Wb) planar, or (B,V,Hb,Wb,Cf) when feat_channels_last != 0;
+ * images (B,V,3,H,W) planar, H=Hb*b, W=Wb*b.
  * tex: levels 0..L concatenated, level k is (B*V, Hb>>k, Wb>>k, FP).
  * rgba (B*V,H,W,4).  Hb, Wb divisible by 2^L.                                 */
 int64_t gdb_texture_floats(int BV, int Hb, int Wb, int feat_dim, int max_mip_level);
-int gdb_prepare_sources(const float* feat, const float* images, int BV, int Cf, int Hb, int Wb, int bundle_size,
-                        int max_mip_level, float* tex, float* rgba, void* stream);
+int gdb_prepare_sources(const float* feat, int feat_channels_last, const float* images, int BV, int Cf, int Hb, int Wb,
+                        int bundle_size, int max_mip_level, float* tex, float* rgba, void* stream);
 
 /* --------------------------------------------------------- render --------- */
 /* Fused per-bundle render, replaces BundleSampler.sample/encode
@@ -122,7 +125,10 @@ int gdb_prepare_sources(const float* feat, const float* images, int BV, int Cf, 
  * vol_cl (B,D,Hb,Wb,8) channels-last feature volume; tex/rgba from
  * gdb_prepare_sources; depth_range, vol_range (B,2,Hb,Wb); mlp: packed
  * parameter block.
- * out_feat (B, 3b^2+F+8, Hb, Wb) planar; out_depth, out_opacity (B,Hb,Wb).
+ * out_feat (B, 3b^2+F+8, Hb, Wb) planar (the reference's layout, out_dec
+ * unused); or, with out_channels_last != 0, out_feat (B,Hb,Wb,3b^2) = the fine
+ * colours and out_dec (B,Hb,Wb,F+8) = the decoder's input, both channels-last.
+ * out_depth, out_opacity (B,Hb,Wb).
  *
  * Optional taps (any may be null; offsets required if any is non-null): the
  * reference's intermediates in its packed sample order -
@@ -142,15 +148,16 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          const float* vol_range, const float* cam, int cam_stride, const float* mlp,
                          int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int max_samples,
                          int max_mip_level, int inv_depth, int adaptive, int precision /* 0 = fp32 */,
-                         float* out_feat, float* out_depth, float* out_opacity, const gdb_render_taps* taps,
-                         void* stream);
+                         int out_channels_last, float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
+                         const gdb_render_taps* taps, void* stream);
 
 /* Output assembly, replaces network.py:175-182 minus the decoder CNN:
  * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
  * and the bilinear xb up-sampling of depth and opacity.
- * feat (B,Ctot,Hb,Wb), dec (B,3,H,W) -> rgb (B,3,H,W), depth/opacity (B,H,W). */
+ * feat (B,Ctot,Hb,Wb), dec (B,3,H,W) -> rgb (B,3,H,W), depth/opacity (B,H,W).
+ * layout bit 0: feat is channels-last (B,Hb,Wb,Ctot); bit 1: dec is (B,H,W,3). */
 int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
-                        int B, int Hb, int Wb, int bundle_size, int reweighting,
+                        int B, int Hb, int Wb, int bundle_size, int reweighting, int layout,
                         float* rgb, float* depth, float* opacity, void* stream);
 
 #ifdef __cplusplus

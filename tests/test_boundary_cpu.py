@@ -98,6 +98,6 @@ def test_ops_refuse_cpu_tensors():
 def test_c_abi_argument_errors_without_gpu():
     """Argument validation happens before any CUDA call, so it can be exercised here."""
     lib = _lib.load()
-    assert lib.gdb_warp_variance_fwd(None, None, None, 1, 1, 1, 3, 32, 8, 8, 8, 4, 4, 0, None, None) == -1
+    assert lib.gdb_warp_variance_fwd(None, None, None, 1, 1, 1, 3, 32, 8, 8, 8, 4, 4, 0, 0, None, None) == -1
     assert b"null" in lib.gdb_last_error_string()
     assert lib.gdb_texture_floats(3, 256, 320, 16, 3) == 3 * 20 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40)

@@ -68,6 +68,10 @@ def test_warp_variance(golden):
         ref_noise = _md(ref, truth)                                             # the reference's own fp32 error
         assert _md(var, truth) <= max(1e-4 * scale, 2.0 * ref_noise)
         assert _md(var, ref) <= 5e-4 * scale
+        # channels-last output (what the cuDNN NDHWC path consumes): same values, other memory order
+        var_cl = ops.warp_variance(feat_cl, proj.to(DEV), rng.to(DEV), D, Ht, Wt, cfg.mvs.inv_depth[s], out_channels_last=True)
+        assert var_cl.shape == var.shape and var_cl.permute(0, 2, 3, 4, 1).is_contiguous()
+        assert torch.equal(var_cl.contiguous(), var)
 
 
 # ------------------------------------------------------------------ K2 / a3
@@ -169,6 +173,16 @@ def _render(golden, prefix, adaptive):
                              cfg.mvs.inv_depth[-1], adaptive)
     for k in ("feat", "depth", "opacity"):
         assert torch.equal(out[k], plain[k])                                   # taps do not change the result
+    split = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples,
+                             cfg.mvs.inv_depth[-1], adaptive, out_channels_last=True)
+    R = 3 * b * b                                                              # channels-last split output: same values
+    assert torch.equal(split["fine"].permute(0, 3, 1, 2), plain["feat"][:, :R])
+    assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), plain["feat"][:, R:])
+    assert torch.equal(split["depth"], plain["depth"])
+    # channels-last feature input to the source preparation: same texture
+    feat_nhwc = tex_ref[:, :, :feat_dim].to(DEV).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    src2 = ops.prepare_sources(feat_nhwc, golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
+    assert torch.equal(src2.tex, src.tex) and torch.equal(src2.rgba, src.rgba)
     return out, (B, Hb, Wb)
 
 
@@ -241,7 +255,7 @@ def test_c_abi_rejects_unsupported_combinations():
     from gdb_nerf_b200 import _lib
     lib = _lib.load()
     z = torch.zeros(64, device=DEV)
-    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 1, 1, 5, 32, 2, 2, 4, 2, 2, 0, z.data_ptr(), None)
+    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 1, 1, 5, 32, 2, 2, 4, 2, 2, 0, 0, z.data_ptr(), None)
     assert code == -2 and b"not instantiated" in lib.gdb_last_error_string()
-    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 3, 1, 1, 3, 32, 2, 2, 4, 2, 2, 0, z.data_ptr(), None)
+    code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 3, 1, 1, 3, 32, 2, 2, 4, 2, 2, 0, 0, z.data_ptr(), None)
     assert code == -1

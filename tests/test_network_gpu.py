@@ -27,8 +27,9 @@ def _fp32_cnn():
     torch.backends.cudnn.allow_tf32 = old
 
 
+@pytest.mark.parametrize("cnn_mode", ["fused", "modules"])
 @pytest.mark.parametrize("case", ["dtu_b2", "nerf_b4"])
-def test_network_forward_matches_reference(case):
+def test_network_forward_matches_reference(case, cnn_mode):
     """Same weights, same batch dict -> same (ret, mvs_depths, blend_rgbs) as the reference's Network.forward."""
     g = load_golden(case)
     spec = CASE_SPECS[case]
@@ -36,6 +37,7 @@ def test_network_forward_matches_reference(case):
     shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     net.load_state_dict(synth_state_dict(shapes, seed=1), strict=True)
     net = net.to(DEV).eval()
+    net.cnn_mode = cnn_mode
     batch = make_batch(spec["B"], spec["V"], spec["H"], spec["W"], spec["near"], spec["far"], spec["focal"], seed=3,
                        images=spec["images"], tilt=spec["tilt"])
     assert np.array_equal(batch["src_views"]["rgb"].numpy(), g.np("in_rgb"))
