@@ -1,0 +1,57 @@
+"""Multi-GPU partitioning of the rendering path.
+
+Target views are independent units (the reference itself loops over the batch,
+bundle_sampler.py:318): a sweep is sharded round-robin over one process per
+GPU with no collective in the data path.  The only communication is the timing
+reduction of a benchmark (max over ranks) and, optionally, gathering the
+rendered images on rank 0.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Indices of the target views rank ``rank`` renders: views[rank::world]."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    return list(range(rank, n_views, world))
+
+
+def shard_rows(n_rows: int, rank: int, world: int, align: int = 8) -> range:
+    """Contiguous bundle-row tile of one large view (rows aligned to the mip block)."""
+    blocks = (n_rows + align - 1) // align
+    lo = (blocks * rank) // world * align
+    hi = min((blocks * (rank + 1)) // world * align, n_rows)
+    return range(lo, hi)
+
+
+def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
+    """Timing reduction used by bench.py: every rank contributes its elapsed time, all get the max."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def gather_images(local: torch.Tensor, view_ids: Sequence[int], n_views: int) -> Optional[torch.Tensor]:
+    """Collect the rendered images of all ranks on rank 0 in view order (views, 3, H, W)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per_rank = (n_views + world - 1) // world
+    pad = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0)
+    if rank != 0:
+        return None
+    out = torch.empty((n_views,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        ids = shard_views(n_views, r, world)
+        out[ids] = bufs[r][: len(ids)]
+    return out

@@ -1,0 +1,78 @@
+"""world_size-2 gloo tests of the N>1 host logic (view sharding, timing reduction, image gather)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gdb_nerf_b200.sharding import gather_images, max_over_ranks, shard_rows, shard_views
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_views, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ids = shard_views(n_views, rank, world)
+        # "render": image content encodes the view id
+        local = torch.stack([torch.full((3, 2, 2), float(i)) for i in ids]) if ids else torch.zeros(0, 3, 2, 2)
+        elapsed = max_over_ranks(10.0 + rank)               # rank 1 is slower
+        full = gather_images(local, ids, n_views)
+        dist.barrier()
+        q.put((rank, ids, elapsed, None if full is None else full[:, 0, 0, 0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_view_sharding_gloo():
+    world, n_views = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_views, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = [r[1] for r in res]
+    assert sorted(ids[0] + ids[1]) == list(range(n_views)) and not set(ids[0]) & set(ids[1])      # disjoint cover
+    assert all(r[2] == 11.0 for r in res)                                                        # max over ranks
+    assert res[0][3] == [0.0, 1.0, 2.0, 3.0, 4.0] and res[1][3] is None                          # gathered in view order
+
+
+def test_shard_helpers_single_process():
+    assert shard_views(8, 3, 8) == [3] and shard_views(200, 7, 8) == list(range(7, 200, 8))
+    rows = [shard_rows(256, r, 8) for r in range(8)]
+    assert rows[0].start == 0 and rows[-1].stop == 256
+    assert all(a.stop == b.start for a, b in zip(rows, rows[1:])) and all(r.start % 8 == 0 for r in rows)
+    assert max_over_ranks(3.5) == 3.5
+
+
+def test_reference_loader_mechanism(tmp_path, monkeypatch):
+    """networks/make_network.py:5-9 does imp.load_source(cfg.network_module, cfg.network_path).Network(cfg)."""
+    import importlib.util
+    import sys
+    from conftest import ROOT
+    from gdb_nerf_b200.config import make_cfg
+    spec = importlib.util.spec_from_file_location("imp_shim", os.path.join(ROOT, "oracle", "ref_shims", "imp.py"))
+    imp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(imp)
+    name = "gdb_nerf_b200.network"
+    saved = sys.modules.pop(name, None)
+    try:
+        mod = imp.load_source(name, os.path.join(ROOT, name.replace(".", "/") + ".py"))
+        net = mod.Network(make_cfg("dtu_eval"))
+        assert sum(p.numel() for p in net.parameters()) == 962311
+    finally:
+        if saved is not None:
+            sys.modules[name] = saved
