@@ -14,114 +14,9 @@
 // waits on its gathers another runs its MLP.  The MLP weights (packed [K][N])
 // live in shared memory once per CTA; each lane keeps its activations in a
 // private shared-memory column ([row][lane], bank = lane: conflict-free).
-#include "gdb_sampling.cuh"
+#include "gdb_render_common.cuh"
 
 namespace gdb {
-
-struct RenderParams {
-  const float* rgba;      // (B*V, H, W, 4)
-  const float* tex;       // mip chain, level k: (B*V, Hb>>k, Wb>>k, FP)
-  const float* vol;       // (B, D, Hb, Wb, 8)
-  const float* depth_range;
-  const float* vol_range;
-  const float* cam;
-  const float* mlp;
-  float* out_feat;        // (B, CT, Hb, Wb) planar, or (B, Hb, Wb, R) when out_cl
-  float* out_dec;         // (B, Hb, Wb, F+8) when out_cl
-  float* out_depth;
-  float* out_opacity;
-  // optional taps
-  const int32_t* offsets;
-  int64_t S_total;
-  float* tap_rfd;
-  float* tap_vox;
-  float* tap_sigma;
-  float* tap_feat;
-  float* tap_w;
-  int64_t tex_level[4];
-  int cam_stride;
-  int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
-};
-
-template <int N>
-__device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restrict__ wrow, float x) {
-#pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    float4 w = *reinterpret_cast<const float4*>(wrow + n);
-    acc[n + 0] = fmaf(w.x, x, acc[n + 0]);
-    acc[n + 1] = fmaf(w.y, x, acc[n + 1]);
-    acc[n + 2] = fmaf(w.z, x, acc[n + 2]);
-    acc[n + 3] = fmaf(w.w, x, acc[n + 3]);
-  }
-}
-template <int N>
-__device__ __forceinline__ void load_row(float (&acc)[N], const float* __restrict__ row) {
-#pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    float4 w = *reinterpret_cast<const float4*>(row + n);
-    acc[n + 0] = w.x; acc[n + 1] = w.y; acc[n + 2] = w.z; acc[n + 3] = w.w;
-  }
-}
-template <int N>
-__device__ __forceinline__ float dot_row(const float (&x)[N], const float* __restrict__ row) {
-  float s = 0.f;
-#pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    float4 w = *reinterpret_cast<const float4*>(row + n);
-    s = fmaf(w.x, x[n + 0], s); s = fmaf(w.y, x[n + 1], s); s = fmaf(w.z, x[n + 2], s); s = fmaf(w.w, x[n + 3], s);
-  }
-  return s;
-}
-
-__device__ __forceinline__ void unit3(float& x, float& y, float& z) {
-  float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);   // F.normalize(eps=1e-12)
-  x /= n; y /= n; z /= n;
-}
-
-// border-clamped bilinear setup for grid_sample(align_corners=False, padding 'border')
-struct Bilin {
-  int o00, o10, o01, o11;   // texel offsets (in texels)
-  float w00, w10, w01, w11;
-};
-__device__ __forceinline__ Bilin bilin_border(float gx, float gy, int Wd, int Hd) {
-  float ix = fminf(fmaxf(((gx + 1.f) * (float)Wd - 1.f) * 0.5f, 0.f), (float)(Wd - 1));
-  float iy = fminf(fmaxf(((gy + 1.f) * (float)Hd - 1.f) * 0.5f, 0.f), (float)(Hd - 1));
-  float x0f = floorf(ix), y0f = floorf(iy);
-  float tx = ix - x0f, ty = iy - y0f;
-  int x0 = (int)x0f, y0 = (int)y0f;
-  int x1 = min(x0 + 1, Wd - 1), y1 = min(y0 + 1, Hd - 1);   // weight is 0 whenever the clamp bites
-  Bilin r;
-  r.o00 = y0 * Wd + x0; r.o10 = y0 * Wd + x1; r.o01 = y1 * Wd + x0; r.o11 = y1 * Wd + x1;
-  r.w00 = (1.f - tx) * (1.f - ty); r.w10 = tx * (1.f - ty); r.w01 = (1.f - tx) * ty; r.w11 = tx * ty;
-  return r;
-}
-
-// nvdiffrast indexTextureLinear, boundary 'clamp'
-struct TexTap {
-  int o00, o10, o01, o11;
-  float fu, fv;
-};
-__device__ __forceinline__ TexTap tex_tap(float u01, float v01, int w, int h) {
-  float u = fminf(fmaxf(u01 * (float)w - 0.5f, 0.f), (float)(w - 1));
-  float v = fminf(fmaxf(v01 * (float)h - 0.5f, 0.f), (float)(h - 1));
-  bool cu = (u == 0.f) || (u == (float)(w - 1));
-  bool cv = (v == 0.f) || (v == (float)(h - 1));
-  int iu0 = (int)floorf(u), iv0 = (int)floorf(v);
-  int iu1 = iu0 + (cu ? 0 : 1), iv1 = iv0 + (cv ? 0 : 1);
-  TexTap t;
-  t.fu = u - (float)iu0; t.fv = v - (float)iv0;
-  t.o00 = iv0 * w + iu0; t.o10 = iv0 * w + iu1; t.o01 = iv1 * w + iu0; t.o11 = iv1 * w + iu1;
-  return t;
-}
-__device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
-__device__ __forceinline__ float4 bilerp4(float4 a00, float4 a10, float4 a01, float4 a11, float fu, float fv) {
-  float4 r;
-  r.x = lerpf(lerpf(a00.x, a10.x, fu), lerpf(a01.x, a11.x, fu), fv);
-  r.y = lerpf(lerpf(a00.y, a10.y, fu), lerpf(a01.y, a11.y, fu), fv);
-  r.z = lerpf(lerpf(a00.z, a10.z, fu), lerpf(a01.z, a11.z, fu), fv);
-  r.w = lerpf(lerpf(a00.w, a10.w, fu), lerpf(a01.w, a11.w, fu), fv);
-  return r;
-}
 
 template <int BS, int FEAT_DIM, int V>
 struct RenderCfg {
@@ -592,7 +487,8 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               "gdb_render_fused_fwd: image %dx%d not divisible by bundle size %d", H, W, bundle_size);
   GDB_REQUIRE(max_samples >= 1 && max_samples <= 32, GDB_E_BADARG, "gdb_render_fused_fwd: max_samples must be 1..32");
   GDB_REQUIRE(max_mip_level >= 0 && max_mip_level <= 3, GDB_E_UNSUPPORTED, "gdb_render_fused_fwd: max_mip_level must be 0..3");
-  GDB_REQUIRE(precision == 0, GDB_E_UNSUPPORTED, "gdb_render_fused_fwd: precision %d not built (0 = fp32)", precision);
+  GDB_REQUIRE(precision == 0 || precision == 1, GDB_E_UNSUPPORTED,
+              "gdb_render_fused_fwd: precision %d not built (0 = fp32 SIMT, 1 = fp16-operand tcgen05 MLP)", precision);
   GDB_REQUIRE(aligned16(rgba) && aligned16(tex) && aligned16(vol_cl) && aligned16(mlp), GDB_E_ALIGN,
               "gdb_render_fused_fwd: rgba/tex/vol/mlp must be 16-byte aligned");
   GDB_REQUIRE(cam_stride == CAM_HEAD + CAM_VIEW * V, GDB_E_BADARG, "gdb_render_fused_fwd: cam_stride %d != %d", cam_stride,
@@ -616,6 +512,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   p.tex_level[0] = 0;
   for (int k = 1; k <= 3; ++k) p.tex_level[k] = p.tex_level[k - 1] + (int64_t)B * V * (p.Hb >> (k - 1)) * (p.Wb >> (k - 1)) * FPad;
   cudaStream_t st = as_stream(stream);
+  if (precision == 1) return render_tc_dispatch(p, bundle_size, feat_dim, V, st);
 #define GDB_R(BSZ, FD, VV) \
   if (bundle_size == BSZ && feat_dim == FD && V == VV) return launch_render<BSZ, FD, VV>(p, st);
   GDB_R(2, 16, 2) GDB_R(2, 16, 3) GDB_R(2, 16, 4) GDB_R(4, 32, 2) GDB_R(4, 32, 3) GDB_R(4, 32, 4)

@@ -1,0 +1,116 @@
+// Device helpers shared by the fused render kernels (fp32 SIMT and tcgen05 variants).
+#pragma once
+#include "gdb_sampling.cuh"
+
+namespace gdb {
+
+struct RenderParams {
+  const float* rgba;      // (B*V, H, W, 4)
+  const float* tex;       // mip chain, level k: (B*V, Hb>>k, Wb>>k, FP)
+  const float* vol;       // (B, D, Hb, Wb, 8)
+  const float* depth_range;
+  const float* vol_range;
+  const float* cam;
+  const float* mlp;
+  float* out_feat;        // (B, CT, Hb, Wb) planar, or (B, Hb, Wb, R) when out_cl
+  float* out_dec;         // (B, Hb, Wb, F+8) when out_cl
+  float* out_depth;
+  float* out_opacity;
+  // optional taps
+  const int32_t* offsets;
+  int64_t S_total;
+  float* tap_rfd;
+  float* tap_vox;
+  float* tap_sigma;
+  float* tap_feat;
+  float* tap_w;
+  int64_t tex_level[4];
+  int cam_stride;
+  int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
+};
+
+template <int N>
+__device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restrict__ wrow, float x) {
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    float4 w = *reinterpret_cast<const float4*>(wrow + n);
+    acc[n + 0] = fmaf(w.x, x, acc[n + 0]);
+    acc[n + 1] = fmaf(w.y, x, acc[n + 1]);
+    acc[n + 2] = fmaf(w.z, x, acc[n + 2]);
+    acc[n + 3] = fmaf(w.w, x, acc[n + 3]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_row(float (&acc)[N], const float* __restrict__ row) {
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    float4 w = *reinterpret_cast<const float4*>(row + n);
+    acc[n + 0] = w.x; acc[n + 1] = w.y; acc[n + 2] = w.z; acc[n + 3] = w.w;
+  }
+}
+template <int N>
+__device__ __forceinline__ float dot_row(const float (&x)[N], const float* __restrict__ row) {
+  float s = 0.f;
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    float4 w = *reinterpret_cast<const float4*>(row + n);
+    s = fmaf(w.x, x[n + 0], s); s = fmaf(w.y, x[n + 1], s); s = fmaf(w.z, x[n + 2], s); s = fmaf(w.w, x[n + 3], s);
+  }
+  return s;
+}
+
+__device__ __forceinline__ void unit3(float& x, float& y, float& z) {
+  float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);   // F.normalize(eps=1e-12)
+  x /= n; y /= n; z /= n;
+}
+
+// border-clamped bilinear setup for grid_sample(align_corners=False, padding 'border')
+struct Bilin {
+  int o00, o10, o01, o11;   // texel offsets (in texels)
+  float w00, w10, w01, w11;
+};
+__device__ __forceinline__ Bilin bilin_border(float gx, float gy, int Wd, int Hd) {
+  float ix = fminf(fmaxf(((gx + 1.f) * (float)Wd - 1.f) * 0.5f, 0.f), (float)(Wd - 1));
+  float iy = fminf(fmaxf(((gy + 1.f) * (float)Hd - 1.f) * 0.5f, 0.f), (float)(Hd - 1));
+  float x0f = floorf(ix), y0f = floorf(iy);
+  float tx = ix - x0f, ty = iy - y0f;
+  int x0 = (int)x0f, y0 = (int)y0f;
+  int x1 = min(x0 + 1, Wd - 1), y1 = min(y0 + 1, Hd - 1);   // weight is 0 whenever the clamp bites
+  Bilin r;
+  r.o00 = y0 * Wd + x0; r.o10 = y0 * Wd + x1; r.o01 = y1 * Wd + x0; r.o11 = y1 * Wd + x1;
+  r.w00 = (1.f - tx) * (1.f - ty); r.w10 = tx * (1.f - ty); r.w01 = (1.f - tx) * ty; r.w11 = tx * ty;
+  return r;
+}
+
+// nvdiffrast indexTextureLinear, boundary 'clamp'
+struct TexTap {
+  int o00, o10, o01, o11;
+  float fu, fv;
+};
+__device__ __forceinline__ TexTap tex_tap(float u01, float v01, int w, int h) {
+  float u = fminf(fmaxf(u01 * (float)w - 0.5f, 0.f), (float)(w - 1));
+  float v = fminf(fmaxf(v01 * (float)h - 0.5f, 0.f), (float)(h - 1));
+  bool cu = (u == 0.f) || (u == (float)(w - 1));
+  bool cv = (v == 0.f) || (v == (float)(h - 1));
+  int iu0 = (int)floorf(u), iv0 = (int)floorf(v);
+  int iu1 = iu0 + (cu ? 0 : 1), iv1 = iv0 + (cv ? 0 : 1);
+  TexTap t;
+  t.fu = u - (float)iu0; t.fv = v - (float)iv0;
+  t.o00 = iv0 * w + iu0; t.o10 = iv0 * w + iu1; t.o01 = iv1 * w + iu0; t.o11 = iv1 * w + iu1;
+  return t;
+}
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
+__device__ __forceinline__ float4 bilerp4(float4 a00, float4 a10, float4 a01, float4 a11, float fu, float fv) {
+  float4 r;
+  r.x = lerpf(lerpf(a00.x, a10.x, fu), lerpf(a01.x, a11.x, fu), fv);
+  r.y = lerpf(lerpf(a00.y, a10.y, fu), lerpf(a01.y, a11.y, fu), fv);
+  r.z = lerpf(lerpf(a00.z, a10.z, fu), lerpf(a01.z, a11.z, fu), fv);
+  r.w = lerpf(lerpf(a00.w, a10.w, fu), lerpf(a01.w, a11.w, fu), fv);
+  return r;
+}
+
+
+// tensor-core (tcgen05) variant, gdb_render_tc.cu
+int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st);
+
+}  // namespace gdb

@@ -119,6 +119,9 @@ class Network(nn.Module):
         # "modules": the plain nn.Module graph in the reference's NCHW layout.  Same arithmetic either way.
         self.cnn_mode = "fused"
         self._cl_ready = False
+        # 0: fp32 SIMT MLP inside the fused render kernel (1e-4 class); 1: fp16-operand tcgen05 MLP with fp32
+        # accumulation (the north star's reduced-precision class, 2e-3; measured ~1e-4)
+        self.mlp_precision = 0
 
     def _channels_last_params(self) -> None:
         if not self._cl_ready:
@@ -186,7 +189,8 @@ class Network(nn.Module):
         sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
         vol_cl = ops.to_channels_last(feat_volume, 8)
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
-                               self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused)
+                               self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
+                               precision=self.mlp_precision)
         if fused:
             rgb_c = self.upsampler(out['dec_in'].permute(0, 3, 1, 2))          # NCHW shape over channels-last memory
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], rgb_c, out['depth'], out['opacity'], b,

@@ -259,3 +259,42 @@ def test_c_abi_rejects_unsupported_combinations():
     assert code == -2 and b"not instantiated" in lib.gdb_last_error_string()
     code = lib.gdb_warp_variance_fwd(z.data_ptr(), z.data_ptr(), z.data_ptr(), 3, 1, 1, 3, 32, 2, 2, 4, 2, 2, 0, 0, z.data_ptr(), None)
     assert code == -1
+
+
+# ------------------------------------------------------------------ K3, tensor-core MLP variant (precision = 1)
+@pytest.mark.parametrize("prefix", ["", "inj_"])
+def test_render_fused_tensor_core_variant(golden, prefix):
+    """fp16-operand tcgen05 MLP: same indices/geometry, rgb/depth within the 2e-3 class of BASELINE.json's north star."""
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    adaptive = True if prefix else cfg.nerf.is_adaptive
+    tex_ref = golden.t("tex_nchw")
+    B, V, F, Hb, Wb = tex_ref.shape
+    feat_dim = F - 3
+    cam = _cam(golden, cfg)
+    dr, vr = golden.t(prefix + "depth_range").to(DEV), golden.t(prefix + "vol_range").to(DEV)
+    sl = ops.sample_bundles(dr, vr, cam, b, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive, want_rays=False)
+    src = ops.prepare_sources(tex_ref[:, :, :feat_dim].contiguous().to(DEV), golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(golden.t("feat_volume").to(DEV), 8)
+    mlp = ops.pack_mlp(golden.mlp(), feat_dim, device=DEV)
+    args = (src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive)
+    tc = ops.render_fused(*args, taps=sl, precision=1)
+    ref32 = ops.render_fused(*args, taps=sl, precision=0)
+    torch.cuda.synchronize()
+    # gathers are the same code in fp32: identical inputs to the MLP
+    assert _md(tc["rgbs_feat_dir"], ref32["rgbs_feat_dir"]) <= 1e-5
+    assert _md(tc["vox_feat"], ref32["vox_feat"]) <= 1e-5
+    # MLP in half precision operands / fp32 accumulation
+    assert _md(tc["sigma"], golden.t(prefix + "sigma")) <= 2e-3
+    assert _md(tc["sample_feat"], golden.t(prefix + "feat")) <= 2e-3
+    assert _md(tc["weights"], golden.t(prefix + "weights")) <= 2e-3
+    ref_feat = golden.t(prefix + "bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2)
+    assert _md(tc["feat"], ref_feat) <= 2e-3
+    assert _md(tc["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 2e-3 * (spec["far"] - spec["near"])
+    assert _md(tc["opacity"].reshape(-1), golden.t(prefix + "bundle_opacity")) <= 1e-5
+    # channels-last outputs of the tensor-core variant
+    split = ops.render_fused(*args, precision=1, out_channels_last=True)
+    R = 3 * b * b
+    assert torch.equal(split["fine"].permute(0, 3, 1, 2), tc["feat"][:, :R])
+    assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), tc["feat"][:, R:])

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--bf16", action="store_true")
     ap.add_argument("--no-tf32", action="store_true")
     ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--tc", action="store_true")
     args = ap.parse_args()
     torch.backends.cudnn.benchmark = args.benchmark
     if args.no_tf32:
@@ -35,6 +36,7 @@ def main():
     cfg = make_cfg(wl["recipe"])
     torch.manual_seed(0)
     net = Network(cfg).to(dev).eval()
+    net.mlp_precision = 1 if args.tc else 0
     if args.channels_last:
         net.feature_net.to(memory_format=torch.channels_last)
         net.upsampler.to(memory_format=torch.channels_last)
