@@ -150,7 +150,10 @@ struct TcCfg {
   static constexpr int A_HVI = A_GX + V * (K_GX / 8) * 2048;
   static constexpr int A_FD = A_HVI + (K_HVI / 8) * 2048;      // V buffers
   static constexpr int A_END = A_FD + V * (K_FD / 8) * 2048;
-  static constexpr int GROUP_BYTES = A_END + 128;              // + mbarrier
+  static constexpr int CAM_OFF = A_END + 128;                  // after the mbarrier: camera block of the tile's view
+  static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
+  // fine colours are gathered with the other taps (before the MLP) and kept in registers when they fit
+  static constexpr bool EARLY_RGB = (3 * BB * V <= 48);
   // TMEM columns per group
   static constexpr int T_W0 = 0;      // V x 64
   static constexpr int T_LR0 = 0;     // 64 (consumed before W0 is issued)
@@ -253,21 +256,31 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
   uint32_t parity = 0;
 
   const int HW = p.Hb * p.Wb;
-  const int NB = p.B * HW;
   const int ns = p.max_samples;
-  const int G = 32 / ns;                         // bundles per warp
-  const int tiles = (NB + 4 * G - 1) / (4 * G);  // a tile = 4 warps x G bundles
+  const int G = 32 / ns;                                   // bundles per warp
+  const int tiles_pv = (HW + 4 * G - 1) / (4 * G);         // tiles per target view (a tile = 4 warps x G bundles, one view)
+  const int tiles = p.B * tiles_pv;
   const int bl = lane / ns, slot = lane - bl * ns;
   const int seg_base = bl * ns;
   const int wq = warp & 3;
+  float* scam = reinterpret_cast<float*>(gsm + C::CAM_OFF);
+  int cur_b = -1;
 
   for (int tile = blockIdx.x * ngroups_cta + g; tile < tiles; tile += gridDim.x * ngroups_cta) {
-    const int bundle = (tile * 4 + wq) * G + bl;
-    const bool has_bundle = bl < G && bundle < NB;
-    const int bidx = has_bundle ? bundle : 0;
-    const int b = bidx / HW, pix = bidx - b * HW;
+    const int b = tile / tiles_pv;                         // uniform over the group
+    if (b != cur_b) {                                      // stage this view's camera block (128 floats for V = 3)
+      group_sync(g);
+      for (int i = row; i < CAM_HEAD + CAM_VIEW * V; i += 128) scam[i] = p.cam[(size_t)b * p.cam_stride + i];
+      group_sync(g);
+      cur_b = b;
+    }
+    const int pix_raw = ((tile - b * tiles_pv) * 4 + wq) * G + bl;
+    const bool has_bundle = bl < G && pix_raw < HW;
+    const int pix = has_bundle ? pix_raw : 0;
+    const int bidx = b * HW + pix;
+    const int bundle = bidx;
     const int yb = pix / p.Wb, xb = pix - yb * p.Wb;
-    const float* head = p.cam + (size_t)b * p.cam_stride;
+    const float* head = scam;
 
     float nr = p.depth_range[(size_t)(b * 2 + 0) * HW + pix], fr_ = p.depth_range[(size_t)(b * 2 + 1) * HW + pix];
     float vn = p.vol_range[(size_t)(b * 2 + 0) * HW + pix], vf = p.vol_range[(size_t)(b * 2 + 1) * HW + pix];
@@ -333,6 +346,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
 #pragma unroll
       for (int c = 0; c < FP; ++c) { fr[v][c] = 0.f; xv[v][c] = 0.f; }
     }
+    float col[C::EARLY_RGB ? V : 1][C::EARLY_RGB ? R : 1];     // fine colours per view (channel-major, then ray)
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const float* cv = head + CAM_HEAD + CAM_VIEW * v;
@@ -342,9 +356,31 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         float dx, dy, dz;
         geo.ray_dir(head, j, dx, dy, dz);
         float wx = fmaf(dx, z, ox), wy = fmaf(dy, z, oy), wz = fmaf(dz, z, oz);
-        ccx += fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
-        ccy += fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
-        ccz += fmaf(wx, cv[CV_E + 8], fmaf(wy, cv[CV_E + 9], fmaf(wz, cv[CV_E + 10], cv[CV_E + 11])));
+        float cx = fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
+        float cy = fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
+        float cz = fmaf(wx, cv[CV_E + 8], fmaf(wy, cv[CV_E + 9], fmaf(wz, cv[CV_E + 10], cv[CV_E + 11])));
+        ccx += cx; ccy += cy; ccz += cz;
+        if constexpr (C::EARLY_RGB) {
+          // fine colour of ray j in view v (bundle_sampler.py:327-337): issued together with the other gathers
+          float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
+          float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
+          float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+          float gx = 2.f * (ix / iz) / (float)p.W - 1.f, gy = 2.f * (iy / iz) / (float)p.H - 1.f;
+          float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (active) {
+            Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
+            const float* ib = p.rgba + (size_t)(b * V + v) * p.H * p.W * 4;
+            c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o00 * 4), bl4.w00);
+            c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o10 * 4), bl4.w10);
+            c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o01 * 4), bl4.w01);
+            c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o11 * 4), bl4.w11);
+            if (p.tap_rfd) {
+              float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow) * C::RFD;
+              tp[0 * BB + j] = c4.x; tp[1 * BB + j] = c4.y; tp[2 * BB + j] = c4.z;
+            }
+          }
+          col[v][0 * BB + j] = c4.x; col[v][1 * BB + j] = c4.y; col[v][2 * BB + j] = c4.z;
+        }
       }
       ccx *= (1.f / BB); ccy *= (1.f / BB); ccz *= (1.f / BB);
       float dist = sqrtf(ccx * ccx + ccy * ccy + ccz * ccz);
@@ -470,31 +506,33 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     mbar_wait(mbar, parity); parity ^= 1;
     tc_fence_after();
     {
-      float im[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) im[k] = 0.f;
-      float aw[V], gsave[V][32];
+      // pass 1: aggregation logits (TMEM reads are cheap; re-reading keeps only one view's 32 columns live)
+      float aw[V];
       float amax = -1e30f;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        tmem_ld32(tmem_row + C::T_G + v * 32, gsave[v]);
+        float gv[32];
+        tmem_ld32(tmem_row + C::T_G + v * 32, gv);
         float s = vec[C::X_SCAL + 0];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          gsave[v][k] = fmaxf(gsave[v][k] + vec[C::X_GLOB_B + k], 0.f);
-          s = fmaf(gsave[v][k], vec[C::X_AGG_W + k], s);
-        }
+        for (int k = 0; k < 32; ++k) s = fmaf(fmaxf(gv[k] + vec[C::X_GLOB_B + k], 0.f), vec[C::X_AGG_W + k], s);
         aw[v] = fmaxf(s, 0.f);
         amax = fmaxf(amax, aw[v]);
       }
       float asum = 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) { aw[v] = expf(aw[v] - amax); asum += aw[v]; }
+      // pass 2: softmax-weighted sum over views
+      float im[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) im[k] = 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
+        float gv[32];
+        tmem_ld32(tmem_row + C::T_G + v * 32, gv);
         float a = aw[v] / asum;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) im[k] = fmaf(gsave[v][k], a, im[k]);
+        for (int k = 0; k < 32; ++k) im[k] = fmaf(fmaxf(gv[k] + vec[C::X_GLOB_B + k], 0.f), a, im[k]);
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -631,6 +669,17 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     float* od = p.out_cl ? p.out_dec + (size_t)bidx * (F + 8) - R : of;
     float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
+    if constexpr (C::EARLY_RGB) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) a = fmaf(col[v][c], wv[v], a);
+        if (tf) tf[c] = a;
+        float s = seg_sum(wgt * a);
+        if (writer) of[(size_t)c * ostr] = s;
+      }
+    } else {
 #pragma unroll 1
     for (int j = 0; j < BB; ++j) {
       float dx, dy, dz;
@@ -667,6 +716,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
       if (writer) {
         of[(size_t)(0 * BB + j) * ostr] = sr; of[(size_t)(1 * BB + j) * ostr] = sg; of[(size_t)(2 * BB + j) * ostr] = sb;
       }
+    }
     }
 #pragma unroll
     for (int c = 0; c < F; ++c) {

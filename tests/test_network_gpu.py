@@ -114,10 +114,14 @@ def test_full_size_sampling_properties_and_counts():
     assert torch.equal(idx, torch.repeat_interleave(torch.arange(NB), counts))
 
 
-def test_full_size_render_against_oracle_and_view_symmetry():
-    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs()
+@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("nerf", 0), ("nerf", 1)])
+def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
+    """BASELINE.json sizes (DTU 512x640 2x2 bundles, NeRF-synthetic 800x800 4x4 bundles): parity with the oracle on
+    identical inputs plus size-independent properties.  precision 1 = tensor-core MLP (2e-3 class)."""
+    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs(workload)
     b = cfg.nerf.bundle_size
     H, W = w["H"], w["W"]
+    tol = 1e-4 if precision == 0 else 2e-3
 
     def run(order):
         o = torch.tensor(order)
@@ -126,23 +130,25 @@ def test_full_size_render_against_oracle_and_view_symmetry():
         src = ops.prepare_sources(data["feat"][:, o].contiguous().to(DEV), data["rgb"][:, o].contiguous().to(DEV), b, cfg.nerf.max_mipmap_level)
         vol_cl = ops.to_channels_last(data["vol"].to(DEV), 8)
         return ops.render_fused(src, vol_cl, data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam,
-                                ops.pack_mlp(mlp, feat_dim, device=DEV), 1, 3, H, W, b, cfg.nerf.max_num_samples, False, True)
+                                ops.pack_mlp(mlp, feat_dim, device=DEV), 1, 3, H, W, b, cfg.nerf.max_num_samples, False, True,
+                                precision=precision)
 
     out = run([0, 1, 2])
     # property: aggregation over source views is symmetric
     perm = run([2, 0, 1])
-    assert _md(out["feat"], perm["feat"]) <= 2e-5
-    assert _md(out["depth"], perm["depth"]) <= 1e-4 * (w["far"] - w["near"])
+    assert _md(out["feat"], perm["feat"]) <= (2e-5 if precision == 0 else 1e-3)
+    assert _md(out["depth"], perm["depth"]) <= tol * (w["far"] - w["near"])
     # property: weights are renormalised per bundle -> opacity == 1
     assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
     dr = data["depth_range"]
-    assert bool(((out["depth"].cpu() >= dr[:, 0] - 1e-2) & (out["depth"].cpu() <= dr[:, 1] + 1e-2)).all())
+    slack = 1e-5 * w["far"]
+    assert bool(((out["depth"].cpu() >= dr[:, 0] - slack) & (out["depth"].cpu() <= dr[:, 1] + slack)).all())
     # full-size parity with the oracle (float32, identical inputs)
     truth = O.render_bundles(mlp, feat_dim, data["rgb"], data["feat"], data["vol"], data["depth_range"], data["vol_range"],
                              rig["src_exts"], rig["src_ints"], rig["tar_exts"], rig["tar_ints"], rig["near_far"], b,
                              cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, False, True)
-    assert _md(out["feat"], truth["bundle_feat"]) <= 1e-4
-    assert _md(out["depth"], truth["bundle_depth"]) <= 1e-4 * (w["far"] - w["near"])
+    assert _md(out["feat"], truth["bundle_feat"]) <= tol
+    assert _md(out["depth"], truth["bundle_depth"]) <= tol * (w["far"] - w["near"])
 
 
 def test_full_size_warp_variance_against_oracle():
