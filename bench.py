@@ -234,7 +234,8 @@ def run_ours(args, wl, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, record):
+    def timed(fn, steps, record, tag="gdb_timed"):
+        torch.cuda.nvtx.range_push(tag)       # lets `ncu --nvtx --nvtx-include "<tag>/"` profile exactly the timed launches
         evs = []
         for _ in range(steps):
             flush.zero_()                                   # L2 flush between timed iterations, outside the events
@@ -246,6 +247,7 @@ def run_ours(args, wl, cfg):
             recording["on"] = False
             evs.append((s, e))
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
         return sum(s.elapsed_time(e) for s, e in evs)       # ms over exactly `steps` steps
 
     for _ in range(max(args.warmup, 3)):
@@ -269,7 +271,7 @@ def run_ours(args, wl, cfg):
         step_device()
     barrier()
     tc_steps = max(3, args.steps // 2)
-    ms_tc = timed(step_device, tc_steps, True)
+    ms_tc = timed(step_device, tc_steps, True, tag="gdb_timed_tc")
     spans_tc = {k: list(v) for k, v in spans.items()}
     spans.clear(); spans.update(spans_fp32)
     net.mlp_precision = 0

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--no-tf32", action="store_true")
     ap.add_argument("--kernels", action="store_true")
     ap.add_argument("--tc", action="store_true")
+    ap.add_argument("--ops", action="store_true", help="ATen ops grouped by input shape (finds the glue copies/adds)")
     args = ap.parse_args()
     torch.backends.cudnn.benchmark = args.benchmark
     if args.no_tf32:
@@ -99,10 +100,24 @@ def main():
         rows.sort(reverse=True)
         out["kernels"] = [{"ms": r[0], "count": r[1], "name": r[2]} for r in rows[:40]]
         out["n_kernel_launches"] = sum(r[1] for r in rows)
+    if args.ops:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
+            run()
+            torch.cuda.synchronize()
+        rows = []
+        for ev in prof.key_averages(group_by_input_shape=True):
+            t = getattr(ev, "self_device_time_total", 0)
+            if t > 0 and ev.device_type != torch.autograd.DeviceType.CUDA:
+                rows.append((t / 1e3, ev.count, ev.key, str(ev.input_shapes)[:160]))
+        rows.sort(reverse=True)
+        out["ops"] = [{"ms": r[0], "count": r[1], "op": r[2], "shapes": r[3]} for r in rows[:60]]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"profile_forward_{args.tag}.json"), "w") as fh:
         json.dump(out, fh, indent=1)
-    print(json.dumps({k: v for k, v in out.items() if k != "kernels"}))
+    print(json.dumps({k: v for k, v in out.items() if k not in ("kernels", "ops")}))
+    for r in out.get("ops", [])[:45]:
+        print(f"  {r['ms']:8.3f} ms x{r['count']:<3d} {r['op']:<34s} {r['shapes']}")
     if args.kernels:
         for r in out["kernels"][:25]:
             print(f"  {r['ms']:8.3f} ms x{r['count']:<4d} {r['name']}")
