@@ -116,37 +116,84 @@ class FeatureNet(nn.Module):
         return outs
 
 
+def _cached(mod: nn.Module, name: str, tensors, make):
+    """Derived eval-time parameters (composed / concatenated weights), rebuilt when a source tensor changes."""
+    key = tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = getattr(mod, name, None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    with torch.no_grad():
+        val = make()
+    object.__setattr__(mod, name, (key, val))
+    return val
+
+
 def feature_net_fused(net: "FeatureNet", x: torch.Tensor, levels: int = 3) -> List[torch.Tensor]:
+    from . import ops
     x = x.contiguous(memory_format=torch.channels_last)
     f0 = run_block(net.conv0[1], run_block(net.conv0[0], x))
     f1 = run_block(net.conv1[1], run_block(net.conv1[0], f0))
     f2 = run_block(net.conv2[1], run_block(net.conv2[0], f1))
     outs = [net.out0(f2)]
     if levels >= 2:
-        top = F.interpolate(f2, size=f1.shape[-2:], mode="nearest") + net.inner1(f1)
+        # top-down step (feature_net.py:52-58): nearest x2 + lateral 1x1 conv + its bias in one pass
+        top = ops.bias_act_add(F.conv2d(f1, net.inner1.weight), net.inner1.bias, f2, relu=False, skip_up2=True)
         outs.append(net.out1(top))
         if levels >= 3:
-            top = F.interpolate(top, size=f0.shape[-2:], mode="nearest") + net.inner2(f0)
+            top = ops.bias_act_add(F.conv2d(f0, net.inner2.weight), net.inner2.bias, top, relu=False, skip_up2=True)
             outs.append(net.out2(top))
     return outs
 
 
-def cost_reg_fused(net: "_CostReg", x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Same data flow as CostRegNet(Small).forward with folded blocks; x is NCDHW-shaped, channels_last_3d strides."""
+def _deconv_skip(block: nn.Sequential, x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    """skip + relu(bn(deconv(x))) (cost_reg_net.py:108-110): library transposed convolution, one fused epilogue."""
+    from . import ops
+    conv = block[0]
+    w, b = _folded(block)
+    d = F.conv_transpose3d(x, w, None, conv.stride, conv.padding, conv.output_padding)
+    if ops._is_cl(d) and ops._is_cl(skip) and d.shape[1] % 4 == 0:
+        return ops.bias_act_add(d, b, skip, relu=True)
+    return skip + (d + b.view(1, -1, 1, 1, 1)).relu_()
+
+
+def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same data flow as CostRegNet(Small).forward with folded blocks; x is NCDHW-shaped, channels_last_3d strides.
+    Returns (volume, logits): volume is a (B,D,H,W,8) channels-last VIEW of the joint head output (or None when the
+    caller does not consume it: the stage-0 feature head only feeds the training-time coarse render), logits a
+    (B,D,H,W) view of the probability head BEFORE its soft-max (the soft-max is fused into the depth-range kernel)."""
     r = run_block
     s0 = r(net.conv0, x)
     s1 = r(net.conv2, r(net.conv1, s0))
     if isinstance(net, CostRegNetSmall):
         y = r(net.conv4, r(net.conv3, s1))
-        y = s1 + r(net.conv5, y)
-        y = s0 + r(net.conv6, y)
+        y = _deconv_skip(net.conv5, y, s1)
+        y = _deconv_skip(net.conv6, y, s0)
     else:
         s2 = r(net.conv4, r(net.conv3, s1))
         y = r(net.conv6, r(net.conv5, s2))
-        y = s2 + r(net.conv7, y)
-        y = s1 + r(net.conv8, y)
-        y = s0 + r(net.conv9, y)
-    return net.feat_head(y), torch.softmax(net.prob_head(y).squeeze(1), dim=1)
+        y = _deconv_skip(net.conv7, y, s2)
+        y = _deconv_skip(net.conv8, y, s1)
+        y = _deconv_skip(net.conv9, y, s0)
+    if not want_volume:
+        return None, F.conv3d(y, net.prob_head.weight, None, 1, 1).squeeze(1)
+    # both heads as ONE convolution (identical arithmetic per output channel), padded to 12 output channels so the
+    # channels-last voxel stays float4-addressable: channels 0-7 feature volume, 8 probability logits
+    fw, pw = net.feat_head.weight, net.prob_head.weight
+    cout = fw.shape[0]
+    cpad = (cout + 1 + 3) & ~3
+
+    def make():
+        w = torch.zeros((cpad, *fw.shape[1:]), device=fw.device, dtype=fw.dtype)
+        w[:cout] = fw
+        w[cout] = pw[0]
+        return w.contiguous(memory_format=torch.channels_last_3d)
+
+    w = _cached(net, "_gdb_heads", (fw, pw), make)
+    out = F.conv3d(y, w, None, 1, 1)                             # (B,cpad,D,H,W) over NDHWC memory
+    cl = out.permute(0, 2, 3, 4, 1)
+    if not cl.is_contiguous():
+        cl = cl.contiguous()
+    return cl[..., :cout], cl[..., cout]
 
 
 class _CostReg(nn.Module):
@@ -254,3 +301,39 @@ class Decoder(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         y = self.in_conv(x)
         return self.out_conv(self.up(y + self.blocks(y)))
+
+
+def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
+    """Eval-time decoder (decoder_rdn.py:44-82) on channels-last data.  Returns the output BEFORE the last pixel
+    shuffle as (B, H/2, W/2, 12) channels-last: the last up-sampling convolution, the pixel shuffle and the 1x1
+    output convolution are all linear, so the 1x1 is folded into the 3x3 (64 -> 3*4 channels instead of 64 -> 256,
+    no 256-channel intermediate); ``gdb_assemble_output`` performs the pending shuffle."""
+    from . import ops
+    y = dec.in_conv(x)
+    h = y
+    for blk in dec.blocks:
+        zb = _cached(blk, "_gdb_zero", (blk.conv1.weight,), lambda: torch.zeros(blk.conv1.weight.shape[0], device=x.device))
+        a = torch.cudnn_convolution_relu(h, blk.conv1.weight, zb, (1, 1), (1, 1), (1, 1), 1)
+        b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
+        c = blk.conv3(torch.cat((h, a, b), 1))
+        gate = blk.se.fc(c.mean((2, 3)))
+        h = ops.gate_add(h, c, gate) if ops._is_cl(h) and ops._is_cl(c) else h + c * gate[:, :, None, None]
+    y = y + h
+    mods = list(dec.up)
+    if not mods:
+        raise ValueError("decoder_fused needs upscale_factor >= 2")
+    for i in range(0, len(mods) - 2, 2):
+        y = mods[i + 1](mods[i](y))
+    up, oc = mods[-2], dec.out_conv
+
+    def make():
+        co, ci = oc.weight.shape[:2]
+        wu = up.weight.view(ci, 4, *up.weight.shape[1:])                          # [c][k] <- channel c*4 + k
+        w = torch.einsum("oc,ckihw->okihw", oc.weight.view(co, ci), wu).reshape(co * 4, *up.weight.shape[1:])
+        b = torch.einsum("oc,ck->ok", oc.weight.view(co, ci), up.bias.view(ci, 4)) + oc.bias[:, None]
+        return w.contiguous(memory_format=torch.channels_last), b.reshape(-1).contiguous()
+
+    w, b = _cached(dec, "_gdb_tail", (up.weight, up.bias, oc.weight, oc.bias), make)
+    out = F.conv2d(y, w, b, 1, 1)                                                 # (B,12,h,w) over NHWC memory
+    return out.permute(0, 2, 3, 1).contiguous()
+

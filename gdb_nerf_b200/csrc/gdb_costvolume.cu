@@ -311,6 +311,76 @@ __global__ void depth_range_kernel(const float* __restrict__ range, int rh, int 
   }
 }
 
+
+// K2 fused with the soft-max of the probability head (cost_reg_net.py:62-63,115-116 -> depth_net.py:172):
+// logits are read with arbitrary (batch, depth, pixel) strides so they may be one channel of a channels-last
+// multi-head convolution output.  prob_d = exp(l_d - max) / sum (ATen's soft-max order), then K2 unchanged.
+template <int DMAX>
+__global__ void depth_range_logits_kernel(const float* __restrict__ range, int rh, int rw, const float* __restrict__ logits,
+                                          int64_t sB, int64_t sD, int64_t sP, int B, int D, int h, int w, float ci_scale,
+                                          int inv_depth, float* __restrict__ depth, float* __restrict__ ci,
+                                          float* __restrict__ vol_range, float* __restrict__ prob_out) {
+  int hw = h * w;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * hw) return;
+  int b = i / hw, p = i % hw;
+  int y = p / w, x = p % w;
+  int ry = rh == 1 ? 0 : y, rx = rw == 1 ? 0 : x;
+  float near_ = range[((size_t)(b * 2 + 0) * rh + ry) * rw + rx];
+  float far_ = range[((size_t)(b * 2 + 1) * rh + ry) * rw + rx];
+  const float* lp = logits + b * sB + p * sP;
+  float pr[DMAX];
+  float m = -INFINITY;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    pr[d] = d < D ? __ldg(lp + d * sD) : -INFINITY;
+    m = fmaxf(m, pr[d]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    pr[d] = d < D ? expf(pr[d] - m) : 0.f;
+    sum += pr[d];
+  }
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) pr[d] = fdiv(pr[d], sum);
+  float mean = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) mean = fadd(mean, fmul(pr[d], hypothesis(near_, far_, d, D, inv_depth)));
+  float var = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) {
+      float t = fsub(hypothesis(near_, far_, d, D, inv_depth), mean);
+      var = fadd(var, fmul(pr[d], fmul(t, t)));
+    }
+  if (prob_out) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+      if (d < D) prob_out[((size_t)b * D + d) * hw + p] = pr[d];
+  }
+  float half = fmul(ci_scale, sqrtf(fmaxf(var, 1e-12f)));
+  float first = hypothesis(near_, far_, 0, D, inv_depth), last = hypothesis(near_, far_, D - 1, D, inv_depth);
+  float lo, hi, dep;
+  if (inv_depth) {
+    lo = fdiv(1.f, fminf(fadd(mean, half), first));
+    hi = fdiv(1.f, fmaxf(fsub(mean, half), last));
+    dep = fdiv(1.f, mean);
+  } else {
+    lo = fmaxf(fsub(mean, half), first);
+    hi = fminf(fadd(mean, half), last);
+    dep = mean;
+  }
+  depth[i] = dep;
+  ci[(size_t)(b * 2 + 0) * hw + p] = lo;
+  ci[(size_t)(b * 2 + 1) * hw + p] = hi;
+  if (vol_range) {
+    vol_range[(size_t)(b * 2 + 0) * hw + p] = first;
+    vol_range[(size_t)(b * 2 + 1) * hw + p] = last;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // planar -> channels-last
 // ---------------------------------------------------------------------------
@@ -399,4 +469,27 @@ extern "C" int gdb_depth_range_fwd(const float* depth_range, int rh, int rw, con
   depth_range_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(depth_range, rh, rw, prob, B, D, h, w, ci_scale,
                                                                     inv_depth, depth, ci, vol_range);
   return cuda_check("gdb_depth_range_fwd");
+}
+
+extern "C" int gdb_depth_range_from_logits_fwd(const float* depth_range, int rh, int rw, const float* logits, int64_t stride_b,
+                                               int64_t stride_d, int64_t stride_pix, int B, int D, int h, int w, float ci_scale,
+                                               int inv_depth, float* depth, float* ci, float* vol_range, float* prob_out,
+                                               void* stream) {
+  GDB_REQUIRE(depth_range && logits && depth && ci && B > 0 && D > 0 && h > 0 && w > 0, GDB_E_BADARG,
+              "gdb_depth_range_from_logits_fwd: bad argument");
+  GDB_REQUIRE((rh == 1 && rw == 1) || (rh == h && rw == w), GDB_E_BADARG,
+              "gdb_depth_range_from_logits_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", h, w, rh, rw);
+  GDB_REQUIRE(D <= 64, GDB_E_UNSUPPORTED, "gdb_depth_range_from_logits_fwd: D=%d > 64 not instantiated", D);
+  int n = B * h * w;
+  cudaStream_t st = as_stream(stream);
+  if (D <= 8)
+    depth_range_logits_kernel<8><<<(n + 127) / 128, 128, 0, st>>>(depth_range, rh, rw, logits, stride_b, stride_d, stride_pix, B, D, h, w,
+                                                                  ci_scale, inv_depth, depth, ci, vol_range, prob_out);
+  else if (D <= 36)
+    depth_range_logits_kernel<36><<<(n + 127) / 128, 128, 0, st>>>(depth_range, rh, rw, logits, stride_b, stride_d, stride_pix, B, D, h, w,
+                                                                   ci_scale, inv_depth, depth, ci, vol_range, prob_out);
+  else
+    depth_range_logits_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(depth_range, rh, rw, logits, stride_b, stride_d, stride_pix, B, D, h, w,
+                                                                   ci_scale, inv_depth, depth, ci, vol_range, prob_out);
+  return cuda_check("gdb_depth_range_from_logits_fwd");
 }

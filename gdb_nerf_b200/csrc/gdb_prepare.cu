@@ -123,7 +123,7 @@ __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot,
                                        const float* __restrict__ bdepth, const float* __restrict__ bopac, int B, int Hb,
                                        int Wb, int BS, int reweighting, int layout, float* __restrict__ rgb,
                                        float* __restrict__ depth, float* __restrict__ opacity) {
-  const bool feat_cl = layout & 1, dec_cl = layout & 2;
+  const bool feat_cl = layout & 1, dec_cl = layout & 2, dec_ps = layout & 4;
   const int H = Hb * BS, W = Wb * BS;
   const size_t HW = (size_t)H * W, hw = (size_t)Hb * Wb;
   size_t n = (size_t)B * HW;
@@ -135,7 +135,12 @@ __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot,
     for (int c = 0; c < 3; ++c) {
       float fine = feat_cl ? feat[((size_t)b * hw + (size_t)yb * Wb + xb) * Ctot + c * BS * BS + j]
                            : feat[((size_t)b * Ctot + c * BS * BS + j) * hw + (size_t)yb * Wb + xb];
-      float v = (dec_cl ? dec[((size_t)b * HW + (size_t)y * W + x) * 3 + c] : dec[((size_t)b * 3 + c) * HW + (size_t)y * W + x]) + fine;
+      float dv;
+      if (dec_ps)   // (B, H/2, W/2, 12): the decoder's last convolution before its pixel shuffle, channel = c*4 + (y%2)*2 + x%2
+        dv = dec[((size_t)b * (HW / 4) + (size_t)(y >> 1) * (W >> 1) + (x >> 1)) * 12 + c * 4 + (y & 1) * 2 + (x & 1)];
+      else
+        dv = dec_cl ? dec[((size_t)b * HW + (size_t)y * W + x) * 3 + c] : dec[((size_t)b * 3 + c) * HW + (size_t)y * W + x];
+      float v = dv + fine;
       if (reweighting) v = 0.5f * (v + fine);
       rgb[((size_t)b * 3 + c) * HW + (size_t)y * W + x] = v;
     }

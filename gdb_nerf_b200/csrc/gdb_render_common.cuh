@@ -26,6 +26,7 @@ struct RenderParams {
   float* tap_w;
   int64_t tex_level[4];
   int cam_stride;
+  int vol_stride;      // floats between consecutive voxels of vol (>= 8, multiple of 4)
   int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
 };
 

@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, feature_net_fused
+from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, decoder_fused, feature_net_fused
 from .nerf import CoarseNeRF, NeRF
 from .sampler import BundleSampler
 
@@ -73,8 +73,13 @@ class DepthNet(nn.Module):
             feat_cl = ops.to_channels_last(feats.flatten(0, 1)).unflatten(0, (B, V))
             variance = ops.warp_variance(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s],
                                          out_channels_last=fused_cnn)
-            volume, prob = cost_reg_fused(self.cost_regs[s], variance) if fused_cnn else self.cost_regs[s](variance)
-            depth, ci, vol_range = ops.depth_range_from_prob(depth_range, prob, self.ci_scales[s], self.inv_depth[s])
+            if fused_cnn:
+                # the feature head of every stage but the last only feeds the training-time coarse render
+                volume, logits = cost_reg_fused(self.cost_regs[s], variance, want_volume=(s == self.num_stages - 1))
+                depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])
+            else:
+                volume, prob = self.cost_regs[s](variance)
+                depth, ci, vol_range = ops.depth_range_from_prob(depth_range, prob, self.ci_scales[s], self.inv_depth[s])
             mvs_depths.append(depth.squeeze(1))
             range_list.append(ci)
             vol_list.append(vol_range)
@@ -177,7 +182,8 @@ class Network(nn.Module):
             depth_range = F.interpolate(depth_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
             vol_range = F.interpolate(vol_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
             mvs_depth = F.interpolate(mvs_depth.unsqueeze(1), size=(Hb, Wb), mode='nearest').squeeze(1)
-        if feat_volume.shape[-2:] != (Hb, Wb):
+        vol_hw = feat_volume.shape[2:4] if fused else feat_volume.shape[-2:]
+        if tuple(vol_hw) != (Hb, Wb):
             raise ValueError("feature volume resolution must equal the bundle map (true for every shipped recipe)")
 
         img_feat = ms_feats[self.feat_level]
@@ -187,14 +193,14 @@ class Network(nn.Module):
         self.sampler.build_rays(tar_exts, tar_ints, (H, W), near_far[:, 0], near_far[:, 1])
         cam = self.sampler.camera_block(src_exts, src_ints, b, self.inv_depth)
         sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
-        vol_cl = ops.to_channels_last(feat_volume, 8)
+        vol_cl = feat_volume if fused else ops.to_channels_last(feat_volume, 8)    # fused: already a (B,D,Hb,Wb,8) view
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
                                self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
                                precision=self.mlp_precision)
         if fused:
-            rgb_c = self.upsampler(out['dec_in'].permute(0, 3, 1, 2))          # NCHW shape over channels-last memory
-            rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], rgb_c, out['depth'], out['opacity'], b,
-                                                                self.reweighting, feat_channels_last=True)
+            dec12 = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2))   # NCHW shape over channels-last memory
+            rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], dec12, out['depth'], out['opacity'], b,
+                                                                self.reweighting, feat_channels_last=True, dec_pre_shuffle=True)
         else:
             rgb_c = self.upsampler(out['feat'][:, 3 * b * b:])
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['feat'], rgb_c, out['depth'], out['opacity'], b, self.reweighting)

@@ -123,6 +123,75 @@ def depth_range_from_prob(depth_range: Tensor, prob: Tensor, ci_scale: float, in
     return depth, ci, vol
 
 
+def depth_range_from_logits(depth_range: Tensor, logits: Tensor, ci_scale: float, inv_depth: bool,
+                            want_prob: bool = False) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """K2 fused with the probability head's soft-max.  ``logits`` is a (B,D,h,w) VIEW with any batch/depth strides whose
+    pixels are equally spaced (e.g. one channel of a channels-last convolution output): no copy is made.
+    -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w), prob (B,D,h,w) or None."""
+    _dev(depth_range, logits)
+    depth_range = _f32(depth_range)
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    B, D, h, w = logits.shape
+    sb, sd, sy, sx = logits.stride()
+    if sy != sx * w:
+        logits = logits.contiguous()
+        sb, sd, sy, sx = logits.stride()
+    _, _, rh, rw = depth_range.shape
+    dev = logits.device
+    depth = torch.empty((B, 1, h, w), device=dev, dtype=torch.float32)
+    ci = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
+    vol = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
+    prob = torch.empty((B, D, h, w), device=dev, dtype=torch.float32) if want_prob else None
+    lib = _lib.load()
+    _lib.check(lib.gdb_depth_range_from_logits_fwd(depth_range.data_ptr(), rh, rw, logits.data_ptr(), sb, sd, sx, B, D, h, w,
+                                                   float(ci_scale), int(inv_depth), depth.data_ptr(), ci.data_ptr(), vol.data_ptr(),
+                                                   _p(prob), _stream()), "gdb_depth_range_from_logits_fwd")
+    return depth, ci, vol, prob
+
+
+# -------------------------------------------------------------------- glue --
+def _is_cl(x: Tensor) -> bool:
+    """Shape (N, C, *spatial) over channels-last memory (N, *spatial, C), dense."""
+    return x.dtype == torch.float32 and x.is_cuda and x.permute(0, *range(2, x.dim()), 1).is_contiguous()
+
+
+def bias_act_add(x: Tensor, bias: Optional[Tensor], skip: Optional[Tensor], relu: bool, skip_up2: bool = False) -> Tensor:
+    """out = skip + act(x + bias) on channels-last tensors of shape (N, C, *spatial); with ``skip_up2`` skip is the
+    half-resolution (N, C, H/2, W/2) map, nearest-neighbour up-sampled on the fly."""
+    _dev(x, bias, skip)
+    Cc = x.shape[1]
+    if not (_is_cl(x) and (skip is None or _is_cl(skip)) and Cc % 4 == 0):
+        raise _lib.GdbError("bias_act_add needs dense channels-last fp32 tensors with C % 4 == 0")
+    N = x.shape[0]
+    S = x.numel() // (N * Cc)
+    Hs = Ws = 0
+    if skip_up2:
+        Hs, Ws = skip.shape[-2:]
+        if x.dim() != 4 or tuple(x.shape[-2:]) != (2 * Hs, 2 * Ws):
+            raise ValueError("skip_up2: x must be (N,C,2Hs,2Ws)")
+    elif skip is not None and skip.shape != x.shape:
+        raise ValueError("skip shape mismatch")
+    out = torch.empty_like(x)             # preserves the channels-last strides
+    lib = _lib.load()
+    _lib.check(lib.gdb_bias_act_add(x.data_ptr(), _p(None if bias is None else _f32(bias)), _p(skip), N, S, Cc, int(relu),
+                                    int(skip_up2), Hs, Ws, out.data_ptr(), _stream()), "gdb_bias_act_add")
+    return out
+
+
+def gate_add(x: Tensor, y: Tensor, gate: Tensor) -> Tensor:
+    """out = x + y * gate[n, c] (channels-last (N,C,H,W)-shaped x, y; gate (N,C))."""
+    _dev(x, y, gate)
+    N, Cc = x.shape[:2]
+    if not (_is_cl(x) and _is_cl(y) and Cc % 4 == 0 and x.shape == y.shape):
+        raise _lib.GdbError("gate_add needs dense channels-last fp32 tensors with C % 4 == 0")
+    S = x.numel() // (N * Cc)
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    _lib.check(lib.gdb_gate_add(x.data_ptr(), y.data_ptr(), _f32(gate).data_ptr(), N, S, Cc, out.data_ptr(), _stream()), "gdb_gate_add")
+    return out
+
+
 # ---------------------------------------------------------------- sampling --
 def camera_block(tar_exts: Tensor, tar_ints: Tensor, src_exts: Tensor, src_ints: Tensor, near_far: Tensor, bundle_size: int,
                  global_num_depth: int, inv_depth: bool) -> Tensor:
@@ -232,9 +301,17 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     ``taps`` (a SampleList) is given, the reference's packed intermediates.
     With ``out_channels_last``: {'fine' (B,Hb,Wb,3b^2), 'dec_in' (B,Hb,Wb,F+8), 'depth', 'opacity'}."""
     _dev(src.tex, src.rgba, vol_cl, depth_range, vol_range, cam, mlp)
-    depth_range, vol_range, vol_cl = _f32(depth_range), _f32(vol_range), _f32(vol_cl)
+    depth_range, vol_range = _f32(depth_range), _f32(vol_range)
     Hb, Wb = H // bundle_size, W // bundle_size
     D = vol_cl.shape[1]
+    # (B,D,Hb,Wb,8) view whose voxels are vol_stride floats apart (the leading channels of a wider channels-last
+    # convolution output) is consumed in place
+    vs = vol_cl.stride(3)
+    if not (vol_cl.dtype == torch.float32 and vol_cl.shape[-1] == 8 and vol_cl.stride(4) == 1 and vs >= 8 and vs % 4 == 0
+            and vol_cl.stride(2) == vs * Wb and vol_cl.stride(1) == vs * Wb * Hb and vol_cl.stride(0) == vs * Wb * Hb * D
+            and vol_cl.data_ptr() % 16 == 0):
+        vol_cl = _f32(vol_cl)
+        vs = 8
     bb = bundle_size * bundle_size
     F = src.feat_dim + 3
     CT = 3 * bb + F + 8
@@ -262,20 +339,25 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     lib = _lib.load()
     _lib.check(lib.gdb_render_fused_fwd(src.rgba.data_ptr(), src.tex.data_ptr(), vol_cl.data_ptr(), depth_range.data_ptr(),
                                         vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], mlp.data_ptr(), B, V, H, W, bundle_size,
-                                        src.feat_dim, D, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
+                                        src.feat_dim, D, vs, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
                                         int(out_channels_last), out_feat.data_ptr(), _p(out_dec), out_depth.data_ptr(), out_opac.data_ptr(),
                                         C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
     return res
 
 
 def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bundle_size: int, reweighting: bool,
-                    feat_channels_last: bool = False):
+                    feat_channels_last: bool = False, dec_pre_shuffle: bool = False):
     """rgb = dec + pixel_shuffle(feat[:, :3b^2]) (network.py:175-182).  ``feat`` is (B,CT,Hb,Wb) planar or, with
     ``feat_channels_last``, (B,Hb,Wb,C) holding at least the 3b^2 fine-colour channels; ``dec`` (B,3,H,W) in either
     memory format."""
     _dev(feat, dec, bdepth, bopac)
     layout = 1 if feat_channels_last else 0
-    if dec.dtype == torch.float32 and not dec.is_contiguous() and dec.permute(0, 2, 3, 1).is_contiguous():
+    if dec_pre_shuffle:
+        # dec: (B, H/2, W/2, 12) dense channels-last output of the decoder's composed last convolution
+        if not (dec.dtype == torch.float32 and dec.is_contiguous() and dec.shape[-1] == 12):
+            raise ValueError("dec_pre_shuffle needs a contiguous (B,H/2,W/2,12) fp32 tensor")
+        layout |= 4
+    elif dec.dtype == torch.float32 and not dec.is_contiguous() and dec.permute(0, 2, 3, 1).is_contiguous():
         layout |= 2
     else:
         dec = _f32(dec)

@@ -75,6 +75,15 @@ int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* 
 int gdb_depth_range_fwd(const float* depth_range, int rh, int rw, const float* prob, int B, int D, int h, int w,
                         float ci_scale, int inv_depth, float* depth, float* ci, float* vol_range, void* stream);
 
+/* K2 fused with the soft-max of the probability head (cost_reg_net.py:62-63,
+ * 115-116 -> depth_net.py:172): logits element (b,d,pixel) lives at
+ * logits[b*stride_b + d*stride_d + pixel*stride_pix] (so it may be one channel
+ * of a channels-last multi-head convolution output).  D <= 64.  prob_out
+ * (B,D,h,w) planar, optional (null: probabilities are not materialised).      */
+int gdb_depth_range_from_logits_fwd(const float* depth_range, int rh, int rw, const float* logits, int64_t stride_b,
+                                    int64_t stride_d, int64_t stride_pix, int B, int D, int h, int w, float ci_scale,
+                                    int inv_depth, float* depth, float* ci, float* vol_range, float* prob_out, void* stream);
+
 /* --------------------------------------------------------- sampling ------- */
 /* Camera block for the sampling / render kernels: replaces
  * BundleSampler.build_rays bundle_sampler.py:30-74 and the per-view constants
@@ -122,7 +131,9 @@ int gdb_prepare_sources(const float* feat, int feat_channels_last, const float* 
  * render_weight_from_density / accumulate_value_along_rays
  * (utils.py:19-43,88-121) and Network.render_bundles (network.py:54-91).
  *
- * vol_cl (B,D,Hb,Wb,8) channels-last feature volume; tex/rgba from
+ * vol_cl (B,D,Hb,Wb,vol_stride) channels-last feature volume, the 8 feature
+ * channels first (vol_stride >= 8, a multiple of 4: the volume may be the leading
+ * channels of a wider multi-head convolution output); tex/rgba from
  * gdb_prepare_sources; depth_range, vol_range (B,2,Hb,Wb); mlp: packed
  * parameter block.
  * out_feat (B, 3b^2+F+8, Hb, Wb) planar (the reference's layout, out_dec
@@ -146,7 +157,7 @@ typedef struct gdb_render_taps {
 
 int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
                          const float* vol_range, const float* cam, int cam_stride, const float* mlp,
-                         int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int max_samples,
+                         int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int max_samples,
                          int max_mip_level, int inv_depth, int adaptive,
                          int precision /* 0 = fp32 SIMT MLP (1e-4 class); 1 = fp16-operand tcgen05 MLP, fp32 accumulate (2e-3 class) */,
                          int out_channels_last, float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
@@ -156,10 +167,26 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
  * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
  * and the bilinear xb up-sampling of depth and opacity.
  * feat (B,Ctot,Hb,Wb), dec (B,3,H,W) -> rgb (B,3,H,W), depth/opacity (B,H,W).
- * layout bit 0: feat is channels-last (B,Hb,Wb,Ctot); bit 1: dec is (B,H,W,3). */
+ * layout bit 0: feat is channels-last (B,Hb,Wb,Ctot); bit 1: dec is (B,H,W,3);
+ * bit 2: dec is (B,H/2,W/2,12) channels-last = the decoder's last convolution
+ * composed with its 1x1 output convolution, pixel shuffle (decoder_rdn.py:78-81)
+ * still pending: channel c*4 + (y%2)*2 + (x%2).                               */
 int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
                         int B, int Hb, int Wb, int bundle_size, int reweighting, int layout,
                         float* rgb, float* depth, float* opacity, void* stream);
+
+/* --------------------------------------------------------- glue ----------- */
+/* Element-wise epilogues between the kernels above and the cuDNN networks
+ * (channels-last fp32, C % 4 == 0; x/out (N,S,C)):
+ * out = skip + act(x + bias): bias (C) or null, relu != 0 applies ReLU, skip
+ * null or (N,S,C); with skip_up2 != 0 skip is (N,Hs,Ws,C) and S == 4*Hs*Ws
+ * (nearest-neighbour x2).  Replaces cost_reg_net.py:108-110 (y = s + relu(..))
+ * and the FPN top-down step feature_net.py:52-58.                             */
+int gdb_bias_act_add(const float* x, const float* bias, const float* skip, int64_t N, int64_t S, int C, int relu,
+                     int skip_up2, int Hs, int Ws, float* out, void* stream);
+/* out = x + y * gate[n,c]: squeeze-excite residual of the decoder's dense
+ * blocks (decoder_rdn.py:31-41).  gate (N,C).                                 */
+int gdb_gate_add(const float* x, const float* y, const float* gate, int64_t N, int64_t S, int C, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -298,3 +298,87 @@ def test_render_fused_tensor_core_variant(golden, prefix):
     R = 3 * b * b
     assert torch.equal(split["fine"].permute(0, 3, 1, 2), tc["feat"][:, :R])
     assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), tc["feat"][:, R:])
+
+
+# ------------------------------------------------------------------ glue next to the path
+def test_depth_range_from_logits_strided(golden):
+    """Soft-max fused into K2, logits read in place as channel 8 of a 12-channel channels-last head output."""
+    cfg = _cfg(golden)
+    g = torch.Generator().manual_seed(11)
+    for s in range(2):
+        rng, prob = golden.t(f"s{s}_range_in"), golden.t(f"s{s}_prob")
+        B, D, h, w = prob.shape
+        logits = torch.log(prob.clamp_min(1e-30)) + torch.randn(B, 1, h, w, generator=g)      # softmax(logits) == prob
+        heads = torch.randn(B, D, h, w, 12, generator=g)
+        heads[..., 8] = logits
+        hd = heads.to(DEV)
+        depth, ci, vol, pr = ops.depth_range_from_logits(rng.to(DEV), hd[..., 8], cfg.mvs.ci_scales[s], cfg.mvs.inv_depth[s], want_prob=True)
+        assert _md(pr, torch.softmax(logits.double(), 1)) <= 5e-7
+        scale = float(golden.t(f"s{s}_depth").abs().max())
+        assert _md(depth, golden.t(f"s{s}_depth")) <= 2e-5 * scale
+        assert _md(ci, golden.t(f"s{s}_ci")) <= 2e-5 * scale
+        d2, c2, v2 = ops.depth_range_from_prob(rng.to(DEV), pr, cfg.mvs.ci_scales[s], cfg.mvs.inv_depth[s])
+        assert torch.equal(d2, depth) and torch.equal(c2, ci) and torch.equal(v2, vol)           # same arithmetic after the soft-max
+
+
+def test_glue_epilogues_match_torch():
+    g = torch.Generator().manual_seed(3)
+    F_ = torch.nn.functional
+    x = torch.randn(2, 8, 4, 6, 10, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    skip = torch.randn(2, 8, 4, 6, 10, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    bias = torch.randn(8, generator=g).to(DEV)
+    out = ops.bias_act_add(x, bias, skip, relu=True)
+    assert torch.equal(out, skip + (x + bias.view(1, -1, 1, 1, 1)).relu())
+    lat = torch.randn(3, 32, 8, 12, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    top = torch.randn(3, 32, 4, 6, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    b2 = torch.randn(32, generator=g).to(DEV)
+    out = ops.bias_act_add(lat, b2, top, relu=False, skip_up2=True)
+    want = F_.interpolate(top, size=(8, 12), mode="nearest") + (lat + b2.view(1, -1, 1, 1))
+    assert _md(out, want) <= 1e-6
+    y = torch.randn(3, 32, 8, 12, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    gate = torch.rand(3, 32, generator=g).to(DEV)
+    assert _md(ops.gate_add(lat, y, gate), lat + y * gate[:, :, None, None]) <= 1e-6
+    with pytest.raises(ops._lib.GdbError):
+        ops.bias_act_add(lat.contiguous(), b2, None, relu=False)                                 # planar memory is refused, not converted
+
+
+def test_assemble_output_pre_shuffle_decoder(golden):
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    B, H, W = spec["B"], spec["H"], spec["W"]
+    Hb, Wb = H // b, W // b
+    feat = golden.t("bundle_feat").view(B, Hb, Wb, -1).contiguous()
+    bd, bo = golden.t("bundle_depth").view(B, Hb, Wb), golden.t("bundle_opacity").view(B, Hb, Wb)
+    dec12 = torch.rand(B, H // 2, W // 2, 12, generator=torch.Generator().manual_seed(6))
+    dec = torch.nn.functional.pixel_shuffle(dec12.permute(0, 3, 1, 2), 2)
+    fine = torch.nn.functional.pixel_shuffle(feat.permute(0, 3, 1, 2)[:, :3 * b * b], b)
+    for rew in (False, True):
+        rgb, _, _ = ops.assemble_output(feat.to(DEV), dec12.to(DEV), bd.to(DEV), bo.to(DEV), b, rew, feat_channels_last=True,
+                                        dec_pre_shuffle=True)
+        want = dec + fine
+        if rew:
+            want = 0.5 * (want + fine)
+        assert _md(rgb, want) <= 1e-6
+
+
+def test_render_fused_reads_strided_volume(golden):
+    """The feature volume may be the leading 8 channels of a wider channels-last tensor (vol_stride = 12)."""
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    B, V, H, W = spec["B"], spec["V"], spec["H"], spec["W"]
+    cam = _cam(golden, cfg)
+    tex_ref = golden.t("tex_nchw")
+    fd = tex_ref.shape[2] - 3
+    src = ops.prepare_sources(tex_ref[:, :, :fd].contiguous().to(DEV), golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol = ops.to_channels_last(golden.t("feat_volume").to(DEV), 8)
+    wide = torch.randn(*vol.shape[:-1], 12, device=DEV)
+    wide[..., :8] = vol
+    mlp = ops.pack_mlp(golden.mlp(), fd, device=DEV)
+    args = (golden.t("depth_range").to(DEV), golden.t("vol_range").to(DEV), cam, mlp, B, V, H, W, b, cfg.nerf.max_num_samples,
+            cfg.mvs.inv_depth[-1], cfg.nerf.is_adaptive)
+    for prec in (0, 1):
+        a = ops.render_fused(src, vol, *args, precision=prec)
+        c = ops.render_fused(src, wide[..., :8], *args, precision=prec)
+        assert torch.equal(a["feat"], c["feat"]) and torch.equal(a["depth"], c["depth"])
