@@ -46,12 +46,14 @@ def layout(feat_dim: int) -> Tuple[List[Tuple[str, int, Tuple[int, int], int]], 
     return out, off
 
 
-def pack_mlp(params: Mapping[str, torch.Tensor], feat_dim: int, device=None) -> torch.Tensor:
-    """params: the ``nerf.*`` state-dict slice (keys without the prefix)."""
+def pack_mlp(params: Mapping[str, torch.Tensor], feat_dim: int, device=None, detach: bool = True) -> torch.Tensor:
+    """params: the ``nerf.*`` state-dict slice (keys without the prefix).  With ``detach=False`` the block is built
+    with differentiable operators (training: the gradient of the block reaches the parameters)."""
     spec, total = layout(feat_dim)
     chunks = []
     for key, _off, (K, Np), n in spec:
-        t = params[key].detach().to(torch.float32)
+        t = params[key].detach() if detach else params[key]
+        t = t.to(torch.float32)
         if key.endswith(".weight"):
             t = t.reshape(-1, t.shape[-1]) if t.dim() == 2 else t.reshape(1, -1)
             # nn.Linear stores (out, in); vector heads (out == 1) are kept as a single row of K inputs

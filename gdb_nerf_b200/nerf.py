@@ -40,6 +40,10 @@ class NeRF(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self._packed_key: Optional[Tuple] = None
 
+    def packed_autograd(self) -> torch.Tensor:
+        """Packed block built with differentiable operators: gradients of the block flow back to the parameters."""
+        return pack_mlp(dict(self.named_parameters()), self.feat_dim, detach=False)
+
     def packed(self) -> torch.Tensor:
         """Flat parameter block on the parameters' device, re-packed only when a
         parameter was modified (optimizer step, load_state_dict, .to())."""
@@ -75,3 +79,22 @@ class CoarseNeRF(nn.Module):
         self.sigma = nn.Sequential(nn.Linear(hid_dim, 1), nn.Softplus())
         self.color = nn.Sequential(nn.Linear(hid_dim + voxel_dim + 16 + F + 4, hid_dim), nn.ReLU(inplace=True),
                                    nn.Linear(hid_dim, 1), nn.ReLU(inplace=True))
+
+    def forward(self, vox: torch.Tensor, feat_rgb_dir: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """vox (B,N,8), feat_rgb_dir (B,N,V,F+4) -> sigma (B,N), rgb (B,N,3)  (depth_net.py:248-298).
+        PyTorch operators: see coarse.py for the status of this training-only row."""
+        V = feat_rgb_dir.shape[-2]
+        x = feat_rgb_dir[..., :-4]
+        if self.viewdir_agg:
+            x = x + self.view_fc(feat_rgb_dir[..., -4:])
+        var, mean = torch.var_mean(x, dim=-2, keepdim=True)
+        g = self.global_fc(torch.cat((x, var.expand(-1, -1, V, -1), mean.expand(-1, -1, V, -1)), -1))
+        a = torch.softmax(self.agg_w_fc(g), dim=-2)
+        img = self.fc((g * a).sum(-2))
+        vi = torch.cat((vox, img), -1)
+        h = self.lr0(vi)
+        sigma = self.sigma(h)
+        hv = torch.cat((h, vi), -1)[..., None, :].expand(-1, -1, V, -1)
+        w = torch.softmax(self.color(torch.cat((hv, feat_rgb_dir), -1)), dim=-2)
+        rgb = (feat_rgb_dir[..., -7:-4] * w).sum(-2)
+        return sigma.squeeze(-1), rgb

@@ -23,7 +23,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import autograd as AG
 from . import ops
+from .coarse import coarse_render
 from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, decoder_fused, feature_net_fused
 from .nerf import CoarseNeRF, NeRF
 from .sampler import BundleSampler
@@ -58,6 +60,37 @@ class DepthNet(nn.Module):
         self.nerfs = nn.ModuleList([
             CoarseNeRF(config.nerf.nerf_hidden_dims, voxel_dim, self.feat_dims[i], config.nerf.viewdir_agg)
             for i in range(self.num_stages - 1)])
+
+    def forward_train(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far):
+        """Training-mode cascade (depth_net.py:118-198 with self.training): the CNNs run as plain modules (batch-norm
+        in batch-statistics mode, autograd), K1 / K2 through their forward+backward kernel pairs, and every stage but
+        the last also renders the coarse supervision image (row a14)."""
+        B, V, _, H, W = src_images.shape
+        mvs_depths, range_list, vol_list, volume_list, blend_rgbs = [], [], [], [], []
+        depth_range = near_far[..., None, None].contiguous()
+        for s in range(self.num_stages):
+            feats = ms_feats[self.vol_levels[s]]
+            Hi, Wi = int(H * self.vol_scales[s]), int(W * self.vol_scales[s])
+            proj = ops.homography_mats(src_exts, src_ints, tar_exts, tar_ints, self.feat_scales[s], self.vol_scales[s])
+            feat_cl = feats.permute(0, 1, 3, 4, 2).contiguous()                       # autograd permutes the gradient back
+            variance = AG.WarpVariance.apply(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s])
+            volume, prob = self.cost_regs[s](variance)
+            depth, ci, vol_range = AG.DepthRange.apply(depth_range, prob, self.ci_scales[s], self.inv_depth[s])
+            mvs_depths.append(depth.squeeze(1))
+            range_list.append(ci)
+            vol_list.append(vol_range)
+            volume_list.append(volume)
+            depth_range = ci
+            if s < self.num_stages - 1:
+                src_ints_s = src_ints.clone()
+                src_ints_s[..., :2, :] *= self.feat_scales[s]
+                tar_ints_s = tar_ints.clone()
+                tar_ints_s[:, :2, :] *= self.vol_scales[s]
+                blend_rgbs.append(coarse_render(self.nerfs[s], volume, feats, src_images, self.feat_scales[s], src_exts, src_ints_s,
+                                                tar_exts, tar_ints_s, ci, vol_range, self.num_samples[s], self.inv_depth[s]))
+                up = self.vol_scales[s + 1] / self.vol_scales[s]
+                depth_range = F.interpolate(ci, scale_factor=up, mode="bilinear", align_corners=False)
+        return mvs_depths, range_list, vol_list, volume_list, blend_rgbs
 
     def forward(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far, fused_cnn: bool = False):
         B, V, _, H, W = src_images.shape
@@ -139,11 +172,46 @@ class Network(nn.Module):
         self._cl_ready = False      # .to()/.cuda() may re-create parameter storage
         return super()._apply(fn, *args, **kwargs)
 
+    def _forward_train(self, src_images, src_exts, src_ints, tar_exts, tar_ints, near_far):
+        """Differentiable forward (train_net.py / trainer.py:44-66 call sites): every star-marked step runs through a
+        forward + backward kernel pair (autograd.py); the CNNs are plain modules; the output assembly uses PyTorch's
+        pixel-shuffle / bilinear operators (pure data movement with a trivial adjoint)."""
+        B, V, _, H, W = src_images.shape
+        feats = self.feature_net(src_images.flatten(0, 1), levels=self._fpn_levels)
+        ms_feats = [f.unflatten(0, (B, V)) for f in feats]
+        mvs_depths, range_list, vol_list, volume_list, blend_rgbs = self.depth_net.forward_train(
+            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far)
+        if not self.training:
+            blend_rgbs = []
+        depth_range, vol_range, feat_volume, mvs_depth = range_list[-1], vol_list[-1], volume_list[-1], mvs_depths[-1]
+        b = self.b_size
+        Hb, Wb = H // b, W // b
+        if depth_range.shape[2:] != (Hb, Wb):
+            depth_range = F.interpolate(depth_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
+            vol_range = F.interpolate(vol_range, size=(Hb, Wb), mode='bilinear', align_corners=False)
+            mvs_depth = F.interpolate(mvs_depth.unsqueeze(1), size=(Hb, Wb), mode='nearest').squeeze(1)
+        if feat_volume.shape[-2:] != (Hb, Wb):
+            raise ValueError("feature volume resolution must equal the bundle map (true for every shipped recipe)")
+        img_feat = ms_feats[self.feat_level]
+        if img_feat.shape[-2:] != (Hb, Wb):
+            img_feat = F.interpolate(img_feat.flatten(0, 1), size=(Hb, Wb), mode='bilinear', align_corners=False).unflatten(0, (B, V))
+        self.sampler.build_rays(tar_exts, tar_ints, (H, W), near_far[:, 0], near_far[:, 1])
+        cam = self.sampler.camera_block(src_exts, src_ints, b, self.inv_depth)
+        feat, bdepth, bopac = AG.render_fused_train(img_feat, src_images, feat_volume, depth_range, vol_range, cam,
+                                                    self.nerf.packed_autograd(), b, self.max_num_samples,
+                                                    self.sampler.max_mipmap_level, self.inv_depth, self.is_adaptive)
+        R = 3 * b * b
+        rgb_f = F.pixel_shuffle(feat[:, :R], b)
+        rgb_c = self.upsampler(feat[:, R:])
+        nerf_depth = F.interpolate(bdepth.unsqueeze(1), scale_factor=b, mode='bilinear', align_corners=False).squeeze(1)
+        nerf_opacity = F.interpolate(bopac.unsqueeze(1), scale_factor=b, mode='bilinear', align_corners=False).squeeze(1)
+        rgb = rgb_c + rgb_f
+        if self.reweighting:
+            rgb = 0.5 * (rgb + rgb_f)
+        ret = {'rgb': rgb, 'nerf_depth': nerf_depth, 'mvs_depth': mvs_depth, 'opacity': nerf_opacity}
+        return ret, mvs_depths, blend_rgbs
+
     def forward(self, batch: Dict[str, Any]) -> Tuple[Dict[str, torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
-        if self.training:
-            raise NotImplementedError(
-                "gdb_nerf_b200.Network: the training path (coarse NeRF + backward kernels, SURVEY.md section 8 row a14/K4) "
-                "is not built yet; call .eval()")
         src_views, tar_views = batch['src_views'], batch['tar_views']
         near_far = batch['near_far']
         src_images = src_views['rgb']
@@ -164,6 +232,9 @@ class Network(nn.Module):
             H, W = src_images.shape[-2:]
             src_ints[..., :2, :] *= self.render_scale
             tar_ints[:, :2, :] *= self.render_scale
+
+        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.nerf.parameters()):
+            return self._forward_train(src_images, src_exts, src_ints, tar_exts, tar_ints, near_far)
 
         fused = self.cnn_mode == "fused"
         if fused:

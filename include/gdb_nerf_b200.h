@@ -175,6 +175,43 @@ int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const flo
                         int B, int Hb, int Wb, int bundle_size, int reweighting, int layout,
                         float* rgb, float* depth, float* opacity, void* stream);
 
+/* --------------------------------------------------------- backward ------- */
+/* Training configuration (dtu_pretrain.yaml): adjoints of the kernels above,
+ * what torch.autograd derives from the reference's Python (there is no
+ * hand-written backward in the reference).  Buffers documented as
+ * "accumulated" must be zeroed by the caller.                                 */
+
+/* Backward of gdb_warp_variance_fwd (depth_net.py:459-474).  g_variance is
+ * PLANAR (B,C,D,Ht,Wt).  d_feat_cl (B,V,Hs,Ws,C) accumulated; d_depth_range
+ * (B,2,Ht,Wt) accumulated, may be null and is ignored for a 1x1 range.        */
+int gdb_warp_variance_bwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw, int B,
+                          int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth, const float* g_variance,
+                          float* d_feat_cl, float* d_depth_range, void* stream);
+
+/* Backward of gdb_depth_range_fwd (depth_net.py:479-514).  g_depth (B,1,h,w),
+ * g_ci (B,2,h,w), g_vol_range (B,2,h,w): any may be null.  d_prob (B,D,h,w)
+ * written; d_depth_range (B,2,h,w) written (null / ignored for a 1x1 range).  */
+int gdb_depth_range_bwd(const float* depth_range, int rh, int rw, const float* prob, int B, int D, int h, int w,
+                        float ci_scale, int inv_depth, const float* g_depth, const float* g_ci, const float* g_vol_range,
+                        float* d_prob, float* d_depth_range, void* stream);
+
+/* Backward of gdb_render_fused_fwd: recomputes the forward from the same
+ * inputs (nothing is saved), see csrc/gdb_render_bwd.cu.  g_feat
+ * (B,3b^2+F+8,Hb,Wb) planar; g_depth, g_opacity (B,Hb,Wb) or null.
+ * d_mlp (packed block) / d_tex (mip chain) / d_vol (B,D,Hb,Wb,8) accumulated;
+ * d_depth_range, d_vol_range (B,2,Hb,Wb) written.                             */
+int gdb_render_fused_bwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
+                         const float* vol_range, const float* cam, int cam_stride, const float* mlp, int B, int V,
+                         int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int max_samples,
+                         int max_mip_level, int inv_depth, int adaptive, const float* g_feat, const float* g_depth,
+                         const float* g_opacity, float* d_mlp, float* d_tex, float* d_vol, float* d_depth_range,
+                         float* d_vol_range, void* stream);
+
+/* Backward of gdb_prepare_sources with respect to the feature maps: pulls the
+ * mip-level gradients down to level 0 (in place in d_tex) and writes the
+ * feature channels as d_feat (B*V,Cf,Hb,Wb) planar.                           */
+int gdb_prepare_sources_bwd(float* d_tex, int BV, int Cf, int Hb, int Wb, int max_mip_level, float* d_feat, void* stream);
+
 /* --------------------------------------------------------- glue ----------- */
 /* Element-wise epilogues between the kernels above and the cuDNN networks
  * (channels-last fp32, C % 4 == 0; x/out (N,S,C)):

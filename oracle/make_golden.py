@@ -182,8 +182,42 @@ def run_case(name: str, spec: dict) -> None:
           f"injected S={rec['inj_indices'].shape[0]} count hist={hist.tolist()}")
 
 
+GRAD_KEYS = ("nerf.", "depth_net.nerfs.0.", "depth_net.cost_regs.0.prob_head.weight", "depth_net.cost_regs.1.prob_head.weight",
+             "depth_net.cost_regs.1.feat_head.weight", "depth_net.cost_regs.1.conv0.0.weight", "feature_net.conv0.0.0.weight",
+             "feature_net.out1.weight", "feature_net.out0.weight", "upsampler.in_conv.weight")
+
+
+def run_grad_case(name: str, spec: dict) -> None:
+    """Training step of the UNMODIFIED reference under autograd (train mode, batch-norm batch statistics):
+    loss = mean(rgb^2) + sum_i mean(blend_i^2), gradients of a representative parameter subset -> <name>_grad.npz."""
+    import networks.gdb_nerf.network as ref_network
+
+    cfg = make_cfg(spec["recipe"])
+    torch.manual_seed(0)
+    net = ref_network.Network(cfg)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth_state_dict(shapes, seed=1), strict=True)
+    net.train(True)
+    batch = make_batch(spec["B"], spec["V"], spec["H"], spec["W"], spec["near"], spec["far"], spec["focal"],
+                       seed=3, images=spec["images"], tilt=spec["tilt"])
+    ret, mvs_depths, blend = net(batch)
+    loss = ret["rgb"].square().mean() + sum(b.square().mean() for b in blend)
+    loss.backward()
+    rec = {"loss": np.array(float(loss)), "ret_rgb": _np(ret["rgb"]), "ret_nerf_depth": _np(ret["nerf_depth"])}
+    for i, b in enumerate(blend):
+        rec[f"blend_rgb_{i}"] = _np(b)
+    for k, p in net.named_parameters():
+        if any(k.startswith(pref) for pref in GRAD_KEYS):
+            rec["grad_" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+    path = os.path.join(ROOT, "tests", "golden", name + "_grad.npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}_grad: loss={float(loss):.6f}, {len(rec)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for case, spec in CASES.items():
         if not only or case in only:
             run_case(case, spec)
+        if spec["train"] and (not only or case + "_grad" in only):
+            run_grad_case(case, spec)

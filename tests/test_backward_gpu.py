@@ -1,0 +1,212 @@
+"""Gradient parity of the backward kernels (training configuration, SURVEY.md 8b "Autograd") against
+torch.autograd run on the float64 CPU oracle, through the C ABI.  Tolerances are relative to the largest
+gradient entry of each tensor (fp32 kernels + atomics vs an fp64 reference): 2e-3."""
+import pytest
+import torch
+
+from conftest import CASE_SPECS, load_golden
+from gdb_nerf_b200 import autograd as AG
+from gdb_nerf_b200 import ops
+from gdb_nerf_b200.config import make_cfg
+from gdb_nerf_b200.mlp_pack import unpack_grad
+from oracle import gdb_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DD = torch.float64
+RTOL = 2e-3
+
+
+def _rel(got, want):
+    want = want.detach().double().cpu()
+    got = got.detach().double().cpu()
+    return float((got - want).abs().max()) / max(float(want.abs().max()), 1e-30)
+
+
+@pytest.mark.parametrize("case", ["train_b2", "dtu_b2", "nerf_b4"])
+@pytest.mark.parametrize("stage", [0, 1])
+def test_warp_variance_backward(case, stage):
+    g = load_golden(case)
+    cfg = make_cfg(CASE_SPECS[case]["recipe"])
+    s = stage
+    feat = g.t(f"s{s}_src_feat")
+    rng = g.t(f"s{s}_range_in")
+    ref = g.t(f"s{s}_variance")
+    D, Ht, Wt = ref.shape[2:]
+    inv = cfg.mvs.inv_depth[s]
+    proj = O.homography_matrices(g.t("in_src_exts"), g.t(f"s{s}_src_ints"), g.t("in_tar_exts"), g.t(f"s{s}_tar_ints"))
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(s))
+    # oracle, float64
+    f64 = feat.to(DD).requires_grad_(True)
+    r64 = rng.to(DD).requires_grad_(True)
+    var64 = O.warp_variance(f64, proj.to(DD), O.depth_hypotheses(r64, D, inv).expand(-1, -1, Ht, Wt), inv)
+    (var64 * w.to(DD)).sum().backward()
+    # kernels
+    fcl = feat.to(DEV).permute(0, 1, 3, 4, 2).contiguous().requires_grad_(True)
+    rd = rng.to(DEV).requires_grad_(True)
+    var = AG.WarpVariance.apply(fcl, proj.to(DEV), rd, D, Ht, Wt, inv)
+    assert _rel(var, var64) <= 1e-4
+    (var * w.to(DEV)).sum().backward()
+    assert _rel(fcl.grad.permute(0, 1, 4, 2, 3), f64.grad) <= RTOL
+    if rng.shape[-1] != 1:
+        assert _rel(rd.grad, r64.grad) <= RTOL
+    else:
+        assert rd.grad is None                       # near/far of the batch are inputs
+
+
+@pytest.mark.parametrize("case", ["train_b2", "dtu_b2", "nerf_b4"])
+@pytest.mark.parametrize("stage", [0, 1])
+def test_depth_range_backward(case, stage):
+    g = load_golden(case)
+    cfg = make_cfg(CASE_SPECS[case]["recipe"])
+    s = stage
+    rng, prob = g.t(f"s{s}_range_in"), g.t(f"s{s}_prob")
+    B, D, h, w = prob.shape
+    inv = cfg.mvs.inv_depth[s]
+    gen = torch.Generator().manual_seed(7 + s)
+    wd, wc, wv = torch.randn(B, 1, h, w, generator=gen), torch.randn(B, 2, h, w, generator=gen), torch.randn(B, 2, h, w, generator=gen)
+    for ci_scale in (cfg.mvs.ci_scales[s], 0.05):     # the small scale keeps the interval strictly inside the clamps
+        r64 = rng.to(DD).requires_grad_(True)
+        p64 = prob.to(DD).requires_grad_(True)
+        dv = O.depth_hypotheses(r64, D, inv).expand(-1, -1, h, w)
+        d64, c64 = O.depth_interval(dv, p64, ci_scale, inv)
+        v64 = dv[:, [0, -1]]
+        ((d64 * wd.to(DD)).sum() + (c64 * wc.to(DD)).sum() + (v64 * wv.to(DD)).sum()).backward()
+        rd = rng.to(DEV).requires_grad_(True)
+        pd = prob.to(DEV).requires_grad_(True)
+        dep, ci, vol = AG.DepthRange.apply(rd, pd, ci_scale, inv)
+        ((dep * wd.to(DEV)).sum() + (ci * wc.to(DEV)).sum() + (vol * wv.to(DEV)).sum()).backward()
+        assert _rel(pd.grad, p64.grad) <= RTOL
+        if rng.shape[-1] != 1:
+            assert _rel(rd.grad, r64.grad) <= RTOL
+
+
+def _render_inputs(g, cfg):
+    tex = g.t("tex_nchw")
+    fd = tex.shape[2] - 3
+    return dict(fd=fd, feat=tex[:, :, :fd].contiguous(), rgb=g.t("in_rgb"), vol=g.t("feat_volume"))
+
+
+@pytest.mark.parametrize("case,prefix", [("train_b2", ""), ("train_b2", "inj_"), ("dtu_b2", "inj_"), ("nerf_b4", ""), ("nerf_b4", "inj_")])
+def test_render_fused_backward(case, prefix):
+    """dL/d(features, feature volume, depth interval, volume range, MLP parameters) of the fused render."""
+    g = load_golden(case)
+    spec = CASE_SPECS[case]
+    cfg = make_cfg(spec["recipe"])
+    b = cfg.nerf.bundle_size
+    adaptive = True if prefix else cfg.nerf.is_adaptive
+    inv = cfg.mvs.inv_depth[-1]
+    x = _render_inputs(g, cfg)
+    fd = x["fd"]
+    dr, vr = g.t(prefix + "depth_range"), g.t(prefix + "vol_range")
+    B, V = x["feat"].shape[:2]
+    H, W = spec["H"], spec["W"]
+    Hb, Wb = H // b, W // b
+    CT = 3 * b * b + fd + 3 + 8
+    gen = torch.Generator().manual_seed(21)
+    wf = torch.randn(B, CT, Hb, Wb, generator=gen)
+    wd = torch.randn(B, Hb, Wb, generator=gen) * (1.0 / (spec["far"] - spec["near"]))
+    wo = torch.randn(B, Hb, Wb, generator=gen)
+
+    # ---- oracle in float64 with autograd
+    f64 = x["feat"].to(DD).requires_grad_(True)
+    v64 = x["vol"].to(DD).requires_grad_(True)
+    dr64 = dr.to(DD).requires_grad_(True)
+    vr64 = vr.to(DD).requires_grad_(True)
+    mlp64 = {k: v.to(DD).requires_grad_(True) for k, v in g.mlp().items()}
+    out = O.render_bundles(mlp64, fd, x["rgb"].to(DD), f64, v64, dr64, vr64, g.t("in_src_exts").to(DD), g.t("in_src_ints").to(DD),
+                           g.t("in_tar_exts").to(DD), g.t("in_tar_ints").to(DD), g.t("in_near_far").to(DD), b,
+                           cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, inv, adaptive)
+    loss = (out["bundle_feat"] * wf.to(DD)).sum() + (out["bundle_depth"] * wd.to(DD)).sum() + (out["bundle_opacity"] * wo.to(DD)).sum()
+    loss.backward()
+
+    # ---- kernels
+    fdv = x["feat"].to(DEV).requires_grad_(True)
+    vdv = x["vol"].to(DEV).requires_grad_(True)
+    drd = dr.to(DEV).requires_grad_(True)
+    vrd = vr.to(DEV).requires_grad_(True)
+    params = {k: v.to(DEV).requires_grad_(True) for k, v in g.mlp().items()}
+    mlp = ops.pack_mlp(params, fd, detach=False)
+    cam = ops.camera_block(g.t("in_tar_exts").to(DEV), g.t("in_tar_ints").to(DEV), g.t("in_src_exts").to(DEV), g.t("in_src_ints").to(DEV),
+                           g.t("in_near_far").to(DEV), b, cfg.nerf.global_num_depth, inv)
+    feat, depth, opac = AG.render_fused_train(fdv, x["rgb"].to(DEV), vdv, drd, vrd, cam, mlp, b, cfg.nerf.max_num_samples,
+                                              cfg.nerf.max_mipmap_level, inv, adaptive)
+    assert _rel(feat, out["bundle_feat"]) <= 1e-4
+    ((feat * wf.to(DEV)).sum() + (depth * wd.to(DEV)).sum() + (opac * wo.to(DEV)).sum()).backward()
+
+    assert _rel(fdv.grad, f64.grad) <= RTOL, "feature-map gradient"
+    assert _rel(vdv.grad, v64.grad) <= RTOL, "feature-volume gradient"
+    assert _rel(drd.grad, dr64.grad) <= RTOL, "depth-interval gradient"
+    assert _rel(vrd.grad, vr64.grad) <= RTOL, "volume-range gradient"
+    for k in params:
+        assert _rel(params[k].grad, mlp64[k].grad) <= RTOL, k
+
+
+def test_unpack_grad_roundtrip():
+    g = load_golden("dtu_b2")
+    p = g.mlp()
+    flat = ops.pack_mlp(p, 16)
+    back = unpack_grad(flat, 16)
+    for k in p:
+        assert torch.equal(back[k].reshape(p[k].shape), p[k])
+
+
+# ------------------------------------------------------------------ whole training step vs the reference under autograd
+def _train_net(case="train_b2"):
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import batch_to, make_batch, synth_state_dict
+    spec = CASE_SPECS[case]
+    net = Network(make_cfg(spec["recipe"]))
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth_state_dict(shapes, seed=1), strict=True)
+    net = net.to(DEV).train()
+    batch = make_batch(spec["B"], spec["V"], spec["H"], spec["W"], spec["near"], spec["far"], spec["focal"], seed=3,
+                       images=spec["images"], tilt=spec["tilt"])
+    return net, batch_to(batch, DEV), spec
+
+
+def test_training_step_matches_reference_gradients():
+    """fwd + bwd of the whole Network in train mode (BASELINE.json configs[4] code path at test size): loss, outputs and
+    parameter gradients against the UNMODIFIED reference under torch.autograd (tests/golden/train_b2_grad.npz)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gg = load_golden("train_b2_grad")
+        net, batch, spec = _train_net()
+        ret, mvs_depths, blend = net(batch)
+        assert len(blend) == 1 and blend[0].shape == gg.t("blend_rgb_0").shape
+        loss = ret["rgb"].square().mean() + sum(b.square().mean() for b in blend)
+        loss.backward()
+        assert _rel(ret["rgb"], gg.t("ret_rgb")) <= 2e-3
+        assert _rel(blend[0], gg.t("blend_rgb_0")) <= 2e-3
+        assert abs(float(loss) - float(gg.np("loss"))) <= 2e-3 * float(gg.np("loss"))
+        params = dict(net.named_parameters())
+        checked = 0
+        for key in gg._z.files:
+            if not key.startswith("grad_"):
+                continue
+            name = key[5:]
+            want = gg.t(key)
+            got = params[name].grad
+            if float(want.abs().max()) == 0.0:
+                assert got is None or float(got.abs().max()) == 0.0, name
+                continue
+            assert got is not None, f"{name} got no gradient"
+            assert _rel(got, want) <= 2e-2, name       # cuDNN vs MKL-DNN batch-norm / conv backward noise included
+            checked += 1
+        assert checked >= 30
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_training_step_updates_every_trainable_parameter():
+    net, batch, _ = _train_net()
+    ret, _, blend = net(batch)
+    (ret["rgb"].square().mean() + blend[0].square().mean()).backward()
+    missing = [k for k, p in net.named_parameters() if p.grad is None]
+    # the reference's own autograd leaves exactly the unused full-resolution FPN branch without gradient
+    assert all(k.startswith(("feature_net.inner2", "feature_net.out2")) for k in missing), missing
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), k
