@@ -83,7 +83,7 @@ def test_forward_refuses_cpu_and_training():
     batch = make_batch(spec["B"], spec["V"], spec["H"], spec["W"], spec["near"], spec["far"], spec["focal"])
     with pytest.raises(_lib.GdbError, match="CUDA"):
         net(batch)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.GdbError, match="CUDA"):      # the training path has no CPU fallback either
         net.train()(batch)
 
 
