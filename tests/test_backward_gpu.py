@@ -17,10 +17,12 @@ DD = torch.float64
 RTOL = 2e-3
 
 
-def _rel(got, want):
+def _rel(got, want, floor=1e-30):
+    """max |got - want| relative to the largest reference entry (``floor``: smallest scale that counts, for
+    gradients that vanish analytically, e.g. the bias in front of a soft-max over views)."""
     want = want.detach().double().cpu()
     got = got.detach().double().cpu()
-    return float((got - want).abs().max()) / max(float(want.abs().max()), 1e-30)
+    return float((got - want).abs().max()) / max(float(want.abs().max()), floor)
 
 
 @pytest.mark.parametrize("case", ["train_b2", "dtu_b2", "nerf_b4"])
@@ -138,8 +140,9 @@ def test_render_fused_backward(case, prefix):
     assert _rel(vdv.grad, v64.grad) <= RTOL, "feature-volume gradient"
     assert _rel(drd.grad, dr64.grad) <= RTOL, "depth-interval gradient"
     assert _rel(vrd.grad, vr64.grad) <= RTOL, "volume-range gradient"
+    scale = max(float(v.grad.abs().max()) for v in mlp64.values())
     for k in params:
-        assert _rel(params[k].grad, mlp64[k].grad) <= RTOL, k
+        assert _rel(params[k].grad, mlp64[k].grad, floor=1e-3 * scale) <= RTOL, k
 
 
 def test_unpack_grad_roundtrip():
@@ -193,7 +196,7 @@ def test_training_step_matches_reference_gradients():
                 assert got is None or float(got.abs().max()) == 0.0, name
                 continue
             assert got is not None, f"{name} got no gradient"
-            assert _rel(got, want) <= 2e-2, name       # cuDNN vs MKL-DNN batch-norm / conv backward noise included
+            assert _rel(got, want, floor=1e-6) <= 2e-2, name       # cuDNN vs MKL-DNN batch-norm / conv backward noise included
             checked += 1
         assert checked >= 30
     finally:
