@@ -191,6 +191,7 @@ def run_ours(args, wl, cfg):
     spans = {"gdb_render_fused_fwd": [], "gdb_warp_variance_fwd": []}
     recording = {"on": False}
     launches_per_call = {"to_channels_last": 1, "homography_mats": 1, "depth_values": 1, "warp_variance": 1, "depth_range_from_prob": 1,
+                         "depth_range_from_logits": 1, "bias_act_add": 1, "gate_add": 1,
                          "camera_block": 1, "prepare_sources": 1, "render_fused": 1, "assemble_output": 1}
 
     def wrap(name, key=None):
@@ -346,6 +347,77 @@ def run_ours(args, wl, cfg):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE.json configs[4]: DTU pre-training step (fwd + bwd of the fused render path and the rest of the network,
+    gradient all-reduce, clip, Adam) on a 64x64 crop = 1024 bundles per GPU.  One JSON line: training steps are not the
+    headline metric; rays/s here counts the rays of the crops all ranks trained on."""
+    import torch.distributed as dist
+
+    from gdb_nerf_b200.config import make_cfg
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.sharding import allreduce_gradients
+    from gdb_nerf_b200.synthetic import batch_to, make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --mode train needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = make_cfg("dtu_pretrain")
+    torch.manual_seed(0)
+    net = Network(cfg).to(dev)
+    if world > 1:
+        net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)            # as trainer.py:16
+    net.train()
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    crop, B, V = 64, 1, 3
+    batch = batch_to(make_batch(B, V, crop, crop, 425.0, 905.0, 1446.0 * crop / 512.0, seed=100 + rank, images="smooth", tilt=0.03), dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        ret, _, blend = net(batch)
+        loss = ret["rgb"].square().mean() + sum(b.square().mean() for b in blend)
+        loss.backward()
+        nbytes = allreduce_gradients(params)
+        torch.nn.utils.clip_grad_value_(params, 40)                        # trainer.py:64
+        opt.step()
+        return loss, nbytes
+
+    for _ in range(max(args.warmup, 3)):
+        loss, nbytes = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    for _ in range(args.steps):
+        loss, nbytes = step()
+    e.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_step = float(ms[0]) / args.steps
+        print(json.dumps({
+            "metric": "training step (fwd+bwd+allreduce+Adam), DTU pretrain, 64x64 crop = 1024 bundles per GPU", "value": world * B * crop * crop / (ms_step * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "loss": float(loss),
+            "config": {"workload": "dtu_pretrain training step, 3 source views, fixed 6 samples/bundle, 1 crop of 64x64 px per GPU "
+                                   "(BASELINE.json configs[4])", "allreduce_bytes": nbytes,
+                       "parallelism": f"data parallel over {world} GPU(s): one flat-bucket NCCL all-reduce of the gradients per step, SyncBN"},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,7 +427,12 @@ def main():
     ap.add_argument("--workload", choices=["dtu", "llff", "nerf"], default="dtu")
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", choices=["eval", "train"], default="eval", help="train: BASELINE.json configs[4] (not the headline)")
     args = ap.parse_args()
+    if args.mode == "train":
+        if args.steps is None:
+            args.steps = 20
+        return run_train(args)
     from gdb_nerf_b200.config import make_cfg
     from gdb_nerf_b200.synthetic import WORKLOADS
     wl = WORKLOADS[args.workload]

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gdb_nerf_b200.sharding import gather_images, max_over_ranks, shard_rows, shard_views
+from gdb_nerf_b200.sharding import allreduce_gradients, gather_images, max_over_ranks, shard_rows, shard_views
 
 
 def _free_port():
@@ -48,6 +48,51 @@ def test_two_rank_view_sharding_gloo():
     assert sorted(ids[0] + ids[1]) == list(range(n_views)) and not set(ids[0]) & set(ids[1])      # disjoint cover
     assert all(r[2] == 11.0 for r in res)                                                        # max over ranks
     assert res[0][3] == [0.0, 1.0, 2.0, 3.0, 4.0] and res[1][3] is None                          # gathered in view order
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+        x = torch.full((5, 4), float(rank + 1))
+        net[1](net[0](x)).sum().backward()              # the last layer is unused on every rank; the others differ per rank
+        if rank == 1:
+            net[2].weight.grad = torch.ones(2, 2)       # ... except that rank 1 has a gradient for its weight
+        nbytes = allreduce_gradients(net.parameters())
+        q.put((rank, nbytes, [p.grad.clone() for p in net.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_gloo():
+    """One flat-bucket all-reduce averages the gradients; unused parameters behave as zeros (DDP find_unused_parameters)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+    want = None
+    for r in range(world):
+        net.zero_grad()
+        net[1](net[0](torch.full((5, 4), float(r + 1)))).sum().backward()
+        gs = [torch.zeros_like(p) if p.grad is None else p.grad.clone() for p in net.parameters()]
+        want = gs if want is None else [a + b for a, b in zip(want, gs)]
+    want = [g / world for g in want]
+    want[4] = torch.full((2, 2), 0.5)                   # net[2].weight: (0 + 1) / 2
+    assert res[0][1] == res[1][1] == 4 * sum(p.numel() for p in net.parameters())
+    for r in range(world):
+        for got, w in zip(res[r][2], want):
+            assert torch.allclose(got, w, atol=1e-6)
 
 
 def test_shard_helpers_single_process():
