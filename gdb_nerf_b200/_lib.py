@@ -55,6 +55,9 @@ SIGNATURES = {
     "gdb_render_fused_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     "gdb_prepare_sources_bwd": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
+    "gdb_coarse_render_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
+    "gdb_coarse_render_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f,
+                                    c_f, c_f, c_f, c_f]),
     "gdb_bias_act_add": (c_i, [c_f, c_f, c_f, c_i64, c_i64, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
     "gdb_gate_add": (c_i, [c_f, c_f, c_f, c_i64, c_i64, c_i, c_f, c_f]),
     "gdb_assemble_output": (c_i, [c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f]),

@@ -151,3 +151,62 @@ def render_fused_train(feat: Tensor, images: Tensor, feat_volume: Tensor, depth_
     vol_cl = feat_volume.permute(0, 2, 3, 4, 1).contiguous()          # (B,D,Hb,Wb,8); autograd permutes the gradient back
     meta = (Cf, max_mip, B, V, H, W, bundle_size, max_samples, bool(inv_depth), bool(adaptive))
     return RenderFused.apply(tex, rgba, vol_cl, depth_range, vol_range, cam, mlp, meta)
+
+
+class CoarseRender(torch.autograd.Function):
+    """K5 (row a14).  tex: level-0 texture of the stage (flat), vol_cl (B,D,Hi,Wi,8), ray_range / vol_range (B,2,Hi,Wi)
+    -> rgb (B,3,Hi,Wi)."""
+
+    @staticmethod
+    def forward(ctx, tex: Tensor, vol_cl: Tensor, ray_range: Tensor, vol_range: Tensor, cam: Tensor, mlp: Tensor, meta: tuple) -> Tensor:
+        feat_dim, B, V, Hs, Ws, num_samples, inv_depth = meta
+        tex, vol_cl = tex.detach(), _f32(vol_cl.detach())
+        ray_range, vol_range, cam, mlp = _f32(ray_range.detach()), _f32(vol_range.detach()), cam.detach(), _f32(mlp.detach())
+        D, Hi, Wi = vol_cl.shape[1:4]
+        rgb = torch.empty((B, 3, Hi, Wi), device=tex.device, dtype=torch.float32)
+        lib = _lib.load()
+        _lib.check(lib.gdb_coarse_render_fwd(tex.data_ptr(), vol_cl.data_ptr(), ray_range.data_ptr(), vol_range.data_ptr(), cam.data_ptr(),
+                                             cam.shape[1], mlp.data_ptr(), B, V, Hi, Wi, Hs, Ws, feat_dim, D, num_samples, int(inv_depth),
+                                             rgb.data_ptr(), _stream()), "gdb_coarse_render_fwd")
+        ctx.save_for_backward(tex, vol_cl, ray_range, vol_range, cam, mlp)
+        ctx.meta = meta
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        tex, vol_cl, ray_range, vol_range, cam, mlp = ctx.saved_tensors
+        feat_dim, B, V, Hs, Ws, num_samples, inv_depth = ctx.meta
+        D, Hi, Wi = vol_cl.shape[1:4]
+        g_rgb = _f32(g_rgb)
+        d_mlp, d_tex, d_vol = torch.zeros_like(mlp), torch.zeros_like(tex), torch.zeros_like(vol_cl)
+        d_rr, d_vr = torch.empty_like(ray_range), torch.empty_like(vol_range)
+        lib = _lib.load()
+        _lib.check(lib.gdb_coarse_render_bwd(tex.data_ptr(), vol_cl.data_ptr(), ray_range.data_ptr(), vol_range.data_ptr(), cam.data_ptr(),
+                                             cam.shape[1], mlp.data_ptr(), B, V, Hi, Wi, Hs, Ws, feat_dim, D, num_samples, int(inv_depth),
+                                             g_rgb.data_ptr(), d_mlp.data_ptr(), d_tex.data_ptr(), d_vol.data_ptr(), d_rr.data_ptr(),
+                                             d_vr.data_ptr(), _stream()), "gdb_coarse_render_bwd")
+        return d_tex, d_vol, d_rr, d_vr, None, d_mlp, None
+
+
+def coarse_render_train(nerf, feat_volume: Tensor, feats: Tensor, src_images: Tensor, src_exts: Tensor, src_ints_stage: Tensor,
+                        tar_exts: Tensor, tar_ints_stage: Tensor, near_far: Tensor, ray_range: Tensor, vol_range: Tensor,
+                        num_samples: int, inv_depth: bool) -> Tensor:
+    """Differentiable coarse render of one cascade stage (depth_net.py:181-191): same arguments as ``coarse.coarse_render``
+    (the PyTorch restatement kept as the test reference), arithmetic in gdb_coarse.cu."""
+    from .mlp_pack import pack_mlp
+    B, V, Cf, Hs, Ws = feats.shape
+    H = src_images.shape[-2]
+    if H % Hs:
+        raise ValueError("image height must be a multiple of the feature-map height")
+    tex, _rgba = PrepareSources.apply(feats, src_images, H // Hs, 0)
+    vol_cl = feat_volume.permute(0, 2, 3, 4, 1).contiguous()
+    cam = ops.camera_block(tar_exts, tar_ints_stage, src_exts, src_ints_stage, near_far, 1, 1, inv_depth)
+    named = dict(nerf.named_parameters())
+    zeros_w = torch.zeros(8, 64, device=feats.device)
+    params = {k: v for k, v in named.items() if not k.startswith("color.")}
+    params.update({"weight.0.weight": named["color.0.weight"], "weight.0.bias": named["color.0.bias"],
+                   "weight.2.weight": named["color.2.weight"], "weight.2.bias": named["color.2.bias"],
+                   "feat_head.0.weight": zeros_w, "feat_head.0.bias": zeros_w[:, 0]})
+    mlp = pack_mlp(params, Cf, detach=False)
+    meta = (Cf, B, V, Hs, Ws, num_samples, bool(inv_depth))
+    return CoarseRender.apply(tex, vol_cl, ray_range, vol_range, cam, mlp, meta)

@@ -2,10 +2,10 @@
 reference: networks/gdb_nerf/depth_net.py:49-116 `_render_rays`, :301-341 `build_rays`,
 :344-396 `get_img_feat_vectorized`).
 
-Status: this row still runs on PyTorch CUDA operators (autograd supplies its backward) -
-41 k samples per DTU view at 1/8 resolution, < 1 % of the training step.  It is NOT a
-hand-written kernel yet and DESIGN.md says so; everything else on the training path is.
-The arithmetic follows the reference step by step so that `blend_rgbs` matches it.
+Status: TEST REFERENCE.  The product path runs this row on hand-written kernels
+(csrc/gdb_coarse.cu through autograd.CoarseRender / coarse_render_train); this PyTorch-operator
+restatement is what tests/test_backward_gpu.py evaluates in float64 on the CPU to check the
+kernels' outputs and gradients.  The arithmetic follows the reference step by step.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ def coarse_render(nerf, feat_volume: Tensor, feats: Tensor, src_images: Tensor, 
     feat_volume (B,8,D,Hi,Wi); feats (B,V,C,Hs,Ws) FPN level of this stage; ray_range / vol_range (B,2,Hi,Wi)."""
     B, V = feats.shape[:2]
     Hi, Wi = ray_range.shape[-2:]
-    dev, dt = feats.device, torch.float32
+    dev, dt = feats.device, feats.dtype
     n = Hi * Wi
     # rays through the pixel centres (depth_net.py:318-331)
     xs = torch.arange(Wi, device=dev, dtype=dt) + 0.5

@@ -110,11 +110,41 @@ __device__ __forceinline__ float linspace01(int i, int n) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Packed fp32 FMA (FFMA2, sm_100): two IEEE fp32 FMAs per issue slot.  A three-register scalar FFMA issues every
+// other cycle per scheduler on Blackwell, FFMA2 carries two lanes in the same slot, so FMA-bound inner loops
+// (bilinear accumulation, the SIMT MLP) run them pairwise.  Results are bit-identical to two fmaf().
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// lerp(a, b, t) = a + t (b - a) on a pair
+__device__ __forceinline__ unsigned long long lerp2(unsigned long long a, unsigned long long b, unsigned long long tt) {
+  return fma2(tt, sub2(b, a), a);
+}
+// (a0, a1) += (v0, v1) * w
+__device__ __forceinline__ void fma2_acc(float& a0, float& a1, float v0, float v1, unsigned long long ww) {
+  unsigned long long r = fma2(pack2(v0, v1), ww, pack2(a0, a1));
+  unpack2(r, a0, a1);
+}
+
 __device__ __forceinline__ float4 f4_scale_add(float4 acc, float4 v, float w) {
-  acc.x = fmaf(v.x, w, acc.x);
-  acc.y = fmaf(v.y, w, acc.y);
-  acc.z = fmaf(v.z, w, acc.z);
-  acc.w = fmaf(v.w, w, acc.w);
+  const unsigned long long ww = pack2(w, w);
+  fma2_acc(acc.x, acc.y, v.x, v.y, ww);
+  fma2_acc(acc.z, acc.w, v.z, v.w, ww);
   return acc;
 }
 

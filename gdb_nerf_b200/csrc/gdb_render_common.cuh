@@ -32,13 +32,12 @@ struct RenderParams {
 
 template <int N>
 __device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restrict__ wrow, float x) {
+  const unsigned long long xx = pack2(x, x);
 #pragma unroll
   for (int n = 0; n < N; n += 4) {
     float4 w = *reinterpret_cast<const float4*>(wrow + n);
-    acc[n + 0] = fmaf(w.x, x, acc[n + 0]);
-    acc[n + 1] = fmaf(w.y, x, acc[n + 1]);
-    acc[n + 2] = fmaf(w.z, x, acc[n + 2]);
-    acc[n + 3] = fmaf(w.w, x, acc[n + 3]);
+    fma2_acc(acc[n + 0], acc[n + 1], w.x, w.y, xx);        // FFMA2: two outputs per issue slot
+    fma2_acc(acc[n + 2], acc[n + 3], w.z, w.w, xx);
   }
 }
 template <int N>
@@ -51,13 +50,15 @@ __device__ __forceinline__ void load_row(float (&acc)[N], const float* __restric
 }
 template <int N>
 __device__ __forceinline__ float dot_row(const float (&x)[N], const float* __restrict__ row) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int n = 0; n < N; n += 4) {
     float4 w = *reinterpret_cast<const float4*>(row + n);
-    s = fmaf(w.x, x[n + 0], s); s = fmaf(w.y, x[n + 1], s); s = fmaf(w.z, x[n + 2], s); s = fmaf(w.w, x[n + 3], s);
+    unsigned long long acc = fma2(pack2(w.x, w.y), pack2(x[n + 0], x[n + 1]), pack2(s0, s1));
+    acc = fma2(pack2(w.z, w.w), pack2(x[n + 2], x[n + 3]), acc);
+    unpack2(acc, s0, s1);
   }
-  return s;
+  return s0 + s1;
 }
 
 __device__ __forceinline__ void unit3(float& x, float& y, float& z) {
@@ -102,11 +103,13 @@ __device__ __forceinline__ TexTap tex_tap(float u01, float v01, int w, int h) {
 }
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 __device__ __forceinline__ float4 bilerp4(float4 a00, float4 a10, float4 a01, float4 a11, float fu, float fv) {
+  // same operation order as the scalar lerpf form, two channels per instruction (FFMA2 / FADD2)
+  const unsigned long long uu = pack2(fu, fu), vv = pack2(fv, fv);
+  unsigned long long lo = lerp2(lerp2(pack2(a00.x, a00.y), pack2(a10.x, a10.y), uu), lerp2(pack2(a01.x, a01.y), pack2(a11.x, a11.y), uu), vv);
+  unsigned long long hi = lerp2(lerp2(pack2(a00.z, a00.w), pack2(a10.z, a10.w), uu), lerp2(pack2(a01.z, a01.w), pack2(a11.z, a11.w), uu), vv);
   float4 r;
-  r.x = lerpf(lerpf(a00.x, a10.x, fu), lerpf(a01.x, a11.x, fu), fv);
-  r.y = lerpf(lerpf(a00.y, a10.y, fu), lerpf(a01.y, a11.y, fu), fv);
-  r.z = lerpf(lerpf(a00.z, a10.z, fu), lerpf(a01.z, a11.z, fu), fv);
-  r.w = lerpf(lerpf(a00.w, a10.w, fu), lerpf(a01.w, a11.w, fu), fv);
+  unpack2(lo, r.x, r.y);
+  unpack2(hi, r.z, r.w);
   return r;
 }
 

@@ -25,7 +25,6 @@ import torch.nn.functional as F
 
 from . import autograd as AG
 from . import ops
-from .coarse import coarse_render
 from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, decoder_fused, feature_net_fused
 from .nerf import CoarseNeRF, NeRF
 from .sampler import BundleSampler
@@ -86,8 +85,8 @@ class DepthNet(nn.Module):
                 src_ints_s[..., :2, :] *= self.feat_scales[s]
                 tar_ints_s = tar_ints.clone()
                 tar_ints_s[:, :2, :] *= self.vol_scales[s]
-                blend_rgbs.append(coarse_render(self.nerfs[s], volume, feats, src_images, self.feat_scales[s], src_exts, src_ints_s,
-                                                tar_exts, tar_ints_s, ci, vol_range, self.num_samples[s], self.inv_depth[s]))
+                blend_rgbs.append(AG.coarse_render_train(self.nerfs[s], volume, feats, src_images, src_exts, src_ints_s, tar_exts,
+                                                         tar_ints_s, near_far, ci, vol_range, self.num_samples[s], self.inv_depth[s]))
                 up = self.vol_scales[s + 1] / self.vol_scales[s]
                 depth_range = F.interpolate(ci, scale_factor=up, mode="bilinear", align_corners=False)
         return mvs_depths, range_list, vol_list, volume_list, blend_rgbs

@@ -212,6 +212,26 @@ int gdb_render_fused_bwd(const float* rgba, const float* tex, const float* vol_c
  * feature channels as d_feat (B*V,Cf,Hb,Wb) planar.                           */
 int gdb_prepare_sources_bwd(float* d_tex, int BV, int Cf, int Hb, int Wb, int max_mip_level, float* d_feat, void* stream);
 
+/* --------------------------------------------------------- coarse render -- */
+/* Training-only coarse render of every cascade stage but the last, replaces
+ * DepthNet._render_rays depth_net.py:49-116 with build_rays :301-341,
+ * get_img_feat_vectorized :344-396 and the coarse NeRF :248-298.
+ * tex (B*V,Hs,Ws,FP): level 0 of gdb_prepare_sources for the stage's FPN level
+ * (feature | bilinearly down-sampled rgb); vol_cl (B,D,Hi,Wi,8); ray_range,
+ * vol_range (B,2,Hi,Wi); cam: gdb_camera_block built with the STAGE-scaled
+ * intrinsics (bundle_size 1); mlp: packed like the fine MLP with the `color`
+ * head in the weight.0 / weight.2 slots.  One ray per (Hi,Wi) pixel,
+ * num_samples fixed samples.  -> rgb (B,3,Hi,Wi).                             */
+int gdb_coarse_render_fwd(const float* tex, const float* vol_cl, const float* ray_range, const float* vol_range,
+                          const float* cam, int cam_stride, const float* mlp, int B, int V, int Hi, int Wi, int Hs,
+                          int Ws, int feat_dim, int D, int num_samples, int inv_depth, float* rgb, void* stream);
+/* Its backward (recomputes the forward).  d_mlp, d_tex (B*V,Hs,Ws,FP), d_vol
+ * accumulated; d_ray_range, d_vol_range (B,2,Hi,Wi) written.                  */
+int gdb_coarse_render_bwd(const float* tex, const float* vol_cl, const float* ray_range, const float* vol_range,
+                          const float* cam, int cam_stride, const float* mlp, int B, int V, int Hi, int Wi, int Hs,
+                          int Ws, int feat_dim, int D, int num_samples, int inv_depth, const float* g_rgb, float* d_mlp,
+                          float* d_tex, float* d_vol, float* d_ray_range, float* d_vol_range, void* stream);
+
 /* --------------------------------------------------------- glue ----------- */
 /* Element-wise epilogues between the kernels above and the cuDNN networks
  * (channels-last fp32, C % 4 == 0; x/out (N,S,C)):

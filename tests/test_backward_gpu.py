@@ -213,3 +213,64 @@ def test_training_step_updates_every_trainable_parameter():
     for k, p in net.named_parameters():
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), k
+
+
+# ------------------------------------------------------------------ row a14: coarse render kernels vs the PyTorch restatement
+@pytest.mark.parametrize("inv_depth,V", [(True, 3), (False, 2), (True, 4)])
+def test_coarse_render_forward_and_backward(inv_depth, V):
+    """gdb_coarse_render_fwd/bwd against coarse.coarse_render (depth_net.py:49-116 restated with PyTorch operators,
+    itself pinned end-to-end by the reference's blend_rgbs) evaluated in float64 on the CPU."""
+    from gdb_nerf_b200.coarse import coarse_render
+    from gdb_nerf_b200.nerf import CoarseNeRF
+    from gdb_nerf_b200.synthetic import camera_rig, smooth_images
+    B, H, W, Cf, D, S = 2, 32, 40, 32, 16, 8
+    Hs, Ws, Hi, Wi = H // 4, W // 4, H // 8, W // 8
+    near, far = 2.5, 5.5
+    gen = torch.Generator().manual_seed(5)
+    rig = camera_rig(B, V, H, W, near, far, 44.0, tilt=0.05)
+    images = smooth_images(B, V, H, W, seed=2)
+    feats = torch.randn(B, V, Cf, Hs, Ws, generator=gen) * 0.5
+    volume = torch.randn(B, 8, D, Hi, Wi, generator=gen) * 0.5
+    mid = near + (far - near) * (0.3 + 0.4 * torch.rand(B, 1, Hi, Wi, generator=gen))
+    half = 0.1 + 0.3 * torch.rand(B, 1, Hi, Wi, generator=gen)
+    ray_range = torch.cat((mid - half, mid + half), 1)
+    vol_range = torch.cat((torch.full_like(mid, near), torch.full_like(mid, far)), 1)
+    if inv_depth:        # a disparity-spaced volume lists its hypotheses far -> near in depth? no: first = near, last = far (depth units)
+        pass
+    src_ints_s = rig["src_ints"].clone(); src_ints_s[..., :2, :] *= 0.25
+    tar_ints_s = rig["tar_ints"].clone(); tar_ints_s[:, :2, :] *= 0.125
+    torch.manual_seed(3)
+    nerf = CoarseNeRF(64, 8, Cf, True)
+    wout = torch.randn(B, 3, Hi, Wi, generator=gen)
+
+    # ---- reference: PyTorch operators, float64, CPU
+    n64 = CoarseNeRF(64, 8, Cf, True).double()
+    n64.load_state_dict({k: v.double() for k, v in nerf.state_dict().items()})
+    f64 = feats.double().requires_grad_(True)
+    v64 = volume.double().requires_grad_(True)
+    rr64 = ray_range.double().requires_grad_(True)
+    vr64 = vol_range.double().requires_grad_(True)
+    want = coarse_render(n64, v64, f64, images.double(), 0.25, rig["src_exts"].double(), src_ints_s.double(), rig["tar_exts"].double(),
+                         tar_ints_s.double(), rr64, vr64, S, inv_depth)
+    (want * wout.double()).sum().backward()
+
+    # ---- kernels
+    nd = CoarseNeRF(64, 8, Cf, True).to(DEV)
+    nd.load_state_dict(nerf.state_dict())
+    fd = feats.to(DEV).requires_grad_(True)
+    vd = volume.to(DEV).requires_grad_(True)
+    rrd = ray_range.to(DEV).requires_grad_(True)
+    vrd = vol_range.to(DEV).requires_grad_(True)
+    got = AG.coarse_render_train(nd, vd, fd, images.to(DEV), rig["src_exts"].to(DEV), src_ints_s.to(DEV), rig["tar_exts"].to(DEV),
+                                 tar_ints_s.to(DEV), rig["near_far"].to(DEV), rrd, vrd, S, inv_depth)
+    assert got.shape == want.shape
+    assert float((got.detach().cpu().double() - want.detach()).abs().max()) <= 1e-4
+    (got * wout.to(DEV)).sum().backward()
+    assert _rel(fd.grad, f64.grad) <= RTOL, "feature gradient"
+    assert _rel(vd.grad, v64.grad) <= RTOL, "volume gradient"
+    assert _rel(rrd.grad, rr64.grad) <= RTOL, "ray-range gradient"
+    assert _rel(vrd.grad, vr64.grad) <= RTOL, "volume-range gradient"
+    ref_p = dict(n64.named_parameters())
+    scale = max(float(p.grad.abs().max()) for p in ref_p.values())
+    for k, p in nd.named_parameters():
+        assert _rel(p.grad, ref_p[k].grad, floor=1e-3 * scale) <= RTOL, k
