@@ -22,6 +22,14 @@
 // read back with tcgen05.ld (32x32b: thread i of warp w reads lane 32*(w%4)+i).
 // Two groups ping-pong on one SM (their phases interleave freely), sharing one
 // copy of the weights in shared memory and splitting the 512 TMEM columns.
+//
+// SPLIT = true is the fp32-class variant of the same kernel: every operand is
+// stored as TWO fp16 planes, x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
+// (22 significant bits), and every K step issues three MMAs, hi*hi + hi*lo +
+// lo*hi, into the same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22
+// relative).  To keep two groups resident with twice the operand bytes the
+// operand regions are aliased by lifetime and weight.0 runs in two passes
+// ([h|vox|img] slice, then the per-view slice, same accumulator).
 #include <cuda_fp16.h>
 
 #include "gdb_render_common.cuh"
@@ -105,8 +113,34 @@ __device__ __forceinline__ void store_chunk(unsigned char* abase, int chunk, int
   *reinterpret_cast<uint4*>(abase + (size_t)chunk * 2048 + row * 16) = q;
 }
 
+// hi/lo fp16 planes of eight fp32 values: x = hi + lo to 22 bits
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    float2 back = __half22float2(hh);
+    __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+template <bool SPLIT>
+__device__ __forceinline__ void store_chunk_p(unsigned char* abase, int lo_off, int chunk, int row, const float (&v)[8]) {
+  if constexpr (SPLIT) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(abase + (size_t)chunk * 2048 + row * 16) = hi;
+    *reinterpret_cast<uint4*>(abase + lo_off + (size_t)chunk * 2048 + row * 16) = lo;
+  } else {
+    store_chunk(abase, chunk, row, v);
+  }
+}
+
 // ------------------------------------------------------------ configuration --
-template <int BS, int FEAT_DIM, int V>
+template <int BS, int FEAT_DIM, int V, bool SPLIT>
 struct TcCfg {
   using ML = MlpLayout<FEAT_DIM>;
   static constexpr int BB = BS * BS;
@@ -115,13 +149,14 @@ struct TcCfg {
   static constexpr int R = 3 * BB;
   static constexpr int CT = R + F + 8;
   static constexpr int RFD = R + F + 4;
+  static constexpr int P = SPLIT ? 2 : 1;                    // fp16 planes per operand
   // K extents (multiples of 16) of the A operands
   static constexpr int K_GS = ((2 * F + 15) / 16) * 16;      // [var | mean]
   static constexpr int K_GX = ((F + 15) / 16) * 16;          // x_v
   static constexpr int K_IM = 32;
   static constexpr int K_HVI = 96;                           // [h(64) | vox(8) | img(16) | 0(8)]
   static constexpr int K_FD = ((F + 4 + 15) / 16) * 16;      // [featrgb_v | dir_v]
-  // fp16 weight matrices in shared memory (bytes), UMMA B layout [K/8][N][8]
+  // fp16 weight matrices in shared memory (bytes), UMMA B layout [K/8][N][8]; the lo plane follows at +W_PLANE
   static constexpr int W_GS = 0;
   static constexpr int W_GX = W_GS + 32 * K_GS * 2;
   static constexpr int W_FC = W_GX + 32 * K_GX * 2;
@@ -129,7 +164,8 @@ struct TcCfg {
   static constexpr int W_SH = W_LR0 + 64 * 32 * 2;
   static constexpr int W_0S = W_SH + 16 * 64 * 2;
   static constexpr int W_0V = W_0S + 64 * K_HVI * 2;
-  static constexpr int W_END = W_0V + 64 * K_FD * 2;
+  static constexpr int W_PLANE = W_0V + 64 * K_FD * 2;
+  static constexpr int W_END = W_PLANE * P;
   // fp32 vectors (floats, after the matrices)
   static constexpr int X_VIEW_W = 0;                 // [4][FP]
   static constexpr int X_VIEW_B = X_VIEW_W + 4 * FP;
@@ -144,16 +180,27 @@ struct TcCfg {
   static constexpr int X_END = X_SCAL + 4;
   static constexpr int VEC_OFF = ((W_END + 127) / 128) * 128;
   static constexpr int GROUP_OFF = ((VEC_OFF + X_END * 4 + 127) / 128) * 128;
-  // per-group A operands (bytes); a chunk is 128 rows x 16 B = 2 KB
-  static constexpr int A_GS = 0;                               // later aliased by A_IM
-  static constexpr int A_GX = A_GS + (K_GS / 8) * 2048;        // V buffers
-  static constexpr int A_HVI = A_GX + V * (K_GX / 8) * 2048;
-  static constexpr int A_FD = A_HVI + (K_HVI / 8) * 2048;      // V buffers
-  static constexpr int A_END = A_FD + V * (K_FD / 8) * 2048;
+  // per-group A operands (bytes); a chunk is 128 rows x 16 B = 2 KB; the lo plane of a region follows its hi plane.
+  //   region S : [var|mean] (GEMM 1), then the aggregated 32-vector (GEMM 2)
+  //   region X : x_v of all views (GEMM 1), then [h|vox|img|0] (GEMM 3, 4) and - two-pass mode - [featrgb_v|dir_v] (GEMM 4b)
+  //   region D : [featrgb_v|dir_v], one-pass mode only (written with the gathers, read by GEMM 4)
+  static constexpr bool TWO_PASS = SPLIT;
+  static constexpr int CH_S = K_GS / 8;
+  static constexpr int CH_X0 = V * (K_GX / 8) > K_HVI / 8 ? V * (K_GX / 8) : K_HVI / 8;
+  static constexpr int CH_X = (TWO_PASS && V * (K_FD / 8) > CH_X0) ? V * (K_FD / 8) : CH_X0;
+  static constexpr int CH_D = TWO_PASS ? 0 : V * (K_FD / 8);
+  static constexpr int LO_S = CH_S * 2048, LO_X = CH_X * 2048, LO_D = CH_D * 2048;       // plane sizes = lo offsets
+  static constexpr int A_GS = 0;
+  static constexpr int A_X = A_GS + P * LO_S;
+  static constexpr int A_GX = A_X;
+  static constexpr int A_HVI = A_X;
+  static constexpr int A_FD = TWO_PASS ? A_X : A_X + P * LO_X;
+  static constexpr int LO_FD = TWO_PASS ? LO_X : LO_D;
+  static constexpr int A_END = A_X + P * LO_X + P * LO_D;
   static constexpr int CAM_OFF = A_END + 128;                  // after the mbarrier: camera block of the tile's view
   static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
   // fine colours are gathered with the other taps (before the MLP) and kept in registers when they fit
-  static constexpr bool EARLY_RGB = (3 * BB * V <= 48);
+  static constexpr bool EARLY_RGB = (3 * BB * V <= 48) && !SPLIT;
   // TMEM columns per group
   static constexpr int T_W0 = 0;      // V x 64
   static constexpr int T_LR0 = 0;     // 64 (consumed before W0 is issued)
@@ -165,12 +212,13 @@ struct TcCfg {
   static constexpr int SMEM = GROUP_OFF + NG * GROUP_BYTES;
   static_assert(64 * V + 32 <= T_COLS && 64 + 32 * V <= 64 * V, "TMEM column plan");
   static_assert(SMEM <= 227 * 1024, "shared memory plan");
-  static_assert(K_IM / 8 <= K_GS / 8, "A_IM aliases A_GS");
+  static_assert(K_IM / 8 <= CH_S, "A_IM aliases A_GS");
 };
 
 // weights: fp32 packed [K][N] block (global) -> fp16 UMMA B operand [K/8][N][8] in shared memory
-__device__ __forceinline__ void stage_b(unsigned char* dst, const float* __restrict__ src, int src_row0, int rows_valid, int N, int Kpad,
-                                        int tid, int nthreads) {
+template <bool SPLIT>
+__device__ __forceinline__ void stage_b(unsigned char* dst, int lo_off, const float* __restrict__ src, int src_row0, int rows_valid, int N,
+                                        int Kpad, int tid, int nthreads) {
   for (int i = tid; i < (Kpad / 8) * N; i += nthreads) {
     int c = i / N, n = i % N;
     float v[8];
@@ -179,23 +227,39 @@ __device__ __forceinline__ void stage_b(unsigned char* dst, const float* __restr
       int k = c * 8 + j;
       v[j] = k < rows_valid ? __ldg(src + (size_t)(src_row0 + k) * N + n) : 0.f;
     }
-    uint4 q = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dst + (size_t)i * 16) = q;
+    if constexpr (SPLIT) {
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(dst + (size_t)i * 16) = hi;
+      *reinterpret_cast<uint4*>(dst + lo_off + (size_t)i * 16) = lo;
+    } else {
+      uint4 q = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dst + (size_t)i * 16) = q;
+    }
   }
 }
 
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int N, int ksteps, uint32_t accumulate) {
+// D (+)= A B over `ksteps` K steps of 16.  SPLIT: hi*hi + hi*lo + lo*hi per step (lo planes at a_addr + a_lo, b_addr + b_lo).
+template <bool SPLIT>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lo, uint32_t b_addr, uint32_t b_lo, int N, int ksteps,
+                                           uint32_t accumulate) {
   const uint32_t idesc = umma_idesc_f16(N);
   for (int ks = 0; ks < ksteps; ++ks) {
     uint64_t ad = umma_desc(a_addr + ks * 2 * 2048, 2048, 128);
     uint64_t bd = umma_desc(b_addr + ks * 2 * (N * 16), N * 16, 128);
     umma_f16(d_tmem, ad, bd, idesc, (ks > 0 || accumulate) ? 1u : 0u);
+    if constexpr (SPLIT) {
+      uint64_t adl = umma_desc(a_addr + a_lo + ks * 2 * 2048, 2048, 128);
+      uint64_t bdl = umma_desc(b_addr + b_lo + ks * 2 * (N * 16), N * 16, 128);
+      umma_f16(d_tmem, ad, bdl, idesc, 1u);
+      umma_f16(d_tmem, adl, bd, idesc, 1u);
+    }
   }
 }
 
-template <int BS, int FEAT_DIM, int V>
+template <int BS, int FEAT_DIM, int V, bool SPLIT>
 __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p) {
-  using C = TcCfg<BS, FEAT_DIM, V>;
+  using C = TcCfg<BS, FEAT_DIM, V, SPLIT>;
   using ML = typename C::ML;
   constexpr int BB = C::BB, F = C::F, FP = C::FP, R = C::R, CT = C::CT;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -211,12 +275,12 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
   // ---- one-time setup: weights -> smem (fp16 B operands + fp32 vectors), mbarriers, TMEM
   {
     const float* m = p.mlp;
-    stage_b(smem + C::W_GS, m + ML::GLOB_W, F, 2 * F, 32, C::K_GS, tid, blockDim.x);
-    stage_b(smem + C::W_GX, m + ML::GLOB_W, 0, F, 32, C::K_GX, tid, blockDim.x);
-    stage_b(smem + C::W_FC, m + ML::FC_W, 0, 32, 16, C::K_IM, tid, blockDim.x);
-    stage_b(smem + C::W_LR0, m + ML::LR0_W, 0, 24, 64, 32, tid, blockDim.x);
-    stage_b(smem + C::W_0S, m + ML::W0_W, 0, 88, 64, C::K_HVI, tid, blockDim.x);
-    stage_b(smem + C::W_0V, m + ML::W0_W, 88, F + 4, 64, C::K_FD, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_GS, C::W_PLANE, m + ML::GLOB_W, F, 2 * F, 32, C::K_GS, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_GX, C::W_PLANE, m + ML::GLOB_W, 0, F, 32, C::K_GX, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_FC, C::W_PLANE, m + ML::FC_W, 0, 32, 16, C::K_IM, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_LR0, C::W_PLANE, m + ML::LR0_W, 0, 24, 64, 32, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_0S, C::W_PLANE, m + ML::W0_W, 0, 88, 64, C::K_HVI, tid, blockDim.x);
+    stage_b<SPLIT>(smem + C::W_0V, C::W_PLANE, m + ML::W0_W, 88, F + 4, 64, C::K_FD, tid, blockDim.x);
     // [sigma | feat_head] as one N=16 operand: n=0 sigma, n=1..8 geometry head
     for (int i = tid; i < 8 * 16; i += blockDim.x) {
       int c = i / 16, n = i % 16;
@@ -226,8 +290,15 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         int k = c * 8 + j;
         v[j] = n == 0 ? __ldg(m + ML::SIG_W + k) : (n <= 8 ? __ldg(m + ML::FH_W + k * 8 + (n - 1)) : 0.f);
       }
-      uint4 q = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(smem + C::W_SH + (size_t)i * 16) = q;
+      if constexpr (SPLIT) {
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(smem + C::W_SH + (size_t)i * 16) = hi;
+        *reinterpret_cast<uint4*>(smem + C::W_SH + C::W_PLANE + (size_t)i * 16) = lo;
+      } else {
+        uint4 q = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(smem + C::W_SH + (size_t)i * 16) = q;
+      }
     }
     for (int i = tid; i < 5 * FP; i += blockDim.x) vec[C::X_VIEW_W + i] = m[ML::VIEW_W + i];   // W [4][FP] + b [FP]
     for (int i = tid; i < 32; i += blockDim.x) { vec[C::X_GLOB_B + i] = m[ML::GLOB_B + i]; vec[C::X_AGG_W + i] = m[ML::AGG_W + i]; }
@@ -238,8 +309,6 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     for (int i = tid; i < 8; i += blockDim.x) vec[C::X_FH_B + i] = m[ML::FH_B + i];
     if (tid == 0) { vec[C::X_SCAL + 0] = m[ML::AGG_B]; vec[C::X_SCAL + 1] = m[ML::SIG_B]; vec[C::X_SCAL + 2] = m[ML::W2_B]; }
     if (row == 0) mbar_init(mbar, 1);
-    // the constant zero chunk of [h|vox|img|0]
-    *reinterpret_cast<uint4*>(gsm + C::A_HVI + 11 * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                    "r"(C::T_COLS * C::NG)
@@ -336,7 +405,6 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         reinterpret_cast<float4*>(p.tap_vox + srow * 8)[1] = hi;
       }
     }
-    store_chunk(gsm + C::A_HVI, 8, row, vox);
 
     // ---- per view: level of detail, mip-mapped feature fetch, direction features; registers keep fp32 copies
     float fr[V][FP];      // feature + rgb per view (fp32, for the final blend)
@@ -347,6 +415,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
       for (int c = 0; c < FP; ++c) { fr[v][c] = 0.f; xv[v][c] = 0.f; }
     }
     float col[C::EARLY_RGB ? V : 1][C::EARLY_RGB ? R : 1];     // fine colours per view (channel-major, then ray)
+    float dirs[C::TWO_PASS ? V : 1][4];                        // direction features, kept for the second weight.0 pass
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const float* cv = head + CAM_HEAD + CAM_VIEW * v;
@@ -444,23 +513,28 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         t = fmaf(vec[C::X_VIEW_W + 3 * FP + c], dir[3], t);
         xv[v][c] = active ? fr[v][c] + fmaxf(t, 0.f) : 0.f;
       }
-      // A operands of this view: x_v and [featrgb_v | dir_v]
+      // A operands of this view: x_v and (one-pass mode) [featrgb_v | dir_v]
 #pragma unroll
       for (int ch = 0; ch < C::K_GX / 8; ++ch) {
         float t8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) t8[j] = (ch * 8 + j < F) ? xv[v][ch * 8 + j] : 0.f;
-        store_chunk(gsm + C::A_GX + v * (C::K_GX / 8) * 2048, ch, row, t8);
+        store_chunk_p<SPLIT>(gsm + C::A_GX + v * (C::K_GX / 8) * 2048, C::LO_X, ch, row, t8);
       }
+      if constexpr (C::TWO_PASS) {
 #pragma unroll
-      for (int ch = 0; ch < C::K_FD / 8; ++ch) {
-        float t8[8];
+        for (int j = 0; j < 4; ++j) dirs[v][j] = dir[j];
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = ch * 8 + j;
-          t8[j] = k < F ? fr[v][k < F ? k : 0] : (k < F + 4 ? dir[(k - F) & 3] : 0.f);
+        for (int ch = 0; ch < C::K_FD / 8; ++ch) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = ch * 8 + j;
+            t8[j] = k < F ? fr[v][k < F ? k : 0] : (k < F + 4 ? dir[(k - F) & 3] : 0.f);
+          }
+          store_chunk(gsm + C::A_FD + v * (C::K_FD / 8) * 2048, ch, row, t8);
         }
-        store_chunk(gsm + C::A_FD + v * (C::K_FD / 8) * 2048, ch, row, t8);
       }
     }
     // [var | mean] over views (nerf.py:73)
@@ -485,7 +559,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         float t8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) t8[j] = vm[ch * 8 + j];
-        store_chunk(gsm + C::A_GS, ch, row, t8);
+        store_chunk_p<SPLIT>(gsm + C::A_GS, C::LO_S, ch, row, t8);
       }
     }
 
@@ -498,8 +572,9 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
       tc_fence_after();
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        issue_gemm(tmem_group + C::T_G + v * 32, a_base + C::A_GS, w_base + C::W_GS, 32, C::K_GS / 16, 0);
-        issue_gemm(tmem_group + C::T_G + v * 32, a_base + C::A_GX + v * (C::K_GX / 8) * 2048, w_base + C::W_GX, 32, C::K_GX / 16, 1);
+        issue_gemm<SPLIT>(tmem_group + C::T_G + v * 32, a_base + C::A_GS, C::LO_S, w_base + C::W_GS, C::W_PLANE, 32, C::K_GS / 16, 0);
+        issue_gemm<SPLIT>(tmem_group + C::T_G + v * 32, a_base + C::A_GX + v * (C::K_GX / 8) * 2048, C::LO_X, w_base + C::W_GX, C::W_PLANE, 32,
+                          C::K_GX / 16, 1);
       }
       umma_commit(mbar);
     }
@@ -539,7 +614,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         float t8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) t8[j] = im[ch * 8 + j];
-        store_chunk(gsm + C::A_GS, ch, row, t8);            // A_IM aliases A_GS (its GEMM has completed)
+        store_chunk_p<SPLIT>(gsm + C::A_GS, C::LO_S, ch, row, t8);   // A_IM aliases A_GS (its GEMM has completed)
       }
     }
     // ================= GEMM 2: fc =================
@@ -548,7 +623,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      issue_gemm(tmem_group + C::T_FC, a_base + C::A_GS, w_base + C::W_FC, 16, C::K_IM / 16, 0);
+      issue_gemm<SPLIT>(tmem_group + C::T_FC, a_base + C::A_GS, C::LO_S, w_base + C::W_FC, C::W_PLANE, 16, C::K_IM / 16, 0);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -558,13 +633,17 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
       tmem_ld16(tmem_row + C::T_FC, img);
 #pragma unroll
       for (int k = 0; k < 16; ++k) img[k] = fmaxf(img[k] + vec[C::X_FC_B + k], 0.f);
+      // region X held x_v until GEMM 1 completed; from here on it is [h | vox | img | 0]
       float t8[8];
+      store_chunk_p<SPLIT>(gsm + C::A_HVI, C::LO_X, 8, row, vox);
 #pragma unroll
       for (int j = 0; j < 8; ++j) t8[j] = img[j];
-      store_chunk(gsm + C::A_HVI, 9, row, t8);
+      store_chunk_p<SPLIT>(gsm + C::A_HVI, C::LO_X, 9, row, t8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) t8[j] = img[8 + j];
-      store_chunk(gsm + C::A_HVI, 10, row, t8);
+      store_chunk_p<SPLIT>(gsm + C::A_HVI, C::LO_X, 10, row, t8);
+      *reinterpret_cast<uint4*>(gsm + C::A_HVI + 11 * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+      if constexpr (SPLIT) *reinterpret_cast<uint4*>(gsm + C::A_HVI + C::LO_X + 11 * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
     }
     // ================= GEMM 3: lr0 on [vox | img | 0] =================
     tc_fence_before();
@@ -572,7 +651,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      issue_gemm(tmem_group + C::T_LR0, a_base + C::A_HVI + 8 * 2048, w_base + C::W_LR0, 64, 2, 0);
+      issue_gemm<SPLIT>(tmem_group + C::T_LR0, a_base + C::A_HVI + 8 * 2048, C::LO_X, w_base + C::W_LR0, C::W_PLANE, 64, 2, 0);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -586,7 +665,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
         float t8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) t8[j] = fmaxf(h[ch * 8 + j] + vec[C::X_LR0_B + half * 32 + ch * 8 + j], 0.f);
-        store_chunk(gsm + C::A_HVI, half * 4 + ch, row, t8);
+        store_chunk_p<SPLIT>(gsm + C::A_HVI, C::LO_X, half * 4 + ch, row, t8);
       }
     }
     // ================= GEMM 4: [sigma | feat_head] and weight.0 =================
@@ -595,16 +674,47 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      issue_gemm(tmem_group + C::T_SH, a_base + C::A_HVI, w_base + C::W_SH, 16, 4, 0);
+      issue_gemm<SPLIT>(tmem_group + C::T_SH, a_base + C::A_HVI, C::LO_X, w_base + C::W_SH, C::W_PLANE, 16, 4, 0);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        issue_gemm(tmem_group + C::T_W0 + v * 64, a_base + C::A_HVI, w_base + C::W_0S, 64, C::K_HVI / 16, 0);
-        issue_gemm(tmem_group + C::T_W0 + v * 64, a_base + C::A_FD + v * (C::K_FD / 8) * 2048, w_base + C::W_0V, 64, C::K_FD / 16, 1);
+        issue_gemm<SPLIT>(tmem_group + C::T_W0 + v * 64, a_base + C::A_HVI, C::LO_X, w_base + C::W_0S, C::W_PLANE, 64, C::K_HVI / 16, 0);
+        if constexpr (!C::TWO_PASS)
+          issue_gemm<SPLIT>(tmem_group + C::T_W0 + v * 64, a_base + C::A_FD + v * (C::K_FD / 8) * 2048, C::LO_FD, w_base + C::W_0V, C::W_PLANE,
+                            64, C::K_FD / 16, 1);
       }
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
     tc_fence_after();
+    if constexpr (C::TWO_PASS) {
+      // second pass of weight.0: [featrgb_v | dir_v] replaces [h|vox|img] in region X (its MMAs have completed)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int ch = 0; ch < C::K_FD / 8; ++ch) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = ch * 8 + j;
+            t8[j] = k < F ? fr[v][k < F ? k : 0] : (k < F + 4 ? dirs[v][(k - F) & 3] : 0.f);
+          }
+          store_chunk_p<SPLIT>(gsm + C::A_FD + v * (C::K_FD / 8) * 2048, C::LO_FD, ch, row, t8);
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      group_sync(g);
+      if (row == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          issue_gemm<SPLIT>(tmem_group + C::T_W0 + v * 64, a_base + C::A_FD + v * (C::K_FD / 8) * 2048, C::LO_FD, w_base + C::W_0V, C::W_PLANE,
+                            64, C::K_FD / 16, 1);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, parity); parity ^= 1;
+      tc_fence_after();
+    }
     float sigma, fh[8], wv[V];
     {
       float sh[16];
@@ -752,10 +862,10 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
   }
 }
 
-template <int BS, int FEAT_DIM, int V>
+template <int BS, int FEAT_DIM, int V, bool SPLIT>
 static int launch_render_tc(const RenderParams& p, cudaStream_t st) {
-  using C = TcCfg<BS, FEAT_DIM, V>;
-  auto kern = render_tc_kernel<BS, FEAT_DIM, V>;
+  using C = TcCfg<BS, FEAT_DIM, V, SPLIT>;
+  auto kern = render_tc_kernel<BS, FEAT_DIM, V, SPLIT>;
   static bool ready = false;
   if (!ready) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -771,9 +881,10 @@ static int launch_render_tc(const RenderParams& p, cudaStream_t st) {
   return cuda_check("gdb_render_fused_fwd(tc)");
 }
 
-int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
-#define GDB_R(BSZ, FD, VV) \
-  if (bundle_size == BSZ && feat_dim == FD && V == VV) return launch_render_tc<BSZ, FD, VV>(p, st);
+int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int split, cudaStream_t st) {
+#define GDB_R(BSZ, FD, VV)                                                                   \
+  if (bundle_size == BSZ && feat_dim == FD && V == VV)                                        \
+    return split ? launch_render_tc<BSZ, FD, VV, true>(p, st) : launch_render_tc<BSZ, FD, VV, false>(p, st);
   GDB_R(2, 16, 2) GDB_R(2, 16, 3) GDB_R(2, 16, 4) GDB_R(4, 32, 2) GDB_R(4, 32, 3) GDB_R(4, 32, 4)
 #undef GDB_R
   return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc): (bundle_size=%d, feat_dim=%d, V=%d) not instantiated", bundle_size, feat_dim, V);

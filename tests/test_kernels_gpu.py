@@ -382,3 +382,41 @@ def test_render_fused_reads_strided_volume(golden):
         a = ops.render_fused(src, vol, *args, precision=prec)
         c = ops.render_fused(src, wide[..., :8], *args, precision=prec)
         assert torch.equal(a["feat"], c["feat"]) and torch.equal(a["depth"], c["depth"])
+
+
+@pytest.mark.parametrize("prefix", ["", "inj_"])
+def test_render_fused_split_precision_tensor_core(golden, prefix):
+    """precision=2: MLP GEMMs on tcgen05 with every operand split into two fp16 planes (hi + lo, three MMAs per K step,
+    fp32 accumulation in TMEM) - the fp32 class of BASELINE.json's north star: same tolerances as the SIMT fp32 kernel."""
+    cfg = _cfg(golden)
+    spec = CASE_SPECS[golden.name]
+    b = cfg.nerf.bundle_size
+    adaptive = True if prefix else cfg.nerf.is_adaptive
+    tex_ref = golden.t("tex_nchw")
+    B, V, F, Hb, Wb = tex_ref.shape
+    feat_dim = F - 3
+    cam = _cam(golden, cfg)
+    dr, vr = golden.t(prefix + "depth_range").to(DEV), golden.t(prefix + "vol_range").to(DEV)
+    sl = ops.sample_bundles(dr, vr, cam, b, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive, want_rays=False)
+    src = ops.prepare_sources(tex_ref[:, :, :feat_dim].contiguous().to(DEV), golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(golden.t("feat_volume").to(DEV), 8)
+    mlp = ops.pack_mlp(golden.mlp(), feat_dim, device=DEV)
+    args = (src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples, cfg.mvs.inv_depth[-1], adaptive)
+    sp = ops.render_fused(*args, taps=sl, precision=2)
+    ref32 = ops.render_fused(*args, taps=sl, precision=0)
+    torch.cuda.synchronize()
+    noise = 3e-4 if spec["images"] == "noise" else 1e-4
+    assert _md(sp["sigma"], golden.t(prefix + "sigma")) <= 1e-4
+    assert _md(sp["sample_feat"], golden.t(prefix + "feat")) <= noise
+    assert _md(sp["weights"], golden.t(prefix + "weights")) <= 1e-4
+    ref_feat = golden.t(prefix + "bundle_feat").view(B, Hb, Wb, -1).permute(0, 3, 1, 2)
+    assert _md(sp["feat"], ref_feat) <= noise
+    assert _md(sp["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 1e-4 * (spec["far"] - spec["near"])
+    assert _md(sp["opacity"].reshape(-1), golden.t(prefix + "bundle_opacity")) <= 1e-5
+    # and it agrees with the SIMT fp32 kernel to a few fp32 ulps of the activations
+    assert _md(sp["sigma"], ref32["sigma"]) <= 2e-5
+    assert _md(sp["feat"], ref32["feat"]) <= 2e-5
+    split = ops.render_fused(*args, precision=2, out_channels_last=True)
+    R = 3 * b * b
+    assert torch.equal(split["fine"].permute(0, 3, 1, 2), sp["feat"][:, :R])
+    assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), sp["feat"][:, R:])

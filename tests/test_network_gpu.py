@@ -114,14 +114,14 @@ def test_full_size_sampling_properties_and_counts():
     assert torch.equal(idx, torch.repeat_interleave(torch.arange(NB), counts))
 
 
-@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("nerf", 0), ("nerf", 1)])
+@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("dtu", 2), ("nerf", 0), ("nerf", 1), ("nerf", 2)])
 def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
     """BASELINE.json sizes (DTU 512x640 2x2 bundles, NeRF-synthetic 800x800 4x4 bundles): parity with the oracle on
     identical inputs plus size-independent properties.  precision 1 = tensor-core MLP (2e-3 class)."""
     cfg, w, rig, data, mlp, feat_dim = _full_size_inputs(workload)
     b = cfg.nerf.bundle_size
     H, W = w["H"], w["W"]
-    tol = 1e-4 if precision == 0 else 2e-3
+    tol = 2e-3 if precision == 1 else 1e-4
 
     def run(order):
         o = torch.tensor(order)
@@ -136,7 +136,7 @@ def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
     out = run([0, 1, 2])
     # property: aggregation over source views is symmetric
     perm = run([2, 0, 1])
-    assert _md(out["feat"], perm["feat"]) <= (2e-5 if precision == 0 else 1e-3)
+    assert _md(out["feat"], perm["feat"]) <= (1e-3 if precision == 1 else 2e-5)
     assert _md(out["depth"], perm["depth"]) <= tol * (w["far"] - w["near"])
     # property: weights are renormalised per bundle -> opacity == 1
     assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
