@@ -1,0 +1,816 @@
+// K3, second-generation tensor-core variant (precision 1: fp16 operands, fp32 accumulation in TMEM).
+//
+// Reference: bundle_sampler.py:193-371, nerf.py:58-115, utils.py:19-43,88-121.
+//
+// Same arithmetic contract as gdb_render_tc.cu (SPLIT = false); what changed is how the work is laid out on the SM:
+//
+//  * NG = 4 tiles of 128 sample rows are in flight per SM (16 warps, <= 128 registers) instead of 2 x 4 warps at 255
+//    registers.  A tile needs 23 operand chunks (46 KB): the regions are aliased by lifetime
+//        X  [x_v | 1] per view      -> after GEMM 1: [h (8 chunks) | vox]
+//        S  [var | mean]            -> after GEMM 1: aggregated 32-vector -> after GEMM 2: img
+//        FD [featrgb_v | dir_v]     -> read again for the final blend, then (with X) the per-ray colour stash
+//    and a tile owns only 128 TMEM columns (weight.0 runs view by view through two 64-column buffers).
+//  * Every warp owns 32 rows end to end (geometry, gathers, epilogues, compositing), so the only cross-warp
+//    synchronisation is the barrier in front of each MMA issue.
+//  * Geometry is computed once per (row, view) with thread = row; the feature fetch then runs with
+//    lane = (row, 16-byte quad of the texel): tap addresses and weights are redistributed by warp shuffles and each
+//    LDG.128 of a warp covers whole texels (80 / 144 contiguous bytes) instead of 32 unrelated lines.  The quad lanes
+//    write the fp16 operand chunks directly.
+//  * Fine colours are fetched after the view weights are known with lane = (row, ray): the four rays of a bundle read
+//    neighbouring source pixels, the blend over views and the compositing weight are applied in registers and the
+//    sum over a bundle's samples runs per (bundle, ray) from a small shared-memory stash (no shuffles).
+//  * All biases ride in the GEMMs (a constant-one K slot), the [var|mean] product is not repeated per view, and the
+//    loops over gather iterations / rays are rolled: the kernel is ~4x smaller than the first tcgen05 variant, whose
+//    top stall reason was instruction fetch.
+#include <cuda_fp16.h>
+
+#include "gdb_render_common.cuh"
+
+#include "gdb_tcgen05.cuh"
+
+namespace gdb {
+
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+template <int BS, int FEAT_DIM, int V, int NG>
+struct Tc2Cfg {
+  using ML = MlpLayout<FEAT_DIM>;
+  static constexpr int BB = BS * BS;
+  static constexpr int F = ML::F;
+  static constexpr int FP = ML::FP;
+  static constexpr int R = 3 * BB;
+  static constexpr int CT = R + F + 8;
+  static constexpr int RFD = R + F + 4;
+  static constexpr int QL = FP / 4;                    // 16-byte quads per texel = lanes per row in the feature fetch
+  static constexpr int IPW = 32 / QL;                  // rows per warp iteration of the feature fetch
+  static constexpr int NIT = (32 + IPW - 1) / IPW;
+  static_assert(F == FP - 1, "the texel has exactly one pad channel (F = feat_dim + 3, feat_dim a multiple of 4)");
+  static_assert(QL % 2 == 1, "the last quad starts a chunk");
+  // operand chunks (a chunk = 8 K values x 128 rows x fp16 = 2 KB)
+  static constexpr int XCH = (F + 1 + 7) / 8;          // [x_v (F) | 1]
+  static constexpr int FDCH = (F + 4 + 7) / 8;         // [featrgb_v (F) | dir_v (4)]
+  static constexpr int SCH = (2 * FP + 7) / 8;         // [var (FP) | mean (FP)]
+  static constexpr int KS_X = (XCH + 1) / 2, KS_FD = (FDCH + 1) / 2, KS_S = (SCH + 1) / 2;   // K steps of 16
+  static constexpr int CH_X = cmax(V * XCH, 9);        // later [h (8) | vox]
+  static constexpr int CH_FD = V * FDCH;
+  static constexpr int CH_S = cmax(SCH, 4);            // later the aggregated vector (4), then img (2)
+  // fp16 weight matrices (bytes), UMMA B layout [K/8][N][8]
+  static constexpr int W_GS = 0;
+  static constexpr int W_GX = W_GS + 32 * KS_S * 32;
+  static constexpr int W_FC = W_GX + 32 * KS_X * 32;
+  static constexpr int W_LR0 = W_FC + 16 * 32 * 2;
+  static constexpr int W_SH = W_LR0 + 64 * 32 * 2;
+  static constexpr int W_0S = W_SH + 16 * 64 * 2;
+  static constexpr int W_0V = W_0S + 64 * 96 * 2;
+  static constexpr int W_END = W_0V + 64 * KS_FD * 32;
+  // fp32 vectors (floats)
+  static constexpr int X_VIEW_W = 0;                   // [4][FP]
+  static constexpr int X_VIEW_B = X_VIEW_W + 4 * FP;   // [FP]
+  static constexpr int X_AGG_W = X_VIEW_B + FP;        // 32
+  static constexpr int X_FC_B = X_AGG_W + 32;          // 16
+  static constexpr int X_W2_W = X_FC_B + 16;           // 64
+  static constexpr int X_FH_B = X_W2_W + 64;           // 8
+  static constexpr int X_SCAL = X_FH_B + 8;            // agg_b, sig_b, w2_b, pad
+  static constexpr int X_END = X_SCAL + 4;
+  static constexpr int VEC_OFF = ((W_END + 127) / 128) * 128;
+  static constexpr int GROUP_OFF = ((VEC_OFF + X_END * 4 + 127) / 128) * 128;
+  // per-group regions (bytes from the group base); S lies after X so that chunk pairs (X[8], S[0]) have a positive stride
+  static constexpr int A_X = 0;
+  static constexpr int A_FD = A_X + CH_X * 2048;
+  static constexpr int A_S = A_FD + CH_FD * 2048;
+  static constexpr int A_END = A_S + CH_S * 2048;
+  static constexpr int CAM_OFF = A_END + 128;          // mbarrier at A_END
+  static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
+  static constexpr int ZERO_OFF = GROUP_OFF + NG * GROUP_BYTES;   // constant chunks after every group
+  static constexpr int ONE_OFF = ZERO_OFF + 2048;
+  static constexpr int SMEM = ONE_OFF + 2048;
+  // per-(row, ray) weighted colours: a warp uses its own rows' 512 B of the first BB chunks of X + FD
+  static_assert(BB <= CH_X + CH_FD, "colour stash must fit in X + FD");
+  static constexpr int NC = F + 10;                    // composited channels: featrgb (F), geometry head (8), depth, opacity
+  static constexpr int NCP = NC <= 32 ? 32 : 64;       // padded row of the transposition stash (swizzled by float4)
+  static_assert(32 * NCP * 4 <= 512 * (CH_X + CH_FD), "compositing stash must fit in the warp's rows of X + FD");
+  // TMEM columns per group
+  static constexpr int TC = cmin(512 / NG, 256);
+  static constexpr int NB = TC / 64;                   // 64-column buffers for weight.0
+  static_assert(V * 32 <= TC && NB >= 2, "TMEM column plan");
+  static constexpr int ROUNDS = 1 + (cmax(V - (NB - 1), 0) + NB - 1) / NB;
+  __host__ __device__ static constexpr int round_start(int r) { return r == 0 ? 0 : (NB - 1) + (r - 1) * NB; }
+  __host__ __device__ static constexpr int round_n(int r) { return cmax(0, cmin(r == 0 ? NB - 1 : NB, V - round_start(r))); }
+};
+
+// weights: fp32 packed block (global) -> fp16 UMMA B operand [Kpad/8][N][8]; value(k, n) supplied by the caller
+template <class Fn>
+__device__ __forceinline__ void stage_b2(unsigned char* dst, int N, int Kpad, int tid, int nthreads, Fn value) {
+  for (int i = tid; i < (Kpad / 8) * N; i += nthreads) {
+    const int c = i / N, n = i - c * N;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = value(c * 8 + j, n);
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 16) =
+        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  }
+}
+
+// one K step (16) of D (+)= A B: the two A chunks may live anywhere (a1 > a0), B K steps are contiguous
+__device__ __forceinline__ void mma_step(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b_addr, int N, uint32_t accumulate) {
+  umma_f16(d_tmem, umma_desc(a0, a1 - a0, 128), umma_desc(b_addr, N * 16, 128), umma_idesc_f16(N), accumulate);
+}
+// `nch` consecutive chunks starting at `a` (odd counts pair the last chunk with the zero chunk)
+__device__ __forceinline__ void mma_chunks(uint32_t d_tmem, uint32_t a, int nch, uint32_t zero_chunk, uint32_t b_addr, int N,
+                                           uint32_t accumulate) {
+  for (int ks = 0; 2 * ks < nch; ++ks) {
+    const uint32_t a0 = a + ks * 4096;
+    const uint32_t a1 = (2 * ks + 1 < nch) ? a0 + 2048 : zero_chunk;
+    mma_step(d_tmem, a0, a1, b_addr + ks * 2 * (N * 16), N, (ks > 0 || accumulate) ? 1u : 0u);
+  }
+}
+
+// F.normalize(eps = 1e-12) with a reciprocal square root (2 ulp): the result feeds fp16 operands
+__device__ __forceinline__ void unit3_fast(float& x, float& y, float& z) {
+  const float inv = rsqrtf(fmaxf(x * x + y * y + z * z, 1e-24f));
+  x *= inv; y *= inv; z *= inv;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+template <int BS, int FEAT_DIM, int V, int NG>
+__global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
+  using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
+  using ML = typename C::ML;
+  constexpr int BB = C::BB, F = C::F, FP = C::FP, R = C::R, CT = C::CT, QL = C::QL, IPW = C::IPW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  float* vec = reinterpret_cast<float*>(smem + C::VEC_OFF);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid >> 7;                      // group = tile slot
+  const int row = tid & 127;                   // sample row == TMEM lane
+  const int wq = warp & 3;
+  unsigned char* gsm = smem + C::GROUP_OFF + (size_t)g * C::GROUP_BYTES;
+  const uint32_t mbar = smem_u32(gsm + C::A_END);
+  const unsigned full = 0xffffffffu;
+
+  // ---- one-time setup: weights -> smem (fp16 B operands + fp32 vectors), constant chunks, mbarriers, TMEM
+  {
+    const float* m = p.mlp;
+    const int nt = blockDim.x;
+    // [var | mean] rows of global_fc: k < F -> var_k, FP <= k < FP + F -> mean_(k - FP)
+    stage_b2(smem + C::W_GS, 32, C::KS_S * 16, tid, nt, [&](int k, int n) {
+      return k < F ? __ldg(m + ML::GLOB_W + (size_t)(F + k) * 32 + n)
+                   : (k >= FP && k < FP + F ? __ldg(m + ML::GLOB_W + (size_t)(2 * F + k - FP) * 32 + n) : 0.f);
+    });
+    // [x_v | 1]: the constant-one slot carries global_fc's bias
+    stage_b2(smem + C::W_GX, 32, C::KS_X * 16, tid, nt, [&](int k, int n) {
+      return k < F ? __ldg(m + ML::GLOB_W + (size_t)k * 32 + n) : (k == F ? __ldg(m + ML::GLOB_B + n) : 0.f);
+    });
+    stage_b2(smem + C::W_FC, 16, 32, tid, nt, [&](int k, int n) { return __ldg(m + ML::FC_W + k * 16 + n); });
+    // [vox (8) | img (16) | 1 | 0]
+    stage_b2(smem + C::W_LR0, 64, 32, tid, nt, [&](int k, int n) {
+      return k < 24 ? __ldg(m + ML::LR0_W + k * 64 + n) : (k == 24 ? __ldg(m + ML::LR0_B + n) : 0.f);
+    });
+    // [sigma | feat_head] as one N = 16 operand: n = 0 sigma, n = 1..8 geometry head
+    stage_b2(smem + C::W_SH, 16, 64, tid, nt, [&](int k, int n) {
+      return n == 0 ? __ldg(m + ML::SIG_W + k) : (n <= 8 ? __ldg(m + ML::FH_W + k * 8 + (n - 1)) : 0.f);
+    });
+    // [h (64) | vox (8) | img (16) | 1 | 0]
+    stage_b2(smem + C::W_0S, 64, 96, tid, nt, [&](int k, int n) {
+      return k < 88 ? __ldg(m + ML::W0_W + (size_t)k * 64 + n) : (k == 88 ? __ldg(m + ML::W0_B + n) : 0.f);
+    });
+    // [featrgb_v (F) | dir_v (4) | 0]
+    stage_b2(smem + C::W_0V, 64, C::KS_FD * 16, tid, nt,
+             [&](int k, int n) { return k < F + 4 ? __ldg(m + ML::W0_W + (size_t)(88 + k) * 64 + n) : 0.f; });
+    for (int i = tid; i < 5 * FP; i += nt) vec[C::X_VIEW_W + i] = m[ML::VIEW_W + i];   // W [4][FP] + b [FP]
+    for (int i = tid; i < 32; i += nt) vec[C::X_AGG_W + i] = m[ML::AGG_W + i];
+    for (int i = tid; i < 16; i += nt) vec[C::X_FC_B + i] = m[ML::FC_B + i];
+    for (int i = tid; i < 64; i += nt) vec[C::X_W2_W + i] = m[ML::W2_W + i];
+    for (int i = tid; i < 8; i += nt) vec[C::X_FH_B + i] = m[ML::FH_B + i];
+    if (tid == 0) { vec[C::X_SCAL + 0] = m[ML::AGG_B]; vec[C::X_SCAL + 1] = m[ML::SIG_B]; vec[C::X_SCAL + 2] = m[ML::W2_B]; }
+    for (int i = tid; i < 128; i += nt) {
+      *reinterpret_cast<uint4*>(smem + C::ZERO_OFF + i * 16) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem + C::ONE_OFF + i * 16) = make_uint4(0x3C00u, 0, 0, 0);    // fp16 1.0 in K slot 0
+    }
+    if (row == 0) mbar_init(mbar, 1);
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                   "r"(C::TC * NG)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tmem_group = tmem_base_s + g * C::TC;                      // column offset of my group
+  const uint32_t tmem_row = tmem_group + ((uint32_t)(wq * 32) << 16);       // my warp's lane quarter
+  uint32_t parity = 0;
+
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t zero_chunk = w_base + C::ZERO_OFF, one_chunk = w_base + C::ONE_OFF;
+  const uint32_t aX = smem_u32(gsm) + C::A_X, aFD = smem_u32(gsm) + C::A_FD, aS = smem_u32(gsm) + C::A_S;
+  unsigned char* const sX = gsm + C::A_X;
+  unsigned char* const sFD = gsm + C::A_FD;
+  unsigned char* const sS = gsm + C::A_S;
+
+  const int HW = p.Hb * p.Wb;
+  const int ns = p.max_samples;
+  const int G = 32 / ns;                                   // bundles per warp
+  const int tiles_pv = (HW + 4 * G - 1) / (4 * G);         // tiles per target view (a tile = 4 warps x G bundles, one view)
+  const int tiles = p.B * tiles_pv;
+  const int bl = lane / ns, slot = lane - bl * ns;
+  const int seg_base = bl * ns;
+  float* scam = reinterpret_cast<float*>(gsm + C::CAM_OFF);
+  const float* head = scam;
+  int cur_b = -1;
+
+  // lane roles of the feature fetch: lane = (row-in-iteration, quad)
+  const int gr = lane / QL, gq = lane - gr * QL;
+  const bool glane = lane < IPW * QL;
+  const bool last_quad = gq == QL - 1;
+  float vw[4][4], vb[4];                                   // view_fc weights of my quad's four channels
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = (glane ? gq : 0) * 4 + e;
+    vb[e] = vec[C::X_VIEW_B + c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vw[j][e] = vec[C::X_VIEW_W + j * FP + c];
+  }
+  const float4* tex4 = reinterpret_cast<const float4*>(p.tex);
+  const float inv_Wb = 1.f / (float)p.Wb, inv_Hb = 1.f / (float)p.Hb, two_W = 2.f / (float)p.W, two_H = 2.f / (float)p.H;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x * NG + g; tile < tiles; tile += gridDim.x * NG) {
+    const int b = tile / tiles_pv;                         // uniform over the group
+    if (b != cur_b) {                                      // stage this view's camera block
+      group_sync(g);
+      for (int i = row; i < CAM_HEAD + CAM_VIEW * V; i += 128) scam[i] = p.cam[(size_t)b * p.cam_stride + i];
+      group_sync(g);
+      cur_b = b;
+    }
+    const int pix_warp0 = ((tile - b * tiles_pv) * 4 + wq) * G;       // first bundle of my warp
+    const int pix_raw = pix_warp0 + bl;
+    const bool has_bundle = bl < G && pix_raw < HW;
+    const int pix = has_bundle ? pix_raw : 0;
+    const int bidx = b * HW + pix;
+    const int yb = pix / p.Wb, xb = pix - yb * p.Wb;
+
+    // =========================== P0: sample placement (thread = row) ===========================
+    float nr = p.depth_range[(size_t)(b * 2 + 0) * HW + pix], fr_ = p.depth_range[(size_t)(b * 2 + 1) * HW + pix];
+    float vn = p.vol_range[(size_t)(b * 2 + 0) * HW + pix], vf = p.vol_range[(size_t)(b * 2 + 1) * HW + pix];
+    const int n = bundle_sample_count(nr, fr_, head[CAM_MINIV], ns, p.inv_depth, p.adaptive);
+    if (p.inv_depth) { nr = fdiv(1.f, nr); fr_ = fdiv(1.f, fr_); vn = fdiv(1.f, vn); vf = fdiv(1.f, vf); }
+    const bool active = has_bundle && slot < n;
+    float z, dnorm;
+    sample_depth(nr, fr_, vn, vf, n, slot, p.inv_depth, z, dnorm);
+    BundleGeom<BS> geo;
+    geo.init(head, yb, xb, p.H, p.W);
+    const float ox = head[CAM_O + 0], oy = head[CAM_O + 1], oz = head[CAM_O + 2];
+    const int64_t srow = (p.offsets && active) ? (int64_t)p.offsets[bidx] + slot : -1;
+
+    float cwx = 0.f, cwy = 0.f, cwz = 0.f;
+#pragma unroll
+    for (int j = 0; j < BB; ++j) {
+      float dx, dy, dz;
+      geo.ray_dir(head, j, dx, dy, dz);
+      cwx += fmaf(dx, z, ox); cwy += fmaf(dy, z, oy); cwz += fmaf(dz, z, oz);
+    }
+    cwx *= (1.f / BB); cwy *= (1.f / BB); cwz *= (1.f / BB);
+    float ball;
+    {
+      float ex = cwx - ox, ey = cwy - oy, ez = cwz - oz;
+      ball = sqrtf(ex * ex + ey * ey + ez * ez) * geo.unit_ball;
+    }
+
+    // ---- voxel feature (bundle_sampler.py:322-324), kept as one packed fp16 chunk until region X is free
+    uint4 voxh = make_uint4(0, 0, 0, 0);
+    if (active) {
+      float ix = fminf(fmaxf(((geo.u + 1.f) * (float)p.Wb - 1.f) * 0.5f, 0.f), (float)(p.Wb - 1));
+      float iy = fminf(fmaxf(((geo.v + 1.f) * (float)p.Hb - 1.f) * 0.5f, 0.f), (float)(p.Hb - 1));
+      float iz = fminf(fmaxf(((dnorm + 1.f) * (float)p.D - 1.f) * 0.5f, 0.f), (float)(p.D - 1));
+      float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+      float tx = ix - x0f, ty = iy - y0f, tz = iz - z0f;
+      int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+      int x1 = min(x0 + 1, p.Wb - 1), y1 = min(y0 + 1, p.Hb - 1), z1 = min(z0 + 1, p.D - 1);
+      const float* vb_ = p.vol + (size_t)b * p.D * HW * p.vol_stride;
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
+        float w = ((k & 1) ? tx : 1.f - tx) * ((k & 2) ? ty : 1.f - ty) * ((k & 4) ? tz : 1.f - tz);
+        const float* tp = vb_ + ((size_t)(zz * p.Hb + yy) * p.Wb + xx) * p.vol_stride;
+        lo = f4_scale_add(lo, ldg4(tp), w);
+        hi = f4_scale_add(hi, ldg4(tp + 4), w);
+      }
+      voxh = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
+      if (p.tap_vox) {
+        reinterpret_cast<float4*>(p.tap_vox + srow * 8)[0] = lo;
+        reinterpret_cast<float4*>(p.tap_vox + srow * 8)[1] = hi;
+      }
+    }
+
+    // ====================== P1: per-view fetch descriptors (thread = row) ======================
+    // a0/a1: float4 index of tap (0,0) at mip levels l0/l1; pk: row strides and flags; bilinear fractions; direction features
+    int d_a0[V], d_a1[V];
+    uint32_t d_pk[V];
+    float d_fu0[V], d_fv0[V], d_fu1[V], d_fv1[V], d_fr[V], d_dir[V][4];
+    float tdx = cwx - ox, tdy = cwy - oy, tdz = cwz - oz;      // unit vector target camera -> sample (view independent)
+    unit3_fast(tdx, tdy, tdz);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float* cv = head + CAM_HEAD + CAM_VIEW * v;
+      // centre of the bundle's points in the source camera frame (bundle_sampler.py:340; the mean commutes with the rigid map)
+      const float ccx = fmaf(cwx, cv[CV_E + 0], fmaf(cwy, cv[CV_E + 1], fmaf(cwz, cv[CV_E + 2], cv[CV_E + 3])));
+      const float ccy = fmaf(cwx, cv[CV_E + 4], fmaf(cwy, cv[CV_E + 5], fmaf(cwz, cv[CV_E + 6], cv[CV_E + 7])));
+      const float ccz = fmaf(cwx, cv[CV_E + 8], fmaf(cwy, cv[CV_E + 9], fmaf(cwz, cv[CV_E + 10], cv[CV_E + 11])));
+      // mip level (:343-348): only its fractional part reaches the output, approximate division is ample
+      const float dist = sqrtf(ccx * ccx + ccy * ccy + ccz * ccz);
+      const float sec = __fdividef(dist, ccz);
+      const float sec_sq = sec * sec;
+      const float rb = __fdividef(dist, ball);
+      const float foot = __fdividef(sec_sq, sqrtf(fmaxf(rb * rb - 1.f, 1e-12f)) + sqrtf(fmaxf(sec_sq - 1.f, 1e-12f)));
+      const float lod = log2f(__fdividef(foot, cv[CV_PIXR]));
+      constexpr float ifb = 1.f / (float)BS;                  // power of two: exact
+      const float pxc = fmaf(ccx, cv[CV_K + 0] * ifb, fmaf(ccy, cv[CV_K + 1] * ifb, ccz * (cv[CV_K + 2] * ifb)));
+      const float pyc = fmaf(ccx, cv[CV_K + 3] * ifb, fmaf(ccy, cv[CV_K + 4] * ifb, ccz * (cv[CV_K + 5] * ifb)));
+      const float pzc = fmaxf(fmaf(ccx, cv[CV_K + 6], fmaf(ccy, cv[CV_K + 7], ccz * cv[CV_K + 8])), 1e-6f);
+      const float rz = fdiv(1.f, pzc);
+      const float u01 = pxc * rz * inv_Wb, v01 = pyc * rz * inv_Hb;
+      d_a0[v] = 0; d_a1[v] = 0; d_pk[v] = 0;
+      d_fu0[v] = d_fv0[v] = d_fu1[v] = d_fv1[v] = d_fr[v] = 0.f;
+      d_dir[v][0] = d_dir[v][1] = d_dir[v][2] = d_dir[v][3] = 0.f;
+      if (active) {
+        float flod = fminf(fmaxf(lod, 0.f), (float)p.L);
+        if (!(flod >= 0.f)) flod = 0.f;
+        int l0 = (int)floorf(flod);
+        int l1 = min(l0 + 1, p.L);
+        const bool tri = flod > 0.f;
+        int w0 = p.Wb >> l0, h0 = p.Hb >> l0, w1 = p.Wb >> l1, h1 = p.Hb >> l1;
+        TexTap ta = tex_tap(u01, v01, w0, h0);
+        TexTap tb = tex_tap(u01, v01, w1, h1);
+        d_a0[v] = (int)(p.tex_level[l0] >> 2) + ((b * V + v) * h0 * w0 + ta.o00) * QL;
+        d_a1[v] = (int)(p.tex_level[l1] >> 2) + ((b * V + v) * h1 * w1 + tb.o00) * QL;
+        d_pk[v] = (uint32_t)((ta.o01 - ta.o00) * QL) | ((uint32_t)((tb.o01 - tb.o00) * QL) << 14) |
+                  ((uint32_t)(ta.o10 - ta.o00) << 28) | ((uint32_t)(tb.o10 - tb.o00) << 29) | ((tri ? 1u : 0u) << 30) | (1u << 31);
+        d_fu0[v] = ta.fu; d_fv0[v] = ta.fv; d_fu1[v] = tb.fu; d_fv1[v] = tb.fv; d_fr[v] = flod - (float)l0;
+        float sx = cwx - cv[CV_C + 0], sy = cwy - cv[CV_C + 1], sz = cwz - cv[CV_C + 2];
+        unit3_fast(sx, sy, sz);
+        float ddx = tdx - sx, ddy = tdy - sy, ddz = tdz - sz;
+        unit3_fast(ddx, ddy, ddz);
+        d_dir[v][0] = ddx; d_dir[v][1] = ddy; d_dir[v][2] = ddz; d_dir[v][3] = tdx * sx + tdy * sy + tdz * sz;
+        if (p.tap_rfd) {
+          float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow) * C::RFD + R + F;
+          tp[0] = ddx; tp[1] = ddy; tp[2] = ddz; tp[3] = d_dir[v][3];
+        }
+      }
+    }
+
+    // ================= P2: mip-mapped feature fetch, lane = (row, quad) =================
+    // writes FD_v = [featrgb_v | dir_v], X_v = [x_v | 1] (nerf.py:69-71) and S = [var | mean] over views (nerf.py:73)
+#pragma unroll 1
+    for (int it = 0; it < C::NIT; ++it) {
+      const int src_raw = it * IPW + gr;
+      const bool ok = glane && src_raw < 32;
+      const int src = min(src_raw, 31);
+      const int orow16 = (wq * 32 + src) * 16;
+      const int64_t srow_g = __shfl_sync(full, srow, src);
+      float xq[V][4];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int a0 = __shfl_sync(full, d_a0[v], src), a1 = __shfl_sync(full, d_a1[v], src);
+        const uint32_t pk = __shfl_sync(full, d_pk[v], src);
+        const float fu0 = __shfl_sync(full, d_fu0[v], src), fv0 = __shfl_sync(full, d_fv0[v], src);
+        const float fu1 = __shfl_sync(full, d_fu1[v], src), fv1 = __shfl_sync(full, d_fv1[v], src);
+        const float frac = __shfl_sync(full, d_fr[v], src);
+        float dir[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dir[j] = __shfl_sync(full, d_dir[v][j], src);
+        const bool act = ok && (pk >> 31);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+          const int dy0 = pk & 0x3FFF, dy1 = (pk >> 14) & 0x3FFF;
+          const int dx0 = ((pk >> 28) & 1) * QL, dx1 = ((pk >> 29) & 1) * QL;
+          const int i0 = a0 + gq;
+          f = bilerp4(__ldg(tex4 + i0), __ldg(tex4 + (i0 + dx0)), __ldg(tex4 + (i0 + dy0)), __ldg(tex4 + (i0 + dy0 + dx0)), fu0, fv0);
+          if ((pk >> 30) & 1) {
+            const int i1 = a1 + gq;
+            float4 bq = bilerp4(__ldg(tex4 + i1), __ldg(tex4 + (i1 + dx1)), __ldg(tex4 + (i1 + dy1)), __ldg(tex4 + (i1 + dy1 + dx1)), fu1, fv1);
+            f.x = lerpf(f.x, bq.x, frac); f.y = lerpf(f.y, bq.y, frac); f.z = lerpf(f.z, bq.z, frac); f.w = lerpf(f.w, bq.w, frac);
+          }
+          if (p.tap_rfd) {
+            float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
+            tp[0] = f.x; tp[1] = f.y; tp[2] = f.z;
+            if (!last_quad) tp[3] = f.w;
+          }
+        }
+        // view_fc + residual, my four channels
+        float fe[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = vb[e];
+          t = fmaf(vw[0][e], dir[0], t);
+          t = fmaf(vw[1][e], dir[1], t);
+          t = fmaf(vw[2][e], dir[2], t);
+          t = fmaf(vw[3][e], dir[3], t);
+          xq[v][e] = act ? fe[e] + fmaxf(t, 0.f) : 0.f;
+        }
+        if (ok) {
+          unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * 2048 + orow16;
+          unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * 2048 + orow16;
+          if (last_quad) {
+            // featrgb's pad channel is K slot F: dir_v follows in FD, the constant one in X
+            *reinterpret_cast<uint4*>(fdp) = make_uint4(pack_h2(f.x, f.y), pack_h2(f.z, dir[0]), pack_h2(dir[1], dir[2]), pack_h2(dir[3], 0.f));
+            *reinterpret_cast<uint4*>(xp) = make_uint4(pack_h2(xq[v][0], xq[v][1]), pack_h2(xq[v][2], act ? 1.f : 0.f), 0u, 0u);
+            xq[v][3] = 0.f;
+          } else {
+            *reinterpret_cast<uint2*>(fdp + (gq & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+            *reinterpret_cast<uint2*>(xp + (gq & 1) * 8) = make_uint2(pack_h2(xq[v][0], xq[v][1]), pack_h2(xq[v][2], xq[v][3]));
+          }
+        }
+      }
+      if (ok) {
+        float var[4], mean[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float mu = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) mu += xq[v][e];
+          mu *= (1.f / V);
+          float s2 = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) { float t = xq[v][e] - mu; s2 = fmaf(t, t, s2); }
+          var[e] = s2 * (1.f / (V - 1));
+          mean[e] = mu;
+        }
+        const int kv = gq, km = QL + gq;      // quad positions of var / mean inside S
+        *reinterpret_cast<uint2*>(sS + (kv >> 1) * 2048 + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
+        *reinterpret_cast<uint2*>(sS + (km >> 1) * 2048 + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
+      }
+    }
+
+    // ================= GEMM 1: global_fc, G_v = [var|mean] W_gs + [x_v|1] W_gx =================
+    tc_fence_before();
+    fence_async_smem();
+    group_sync(g);
+    if (row == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int v = 0; v < V; ++v) {
+        mma_chunks(tmem_group + v * 32, aS, C::SCH, zero_chunk, w_base + C::W_GS, 32, 0);
+        mma_chunks(tmem_group + v * 32, aX + v * C::XCH * 2048, C::XCH, zero_chunk, w_base + C::W_GX, 32, 1);
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, parity); parity ^= 1;
+    tc_fence_after();
+    {
+      // pass 1: aggregation logits (re-reading TMEM keeps only one view's 32 columns live)
+      float aw[V];
+#pragma unroll 1
+      for (int v = 0; v < V; ++v) {
+        float gv[32];
+        tmem_ld32(tmem_row + v * 32, gv);
+        float s = vec[C::X_SCAL + 0];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s = fmaf(fmaxf(gv[k], 0.f), vec[C::X_AGG_W + k], s);
+        s = fmaxf(s, 0.f);
+#pragma unroll
+        for (int u = 0; u < V; ++u)
+          if (u == v) aw[u] = s;
+      }
+      float amax = aw[0];
+#pragma unroll
+      for (int v = 1; v < V; ++v) amax = fmaxf(amax, aw[v]);
+      float asum = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { aw[v] = expf(aw[v] - amax); asum += aw[v]; }
+      const float rsum = 1.f / asum;
+      // pass 2: softmax-weighted sum over views
+      float im[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) im[k] = 0.f;
+#pragma unroll 1
+      for (int v = 0; v < V; ++v) {
+        float gv[32];
+        tmem_ld32(tmem_row + v * 32, gv);
+        float a = aw[0];
+#pragma unroll
+        for (int u = 1; u < V; ++u)
+          if (u == v) a = aw[u];
+        a *= rsum;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) im[k] = fmaf(fmaxf(gv[k], 0.f), a, im[k]);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(im[ch * 8 + 0], im[ch * 8 + 1]), pack_h2(im[ch * 8 + 2], im[ch * 8 + 3]),
+                                                                          pack_h2(im[ch * 8 + 4], im[ch * 8 + 5]), pack_h2(im[ch * 8 + 6], im[ch * 8 + 7]));
+    }
+    // ================= GEMM 2: fc =================
+    tc_fence_before();
+    fence_async_smem();
+    group_sync(g);
+    if (row == 0) {
+      tc_fence_after();
+      mma_chunks(tmem_group, aS, 4, zero_chunk, w_base + C::W_FC, 16, 0);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, parity); parity ^= 1;
+    tc_fence_after();
+    {
+      float img[16];
+      tmem_ld16(tmem_row, img);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) img[k] = fmaxf(img[k] + vec[C::X_FC_B + k], 0.f);
+      // X[8] <- vox, S[0..1] <- img (their previous contents were consumed by GEMMs 1 and 2)
+      *reinterpret_cast<uint4*>(sX + 8 * 2048 + row * 16) = voxh;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(img[ch * 8 + 0], img[ch * 8 + 1]), pack_h2(img[ch * 8 + 2], img[ch * 8 + 3]),
+                                                                          pack_h2(img[ch * 8 + 4], img[ch * 8 + 5]), pack_h2(img[ch * 8 + 6], img[ch * 8 + 7]));
+    }
+    // ================= GEMM 3: lr0 on [vox | img | 1] =================
+    tc_fence_before();
+    fence_async_smem();
+    group_sync(g);
+    if (row == 0) {
+      tc_fence_after();
+      mma_step(tmem_group, aX + 8 * 2048, aS, w_base + C::W_LR0, 64, 0);
+      mma_step(tmem_group, aS + 2048, one_chunk, w_base + C::W_LR0 + 2 * 64 * 16, 64, 1);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, parity); parity ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float h[32];
+      tmem_ld32(tmem_row + half * 32, h);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(sX + (half * 4 + ch) * 2048 + row * 16) =
+            make_uint4(pack_h2(fmaxf(h[ch * 8 + 0], 0.f), fmaxf(h[ch * 8 + 1], 0.f)), pack_h2(fmaxf(h[ch * 8 + 2], 0.f), fmaxf(h[ch * 8 + 3], 0.f)),
+                       pack_h2(fmaxf(h[ch * 8 + 4], 0.f), fmaxf(h[ch * 8 + 5], 0.f)), pack_h2(fmaxf(h[ch * 8 + 6], 0.f), fmaxf(h[ch * 8 + 7], 0.f)));
+    }
+    // ================= GEMM 4: [sigma | feat_head] and weight.0, view by view through NB 64-column buffers =================
+    float sigma = 0.f, fh[8], wv[V];
+#pragma unroll
+    for (int r = 0; r < C::ROUNDS; ++r) {
+      const int v0 = C::round_start(r), nv = C::round_n(r);
+      tc_fence_before();
+      fence_async_smem();
+      group_sync(g);
+      if (row == 0) {
+        tc_fence_after();
+        if (r == 0) mma_chunks(tmem_group + (C::NB - 1) * 64, aX, 8, zero_chunk, w_base + C::W_SH, 16, 0);
+#pragma unroll 1
+        for (int i = 0; i < nv; ++i) {
+          const uint32_t d = tmem_group + i * 64;
+          mma_chunks(d, aX, 8, zero_chunk, w_base + C::W_0S, 64, 0);                                   // h
+          mma_step(d, aX + 8 * 2048, aS, w_base + C::W_0S + 8 * 64 * 16, 64, 1);                        // vox | img[0:8]
+          mma_step(d, aS + 2048, one_chunk, w_base + C::W_0S + 10 * 64 * 16, 64, 1);                    // img[8:16] | 1
+          mma_chunks(d, aFD + (v0 + i) * C::FDCH * 2048, C::FDCH, zero_chunk, w_base + C::W_0V, 64, 1); // featrgb_v | dir_v
+        }
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, parity); parity ^= 1;
+      tc_fence_after();
+      if (r == 0) {
+        float sh[16];
+        tmem_ld16(tmem_row + (C::NB - 1) * 64, sh);
+        float s = sh[0] + vec[C::X_SCAL + 1];
+        sigma = s > 20.f ? s : log1pf(expf(s));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fh[k] = fmaxf(sh[1 + k] + vec[C::X_FH_B + k], 0.f);
+      }
+#pragma unroll 1
+      for (int i = 0; i < nv; ++i) {
+        float s2 = vec[C::X_SCAL + 2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float hid[32];
+          tmem_ld32(tmem_row + i * 64 + half * 32, hid);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) s2 = fmaf(fmaxf(hid[k], 0.f), vec[C::X_W2_W + half * 32 + k], s2);
+        }
+        s2 = fmaxf(s2, 0.f);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (v == v0 + i) wv[v] = s2;
+      }
+    }
+    {
+      float wmax = -1e30f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) wmax = fmaxf(wmax, wv[v]);
+      float wsum = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { wv[v] = expf(wv[v] - wmax); wsum += wv[v]; }
+#pragma unroll
+      for (int v = 0; v < V; ++v) wv[v] /= wsum;
+    }
+    tc_fence_before();      // TMEM reads of this tile are ordered before the barrier that precedes the next tile's MMAs
+
+    // ======================= compositing weights (utils.py:19-43) =======================
+    float alpha = active ? 1.f - expf(-sigma) : 0.f;
+    float one_minus = 1.f - alpha;
+    float T = 1.f;
+    for (int k = 0; k + 1 < ns; ++k) {
+      float o = __shfl_sync(full, one_minus, min(seg_base + k, 31));
+      if (k < slot) T *= o;
+    }
+    float wgt = alpha * T;
+    float wtot = 0.f;
+    for (int k = 0; k < ns; ++k) {
+      float o = __shfl_sync(full, wgt, min(seg_base + k, 31));
+      if (k < n) wtot += o;
+    }
+    wgt = active ? wgt / fmaxf(wtot, 1e-6f) : 0.f;
+    if (p.tap_sigma && active) p.tap_sigma[srow] = sigma;
+    if (p.tap_w && active) p.tap_w[srow] = wgt;
+
+    auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+    const size_t ostr = p.out_cl ? 1 : (size_t)HW;
+    float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
+
+    // ---- blended features sum_v w_v featrgb_v (featrgb read back from the FD operand), geometry head, depth, opacity:
+    //      weighted by the compositing weight and transposed through shared memory (the warp's own rows of region X),
+    //      then summed over a bundle's samples in slot order with lane = (bundle, channel) and stored coalesced
+    {
+      float vals[C::NCP];
+#pragma unroll
+      for (int c = 0; c < C::NCP; ++c) vals[c] = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < C::FDCH; ++ch) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const uint4 q = *reinterpret_cast<const uint4*>(sFD + (v * C::FDCH + ch) * 2048 + row * 16);
+          const float2 f0 = h2_to_f2(q.x), f1 = h2_to_f2(q.y), f2 = h2_to_f2(q.z), f3 = h2_to_f2(q.w);
+          acc[0] = fmaf(f0.x, wv[v], acc[0]); acc[1] = fmaf(f0.y, wv[v], acc[1]);
+          acc[2] = fmaf(f1.x, wv[v], acc[2]); acc[3] = fmaf(f1.y, wv[v], acc[3]);
+          acc[4] = fmaf(f2.x, wv[v], acc[4]); acc[5] = fmaf(f2.y, wv[v], acc[5]);
+          acc[6] = fmaf(f3.x, wv[v], acc[6]); acc[7] = fmaf(f3.y, wv[v], acc[7]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (ch * 8 + e < F) vals[ch * 8 + e] = acc[e];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vals[F + k] = fh[k];
+      if (tf) {
+#pragma unroll
+        for (int c = 0; c < F + 8; ++c) tf[R + c] = vals[c];
+      }
+      vals[F + 8] = p.inv_depth ? fdiv(1.f, z) : z;
+      vals[F + 9] = 1.f;
+      __syncwarp();          // every lane has read its FD rows
+#pragma unroll
+      for (int q4 = 0; q4 < C::NCP / 4; ++q4)
+        *stash_f(lane * C::NCP + ((q4 ^ (lane & 7)) << 2)) =
+            make_float4(wgt * vals[q4 * 4 + 0], wgt * vals[q4 * 4 + 1], wgt * vals[q4 * 4 + 2], wgt * vals[q4 * 4 + 3]);
+      __syncwarp();
+#pragma unroll 1
+      for (int base = 0; base < G * C::NC; base += 32) {
+        const int item = base + lane;
+        const int bb = min(item / C::NC, G - 1), c = item - (item / C::NC) * C::NC;
+        const int nb = __shfl_sync(full, n, bb * ns);               // every lane of a bundle holds its count
+        const int pixb = pix_warp0 + bb;
+        if (item < G * C::NC && pixb < HW) {
+          float a = 0.f;
+          for (int k = 0; k < nb; ++k) {
+            const int rl = bb * ns + k;
+            const float o = *reinterpret_cast<const float*>(stash_f(rl * C::NCP + (((c >> 2) ^ (rl & 7)) << 2) + (c & 3)));
+            a = k == 0 ? o : a + o;
+          }
+          if (c < F + 8) {
+            float* odb = p.out_cl ? p.out_dec + (size_t)(b * HW + pixb) * (F + 8) + c : p.out_feat + ((size_t)b * CT + R + c) * HW + pixb;
+            *odb = a;
+          } else if (c == F + 8) {
+            p.out_depth[(size_t)b * HW + pixb] = p.inv_depth ? fdiv(1.f, a) : a;
+          } else {
+            p.out_opacity[(size_t)b * HW + pixb] = a;
+          }
+        }
+      }
+    }
+
+    // ============== P6: fine colours, lane = (row, ray) (bundle_sampler.py:327-337) ==============
+    // every lane of the warp is done with its FD rows (the stash aliases X + FD, rows of this warp only)
+    __syncwarp();
+    auto stash = [&](int t) { return reinterpret_cast<float4*>(gsm + (t >> 5) * 2048 + wq * 512 + (t & 31) * 16); };
+#pragma unroll 1
+    for (int it = 0; it < BB; ++it) {
+      const int item = it * 32 + lane;
+      const int r = item / BB, j = item - r * BB;
+      const float zr = __shfl_sync(full, z, r);
+      const float x0r = __shfl_sync(full, geo.x0, r), y0r = __shfl_sync(full, geo.y0, r);
+      const float wr = __shfl_sync(full, wgt, r);
+      const bool actr = __shfl_sync(full, active ? 1 : 0, r) != 0;
+      const int64_t srow_r = __shfl_sync(full, srow, r);
+      float wvr[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) wvr[v] = __shfl_sync(full, wv[v], r);
+      const float x = x0r + (float)(j % BS), y = y0r + (float)(j / BS);
+      const float* M = head + CAM_M;
+      const float dx = fmaf(x, M[0], fmaf(y, M[1], M[2]));
+      const float dy = fmaf(x, M[3], fmaf(y, M[4], M[5]));
+      const float dz = fmaf(x, M[6], fmaf(y, M[7], M[8]));
+      const float wx = fmaf(dx, zr, ox), wy = fmaf(dy, zr, oy), wz = fmaf(dz, zr, oz);
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float* cv = head + CAM_HEAD + CAM_VIEW * v;
+        float cx = fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
+        float cy = fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
+        float cz = fmaf(wx, cv[CV_E + 8], fmaf(wy, cv[CV_E + 9], fmaf(wz, cv[CV_E + 10], cv[CV_E + 11])));
+        float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
+        float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
+        float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+        const float rz = fdiv(1.f, iz);
+        float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (actr) {
+          Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
+          const float* ib = p.rgba + (size_t)(b * V + v) * p.H * p.W * 4;
+          c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o00 * 4), bl4.w00);
+          c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o10 * 4), bl4.w10);
+          c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o01 * 4), bl4.w01);
+          c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o11 * 4), bl4.w11);
+          if (p.tap_rfd) {
+            float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_r) * C::RFD;
+            tp[0 * BB + j] = c4.x; tp[1 * BB + j] = c4.y; tp[2 * BB + j] = c4.z;
+          }
+        }
+        cr = fmaf(c4.x, wvr[v], cr); cg = fmaf(c4.y, wvr[v], cg); cb = fmaf(c4.z, wvr[v], cb);
+      }
+      if (p.tap_feat && actr) {
+        float* tfr = p.tap_feat + srow_r * CT;
+        tfr[0 * BB + j] = cr; tfr[1 * BB + j] = cg; tfr[2 * BB + j] = cb;
+      }
+      *stash(r * BB + j) = make_float4(wr * cr, wr * cg, wr * cb, 0.f);
+    }
+    __syncwarp();
+    // sum over the samples of a bundle in slot order, thread = (bundle, ray)
+#pragma unroll 1
+    for (int base = 0; base < G * BB; base += 32) {
+      const int item = base + lane;
+      const int bb = min(item / BB, G - 1), j = item % BB;
+      const int nb = __shfl_sync(full, n, bb * ns);                 // every lane of a bundle holds its count
+      const int pixb = pix_warp0 + bb;
+      if (item < G * BB && pixb < HW) {
+        float4 a = *stash((bb * ns) * BB + j);
+        for (int k = 1; k < nb; ++k) {
+          const float4 o = *stash((bb * ns + k) * BB + j);
+          a.x += o.x; a.y += o.y; a.z += o.z;
+        }
+        float* ofb = p.out_cl ? p.out_feat + (size_t)(b * HW + pixb) * R : p.out_feat + (size_t)b * CT * HW + pixb;
+        ofb[(size_t)(0 * BB + j) * ostr] = a.x;
+        ofb[(size_t)(1 * BB + j) * ostr] = a.y;
+        ofb[(size_t)(2 * BB + j) * ostr] = a.z;
+      }
+    }
+    __syncwarp();           // stash reads complete before the next tile's gathers overwrite X / FD
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(C::TC * NG) : "memory");
+  }
+}
+
+template <int BS, int FEAT_DIM, int V, int NG>
+static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
+  using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
+  static_assert(C::SMEM <= 227 * 1024, "shared memory plan");
+  auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG>;
+  static bool ready = false;
+  if (!ready) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return fail((int)e, "gdb_render_fused_fwd(tc2): cudaFuncSetAttribute(%d B): %s", C::SMEM, cudaGetErrorString(e));
+    ready = true;
+  }
+  if ((long)p.Wb * C::QL >= (1 << 14))
+    return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): bundle map width %d too large for the packed tap stride", p.Wb);
+  const int G = 32 / p.max_samples;
+  const long NB = (long)p.B * p.Hb * p.Wb;
+  const long tiles = (NB + 4 * G - 1) / (4 * G);
+  long ctas = (tiles + NG - 1) / NG;
+  if (ctas > sm_count()) ctas = sm_count();
+  kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(p);
+  return cuda_check("gdb_render_fused_fwd(tc2)");
+}
+
+int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
+  if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4>(p, st);
+  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4>(p, st);
+  if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2>(p, st);
+  if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2>(p, st);
+  if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2>(p, st);
+  if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1>(p, st);
+  return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): (bundle_size=%d, feat_dim=%d, V=%d) not instantiated", bundle_size, feat_dim, V);
+}
+
+}  // namespace gdb

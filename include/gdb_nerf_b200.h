@@ -160,7 +160,8 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int max_samples,
                          int max_mip_level, int inv_depth, int adaptive,
                          int precision /* 0 = fp32 SIMT MLP (1e-4 class); 1 = fp16-operand tcgen05 MLP, fp32 accumulate (2e-3 class);
-                                          2 = split-fp16 (hi+lo) tcgen05 MLP, three MMAs per K step, fp32 accumulate (1e-4 class) */,
+                                          2 = split-fp16 (hi+lo) tcgen05 MLP, three MMAs per K step, fp32 accumulate (1e-4 class);
+                                          3 = the first-generation kernel of class 1 (kept for A/B measurements) */,
                          int out_channels_last, float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
                          const gdb_render_taps* taps, void* stream);
 

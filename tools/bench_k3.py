@@ -39,7 +39,7 @@ cam = ops.camera_block(rig["tar_exts"].to(dev), rig["tar_ints"].to(dev), rig["sr
 src = ops.prepare_sources(feat, rgb, b, cfg.nerf.max_mipmap_level)
 vol_cl = ops.to_channels_last(vol, 8)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for prec in ([0, 1, 2] if args.precision < 0 else [args.precision]):
+for prec in ([0, 1, 2, 3] if args.precision < 0 else [args.precision]):
     ts = []
     for i in range(args.iters + 2):
         flush.zero_()
