@@ -91,7 +91,8 @@ struct Tc2Cfg {
   static constexpr int NCP = NC <= 32 ? 32 : 64;       // padded row of the transposition stash (swizzled by float4)
   static_assert(32 * NCP * 4 <= 512 * (CH_X + CH_FD), "compositing stash must fit in the warp's rows of X + FD");
   // TMEM columns per group
-  static constexpr int TC = cmin(512 / NG, 256);
+  static constexpr int TC = cmin((512 / NG) & ~31, 256);
+  static constexpr int TALLOC = NG * TC <= 256 ? 256 : 512;      // tcgen05.alloc takes a power of two
   static constexpr int NB = TC / 64;                   // 64-column buffers for weight.0
   static_assert(V * 32 <= TC && NB >= 2, "TMEM column plan");
   static constexpr int ROUNDS = 1 + (cmax(V - (NB - 1), 0) + NB - 1) / NB;
@@ -133,7 +134,8 @@ __device__ __forceinline__ void unit3_fast(float& x, float& y, float& z) {
 }
 __device__ __forceinline__ float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 
-template <int BS, int FEAT_DIM, int V, int NG>
+// TAPS: the per-sample parity outputs (tests); the production instantiation carries none of that code or state
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   using ML = typename C::ML;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     if (row == 0) mbar_init(mbar, 1);
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                   "r"(C::TC * NG)
+                   "r"(C::TALLOC)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -226,14 +228,6 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   const int gr = lane / QL, gq = lane - gr * QL;
   const bool glane = lane < IPW * QL;
   const bool last_quad = gq == QL - 1;
-  float vw[4][4], vb[4];                                   // view_fc weights of my quad's four channels
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int c = (glane ? gq : 0) * 4 + e;
-    vb[e] = vec[C::X_VIEW_B + c];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) vw[j][e] = vec[C::X_VIEW_W + j * FP + c];
-  }
   const float4* tex4 = reinterpret_cast<const float4*>(p.tex);
   const float inv_Wb = 1.f / (float)p.Wb, inv_Hb = 1.f / (float)p.Hb, two_W = 2.f / (float)p.W, two_H = 2.f / (float)p.H;
 
@@ -264,7 +258,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     BundleGeom<BS> geo;
     geo.init(head, yb, xb, p.H, p.W);
     const float ox = head[CAM_O + 0], oy = head[CAM_O + 1], oz = head[CAM_O + 2];
-    const int64_t srow = (p.offsets && active) ? (int64_t)p.offsets[bidx] + slot : -1;
+    const int64_t srow = (TAPS && p.offsets && active) ? (int64_t)p.offsets[bidx] + slot : -1;
 
     float cwx = 0.f, cwy = 0.f, cwz = 0.f;
 #pragma unroll
@@ -301,7 +295,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         hi = f4_scale_add(hi, ldg4(tp + 4), w);
       }
       voxh = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
-      if (p.tap_vox) {
+      if (TAPS && p.tap_vox) {
         reinterpret_cast<float4*>(p.tap_vox + srow * 8)[0] = lo;
         reinterpret_cast<float4*>(p.tap_vox + srow * 8)[1] = hi;
       }
@@ -356,7 +350,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float ddx = tdx - sx, ddy = tdy - sy, ddz = tdz - sz;
         unit3_fast(ddx, ddy, ddz);
         d_dir[v][0] = ddx; d_dir[v][1] = ddy; d_dir[v][2] = ddz; d_dir[v][3] = tdx * sx + tdy * sy + tdz * sz;
-        if (p.tap_rfd) {
+        if (TAPS && p.tap_rfd) {
           float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow) * C::RFD + R + F;
           tp[0] = ddx; tp[1] = ddy; tp[2] = ddz; tp[3] = d_dir[v][3];
         }
@@ -371,8 +365,20 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       const bool ok = glane && src_raw < 32;
       const int src = min(src_raw, 31);
       const int orow16 = (wq * 32 + src) * 16;
-      const int64_t srow_g = __shfl_sync(full, srow, src);
+      const int64_t srow_g = TAPS ? __shfl_sync(full, srow, src) : 0;
       float xq[V][4];
+      // view_fc weights of my quad's four channels (re-read per iteration: keeping them live across the tile costs spills)
+      float4 vw0, vw1, vw2, vw3, vbq;
+      {
+        const float* vq = vec + (glane ? gq : 0) * 4;
+        vw0 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 0 * FP);
+        vw1 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 1 * FP);
+        vw2 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 2 * FP);
+        vw3 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 3 * FP);
+        vbq = *reinterpret_cast<const float4*>(vq + C::X_VIEW_B);
+      }
+      const float vw[4][4] = {{vw0.x, vw0.y, vw0.z, vw0.w}, {vw1.x, vw1.y, vw1.z, vw1.w}, {vw2.x, vw2.y, vw2.z, vw2.w}, {vw3.x, vw3.y, vw3.z, vw3.w}};
+      const float vb[4] = {vbq.x, vbq.y, vbq.z, vbq.w};
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int a0 = __shfl_sync(full, d_a0[v], src), a1 = __shfl_sync(full, d_a1[v], src);
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             float4 bq = bilerp4(__ldg(tex4 + i1), __ldg(tex4 + (i1 + dx1)), __ldg(tex4 + (i1 + dy1)), __ldg(tex4 + (i1 + dy1 + dx1)), fu1, fv1);
             f.x = lerpf(f.x, bq.x, frac); f.y = lerpf(f.y, bq.y, frac); f.z = lerpf(f.z, bq.z, frac); f.w = lerpf(f.w, bq.w, frac);
           }
-          if (p.tap_rfd) {
+          if (TAPS && p.tap_rfd) {
             float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
             tp[0] = f.x; tp[1] = f.y; tp[2] = f.z;
             if (!last_quad) tp[3] = f.w;
@@ -623,12 +629,12 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       if (k < n) wtot += o;
     }
     wgt = active ? wgt / fmaxf(wtot, 1e-6f) : 0.f;
-    if (p.tap_sigma && active) p.tap_sigma[srow] = sigma;
-    if (p.tap_w && active) p.tap_w[srow] = wgt;
+    if (TAPS && p.tap_sigma && active) p.tap_sigma[srow] = sigma;
+    if (TAPS && p.tap_w && active) p.tap_w[srow] = wgt;
 
     auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
     const size_t ostr = p.out_cl ? 1 : (size_t)HW;
-    float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
+    float* tf = (TAPS && p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     // ---- blended features sum_v w_v featrgb_v (featrgb read back from the FD operand), geometry head, depth, opacity:
     //      weighted by the compositing weight and transposed through shared memory (the warp's own rows of region X),
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       const float x0r = __shfl_sync(full, geo.x0, r), y0r = __shfl_sync(full, geo.y0, r);
       const float wr = __shfl_sync(full, wgt, r);
       const bool actr = __shfl_sync(full, active ? 1 : 0, r) != 0;
-      const int64_t srow_r = __shfl_sync(full, srow, r);
+      const int64_t srow_r = TAPS ? __shfl_sync(full, srow, r) : 0;
       float wvr[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) wvr[v] = __shfl_sync(full, wv[v], r);
@@ -736,14 +742,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o10 * 4), bl4.w10);
           c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o01 * 4), bl4.w01);
           c4 = f4_scale_add(c4, ldg4(ib + (size_t)bl4.o11 * 4), bl4.w11);
-          if (p.tap_rfd) {
+          if (TAPS && p.tap_rfd) {
             float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_r) * C::RFD;
             tp[0 * BB + j] = c4.x; tp[1 * BB + j] = c4.y; tp[2 * BB + j] = c4.z;
           }
         }
         cr = fmaf(c4.x, wvr[v], cr); cg = fmaf(c4.y, wvr[v], cg); cb = fmaf(c4.z, wvr[v], cb);
       }
-      if (p.tap_feat && actr) {
+      if (TAPS && p.tap_feat && actr) {
         float* tfr = p.tap_feat + srow_r * CT;
         tfr[0 * BB + j] = cr; tfr[1 * BB + j] = cg; tfr[2 * BB + j] = cb;
       }
@@ -777,15 +783,15 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(C::TC * NG) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(C::TALLOC) : "memory");
   }
 }
 
-template <int BS, int FEAT_DIM, int V, int NG>
-static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS>
+static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   static_assert(C::SMEM <= 227 * 1024, "shared memory plan");
-  auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG>;
+  auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG, TAPS>;
   static bool ready = false;
   if (!ready) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -802,10 +808,18 @@ static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
   kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(p);
   return cuda_check("gdb_render_fused_fwd(tc2)");
 }
+template <int BS, int FEAT_DIM, int V, int NG>
+static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
+  const bool taps = p.tap_rfd || p.tap_vox || p.tap_sigma || p.tap_feat || p.tap_w;
+  return taps ? launch_render_tc2_t<BS, FEAT_DIM, V, NG, true>(p, st) : launch_render_tc2_t<BS, FEAT_DIM, V, NG, false>(p, st);
+}
 
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
   if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4>(p, st);
-  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4>(p, st);
+#ifndef GDB_TC2_NG
+#define GDB_TC2_NG 4
+#endif
+  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, GDB_TC2_NG>(p, st);
   if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2>(p, st);
   if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2>(p, st);
   if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2>(p, st);

@@ -15,8 +15,12 @@ ap.add_argument("--precision", type=int, default=-1)
 ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--workload", default="dtu")
+ap.add_argument("--lib", default="", help="alternative build of the library (A/B measurements)")
 ap.add_argument("--narrow", action="store_true", help="narrow depth ranges (adaptive counts 1..max) instead of saturated")
 args = ap.parse_args()
+if args.lib:
+    from gdb_nerf_b200 import _lib as _L
+    _L.LIB_PATH = os.path.abspath(args.lib)
 w = WORKLOADS[args.workload]; cfg = make_cfg(w["recipe"]); b = cfg.nerf.bundle_size
 H, W, V, B = w["H"], w["W"], 3, args.B
 Hb, Wb = H // b, W // b
