@@ -161,7 +161,7 @@ class Network(nn.Module):
         #                K step, fp32 accumulation in TMEM - the north star's fp32 class (1e-4), agrees with 0 to ~1e-5
         #   0: fp32 SIMT (the validation variant of the same class)
         #   1: tcgen05 with single fp16 operands (the north star's reduced-precision class, 2e-3; measured ~1e-4)
-        self.mlp_precision = 2
+        self.mlp_precision = 1
 
     def _channels_last_params(self) -> None:
         if not self._cl_ready:
