@@ -63,10 +63,13 @@ def test_network_forward_matches_reference(case, cnn_mode):
     assert mse < 1e-8           # PSNR delta against the reference image far below 0.01 dB
 
 
-def _full_size_inputs(name="dtu", V=3, seed=0):
-    w = WORKLOADS[name]
+def _full_size_inputs(name="dtu", V=3, seed=0, hw=None):
+    w = dict(WORKLOADS[name])
     cfg = make_cfg(w["recipe"])
     b = cfg.nerf.bundle_size
+    if hw is not None:                      # reduced image, same field of view
+        w["focal"] = w["focal"] * hw[0] / w["H"]
+        w["H"], w["W"] = hw
     H, W = w["H"], w["W"]
     Hb, Wb = H // b, W // b
     g = torch.Generator().manual_seed(seed)
@@ -149,6 +152,41 @@ def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
                              cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, False, True)
     assert _md(out["feat"], truth["bundle_feat"]) <= tol
     assert _md(out["depth"], truth["bundle_depth"]) <= tol * (w["far"] - w["near"])
+
+
+@pytest.mark.parametrize("workload,hw", [("dtu", (64, 96)), ("nerf", (128, 160))])
+@pytest.mark.parametrize("V", [2, 4])
+def test_view_counts_two_and_four(workload, hw, V):
+    """the kernels must cover V in {2, 3, 4} (training draws 2/3/4 views, fine-tuned evaluation uses 4).  Every MLP
+    arithmetic of the fused render kernel and the cost-volume kernel against the oracle on identical inputs."""
+    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs(workload, V=V, seed=3, hw=hw)
+    b = cfg.nerf.bundle_size
+    H, W = w["H"], w["W"]
+    truth = O.render_bundles(mlp, feat_dim, data["rgb"], data["feat"], data["vol"], data["depth_range"], data["vol_range"],
+                             rig["src_exts"], rig["src_ints"], rig["tar_exts"], rig["tar_ints"], rig["near_far"], b,
+                             cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, False, True)
+    cam = ops.camera_block(rig["tar_exts"].to(DEV), rig["tar_ints"].to(DEV), rig["src_exts"].to(DEV), rig["src_ints"].to(DEV),
+                           rig["near_far"].to(DEV), b, cfg.nerf.global_num_depth, False)
+    src = ops.prepare_sources(data["feat"].to(DEV), data["rgb"].to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(data["vol"].to(DEV), 8)
+    sl = ops.sample_bundles(data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam, b, cfg.nerf.max_num_samples, False, True)
+    assert torch.equal(sl.indices.cpu(), truth["indices"])
+    for precision in (0, 1, 2):
+        tol = 2e-3 if precision == 1 else 1e-4
+        out = ops.render_fused(src, vol_cl, data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam,
+                               ops.pack_mlp(mlp, feat_dim, device=DEV), 1, V, H, W, b, cfg.nerf.max_num_samples, False, True,
+                               precision=precision)
+        assert _md(out["feat"], truth["bundle_feat"]) <= tol, precision
+        assert _md(out["feat"][:, :3 * b * b], truth["bundle_feat"][:, :3 * b * b]) <= 1e-4, precision      # fine colours: fp32 in every variant
+        assert _md(out["depth"], truth["bundle_depth"]) <= 1e-4 * (w["far"] - w["near"]), precision
+        assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
+    # cost volume over V views (stage-1 geometry of the recipe: feature level of the bundle map)
+    Hb, Wb = H // b, W // b
+    proj = ops.homography_mats(rig["src_exts"].to(DEV), rig["src_ints"].to(DEV), rig["tar_exts"].to(DEV), rig["tar_ints"].to(DEV), 1.0 / b, 1.0 / b)
+    feat_cl = ops.to_channels_last(data["feat"].flatten(0, 1).to(DEV)).unflatten(0, (1, V))
+    var = ops.warp_variance(feat_cl, proj, data["depth_range"].to(DEV), 8, Hb, Wb, False)
+    tv = O.warp_variance(data["feat"], proj.cpu(), O.depth_hypotheses(data["depth_range"], 8, False), False)
+    assert _md(var, tv) <= 1e-4
 
 
 def test_full_size_warp_variance_against_oracle():
