@@ -214,3 +214,27 @@ def test_full_size_warp_variance_against_oracle():
         dv = O.depth_hypotheses(rng, D, cfg.mvs.inv_depth[s]).expand(1, D, Ht, Wt)
         truth = O.warp_variance(feat, proj.cpu(), dv, cfg.mvs.inv_depth[s])
         assert _md(var, truth) <= 1e-4 * max(1.0, float(truth.abs().max()))
+
+
+@pytest.mark.parametrize("workload", ["dtu", "nerf"])
+def test_default_mlp_arithmetic_meets_fp32_class_end_to_end(workload):
+    """The default MLP arithmetic (tcgen05, fp16 operands, fp32 accumulation) against the fp32 SIMT arithmetic through the
+    whole Network.forward at BASELINE.json sizes: the north star's fp32-class tolerance (1e-4 absolute on rgb and depth)
+    holds on the outputs, PSNR delta far below 0.01 dB."""
+    from gdb_nerf_b200.synthetic import workload_batch
+    w = WORKLOADS[workload]
+    cfg = make_cfg(w["recipe"])
+    torch.manual_seed(0)
+    net = Network(cfg).to(DEV).eval()
+    assert net.mlp_precision == 1
+    batch = batch_to(workload_batch(workload, B=1), DEV)
+    outs = {}
+    with torch.no_grad():
+        for prec in (0, 1):
+            net.mlp_precision = prec
+            outs[prec] = net(batch)[0]
+    assert _md(outs[1]["rgb"], outs[0]["rgb"]) <= 1e-4
+    assert _md(outs[1]["nerf_depth"], outs[0]["nerf_depth"]) <= 1e-4 * (w["far"] - w["near"])
+    assert _md(outs[1]["mvs_depth"], outs[0]["mvs_depth"]) <= 1e-5 * (w["far"] - w["near"])     # same CNNs; cuDNN run-to-run noise only
+    mse = float(((outs[1]["rgb"].double() - outs[0]["rgb"].double()) ** 2).mean())
+    assert mse < 1e-9
