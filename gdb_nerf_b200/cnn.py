@@ -196,6 +196,103 @@ def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True) -
     return cl[..., :cout], cl[..., cout]
 
 
+# ---------------------------------------------------------------------------
+# Depth-folded execution of the 3-D U-Net (eval mode): with D <= 8 hypotheses the depth axis is folded into the
+# channels (channel = d*C + c) and every 3x3x3 convolution becomes a 3x3 2-D convolution whose weight is the
+# block-Toeplitz expansion of the 3-D kernel along depth (zero blocks where |d_in - s*d_out| > 1, which is also the
+# zero padding).  Same products, same BN folding; the 64-128 channel 2-D shapes are the ones cuDNN runs efficiently,
+# the 8/16-channel 3-D shapes are not (stage-1 conv0: 0.95 ms as Conv3d 16->8, 0.16 ms as Conv2d 128->64).
+# ---------------------------------------------------------------------------
+def fold_depth_weight(w3: torch.Tensor, d_in: int, stride: int, transposed: bool) -> Tuple[torch.Tensor, int]:
+    """(Co,Ci,3,3,3) Conv3d weight (padding 1, isotropic ``stride``) -> (d_out*Co, d_in*Ci, 3, 3) Conv2d weight, or
+    (Ci,Co,3,3,3) ConvTranspose3d weight (stride 2, padding 1, output_padding 1) -> (d_in*Ci, d_out*Co, 3, 3)
+    ConvTranspose2d weight.  Returns (weight, d_out)."""
+    if transposed:
+        ci, co = w3.shape[:2]
+        d_out = 2 * d_in
+        w2 = w3.new_zeros((d_in, ci, d_out, co, 3, 3))
+        for di in range(d_in):
+            for kd in range(3):
+                do = 2 * di - 1 + kd
+                if 0 <= do < d_out:
+                    w2[di, :, do, :] = w3[:, :, kd]
+        return w2.reshape(d_in * ci, d_out * co, 3, 3), d_out
+    co, ci = w3.shape[:2]
+    d_out = (d_in + 2 - 3) // stride + 1
+    w2 = w3.new_zeros((d_out, co, d_in, ci, 3, 3))
+    for do in range(d_out):
+        for kd in range(3):
+            di = do * stride + kd - 1
+            if 0 <= di < d_in:
+                w2[do, :, di, :] = w3[:, :, kd]
+    return w2.reshape(d_out * co, d_in * ci, 3, 3), d_out
+
+
+def _folded2d(block: nn.Sequential, d_in: int):
+    conv = block[0]
+    w3, shift = _folded(block)
+    transposed = isinstance(conv, nn.ConvTranspose3d)
+
+    def make():
+        w2, d_out = fold_depth_weight(w3, d_in, conv.stride[0], transposed)
+        return w2.contiguous(memory_format=torch.channels_last), shift.repeat(d_out).contiguous(), d_out
+
+    return _cached(block, f"_gdb_dfold{d_in}", (w3, shift), make)
+
+
+def cost_reg_folded(net: "_CostReg", x: torch.Tensor, D: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """CostRegNet(Small).forward on a depth-folded volume: x is (B, D*C, H, W)-shaped over (B,H,W,D,C) memory.
+    Returns (volume, logits) as (B,D,H,W,8) / (B,D,H,W) VIEWS of the joint head output, whose memory is (B,H,W,D,12)."""
+    from . import ops
+
+    def r(block, t, d):
+        w, b, d_out = _folded2d(block, d)
+        s = block[0].stride[0]
+        return torch.cudnn_convolution_relu(t, w, b, (s, s), (1, 1), (1, 1), 1), d_out
+
+    def up(block, t, skip, d):
+        w, b, d_out = _folded2d(block, d)
+        y = F.conv_transpose2d(t, w, None, 2, 1, 1)
+        return ops.bias_act_add(y, b, skip, relu=True), d_out
+
+    s0, d0 = r(net.conv0, x, D)
+    t, d1 = r(net.conv1, s0, d0)
+    s1, d1 = r(net.conv2, t, d1)
+    if isinstance(net, CostRegNetSmall):
+        t, d2 = r(net.conv3, s1, d1)
+        y, d2 = r(net.conv4, t, d2)
+        y, d = up(net.conv5, y, s1, d2)
+        y, d = up(net.conv6, y, s0, d)
+    else:
+        t, d2 = r(net.conv3, s1, d1)
+        s2, d2 = r(net.conv4, t, d2)
+        t, d3 = r(net.conv5, s2, d2)
+        y, d3 = r(net.conv6, t, d3)
+        y, d = up(net.conv7, y, s2, d3)
+        y, d = up(net.conv8, y, s1, d)
+        y, d = up(net.conv9, y, s0, d)
+    if d != D:
+        raise ValueError(f"depth-folded cost regularisation needs D divisible by the U-Net's total stride (D = {D})")
+    fw, pw = net.feat_head.weight, net.prob_head.weight
+    cout = fw.shape[0]
+    cpad = (cout + 1 + 3) & ~3
+
+    def make():
+        w = torch.zeros((cpad, *fw.shape[1:]), device=fw.device, dtype=fw.dtype)
+        w[:cout] = fw
+        w[cout] = pw[0]
+        return fold_depth_weight(w, D, 1, False)[0].contiguous(memory_format=torch.channels_last)
+
+    w = _cached(net, f"_gdb_heads2d{D}", (fw, pw), make)
+    out = F.conv2d(y, w, None, 1, 1)                              # (B, D*cpad, H, W) over (B,H,W,D,cpad) memory
+    B, _, H, W = out.shape
+    cl = out.permute(0, 2, 3, 1)
+    if not cl.is_contiguous():
+        cl = cl.contiguous()
+    cl = cl.view(B, H, W, D, cpad)
+    return cl[..., :cout].permute(0, 3, 1, 2, 4), cl[..., cout].permute(0, 3, 1, 2)
+
+
 class _CostReg(nn.Module):
     def _heads(self, c: int, cout: int) -> None:
         self.feat_head = nn.Conv3d(c, cout, 3, padding=1, bias=False)

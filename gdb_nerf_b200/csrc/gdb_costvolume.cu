@@ -136,7 +136,7 @@ __device__ __forceinline__ WarpTap warp_tap(const float* __restrict__ P, float r
   return t;
 }
 
-template <int C, int V, bool OUT_CL>
+template <int C, int V, int OUT_CL>      // 0: (B,C,D,Ht,Wt) planar; 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
 __global__ void __launch_bounds__(256)
 warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
                      int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
@@ -231,7 +231,8 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
     }
     var.x *= invV; var.y *= invV; var.z *= invV; var.w *= invV;
     if (OUT_CL) {
-      if (live) __stcs(reinterpret_cast<float4*>(out + (((size_t)b * D + d) * HW + pix) * C + q * 4), var);
+      if (live)
+        __stcs(reinterpret_cast<float4*>(out + (OUT_CL == 2 ? (((size_t)b * HW + pix) * D + d) : (((size_t)b * D + d) * HW + pix)) * C + q * 4), var);
     } else {
       float* t = tile[buf];
       t[(q * 4 + 0) * ROW + pl] = var.x;
@@ -261,10 +262,12 @@ static int launch_warp_variance(const float* feat, const float* proj, const floa
   int DCH = D;
   while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
   dim3 grid(tiles, (D + DCH - 1) / DCH, B);
-  if (out_cl)
-    warp_variance_kernel<C, V, true><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+  if (out_cl == 2)
+    warp_variance_kernel<C, V, 2><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+  else if (out_cl)
+    warp_variance_kernel<C, V, 1><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
   else
-    warp_variance_kernel<C, V, false><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+    warp_variance_kernel<C, V, 0><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
   return cuda_check("gdb_warp_variance_fwd");
 }
 

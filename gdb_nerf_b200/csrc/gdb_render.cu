@@ -107,13 +107,13 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
       float tx = ix - x0f, ty = iy - y0f, tz = iz - z0f;
       int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
       int x1 = min(x0 + 1, p.Wb - 1), y1 = min(y0 + 1, p.Hb - 1), z1 = min(z0 + 1, p.D - 1);
-      const float* vb = p.vol + (size_t)b * p.D * HW * p.vol_stride;
+      const float* vb = p.vol + (size_t)b * p.vol_sb;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
         float w = ((k & 1) ? tx : 1.f - tx) * ((k & 2) ? ty : 1.f - ty) * ((k & 4) ? tz : 1.f - tz);
-        const float* tp = vb + ((size_t)(zz * p.Hb + yy) * p.Wb + xx) * p.vol_stride;
+        const float* tp = vb + zz * p.vol_sz + yy * p.vol_sy + xx * p.vol_sx;
         lo = f4_scale_add(lo, ldg4(tp), w);
         hi = f4_scale_add(hi, ldg4(tp + 4), w);
       }
@@ -476,7 +476,7 @@ extern "C" int gdb_mlp_param_floats(int feat_dim) {
 
 extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
                                     const float* vol_range, const float* cam, int cam_stride, const float* mlp, int B,
-                                    int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int max_samples,
+                                    int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int vol_layout, int max_samples,
                                     int max_mip_level, int inv_depth, int adaptive, int precision, int out_channels_last,
                                     float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
                                     const gdb_render_taps* taps, void* stream) {
@@ -507,8 +507,14 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   GDB_REQUIRE(vol_stride >= 8 && vol_stride % 4 == 0, GDB_E_BADARG, "gdb_render_fused_fwd: vol_stride %d must be >= 8 and a multiple of 4", vol_stride);
   p.cam_stride = cam_stride;
   p.vol_stride = vol_stride;
+  GDB_REQUIRE(vol_layout == 0 || vol_layout == 1, GDB_E_BADARG, "gdb_render_fused_fwd: vol_layout must be 0 (B,D,Hb,Wb,.) or 1 (B,Hb,Wb,D,.)");
   p.B = B; p.H = H; p.W = W; p.Hb = H / bundle_size; p.Wb = W / bundle_size; p.D = D; p.max_samples = max_samples;
   p.L = max_mip_level; p.inv_depth = inv_depth; p.adaptive = adaptive;
+  if (vol_layout == 0) {
+    p.vol_sx = vol_stride; p.vol_sy = (int64_t)vol_stride * p.Wb; p.vol_sz = p.vol_sy * p.Hb; p.vol_sb = p.vol_sz * D;
+  } else {
+    p.vol_sz = vol_stride; p.vol_sx = (int64_t)vol_stride * D; p.vol_sy = p.vol_sx * p.Wb; p.vol_sb = p.vol_sy * p.Hb;
+  }
   const int m = 1 << max_mip_level;
   GDB_REQUIRE(p.Hb % m == 0 && p.Wb % m == 0, GDB_E_BADARG, "gdb_render_fused_fwd: bundle map %dx%d not divisible by %d", p.Hb, p.Wb, m);
   const int FPad = (feat_dim + 3 + 3) & ~3;

@@ -284,13 +284,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       float tx = ix - x0f, ty = iy - y0f, tz = iz - z0f;
       int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
       int x1 = min(x0 + 1, p.Wb - 1), y1 = min(y0 + 1, p.Hb - 1), z1 = min(z0 + 1, p.D - 1);
-      const float* vb_ = p.vol + (size_t)b * p.D * HW * p.vol_stride;
+      const float* vb_ = p.vol + (size_t)b * p.vol_sb;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
         float w = ((k & 1) ? tx : 1.f - tx) * ((k & 2) ? ty : 1.f - ty) * ((k & 4) ? tz : 1.f - tz);
-        const float* tp = vb_ + ((size_t)(zz * p.Hb + yy) * p.Wb + xx) * p.vol_stride;
+        const float* tp = vb_ + zz * p.vol_sz + yy * p.vol_sy + xx * p.vol_sx;
         lo = f4_scale_add(lo, ldg4(tp), w);
         hi = f4_scale_add(hi, ldg4(tp + 4), w);
       }

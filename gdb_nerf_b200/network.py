@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import autograd as AG
 from . import ops
-from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_fused, decoder_fused, feature_net_fused
+from .cnn import CostRegNet, CostRegNetSmall, Decoder, FeatureNet, cost_reg_folded, cost_reg_fused, decoder_fused, feature_net_fused
 from .nerf import CoarseNeRF, NeRF
 from .sampler import BundleSampler
 
@@ -56,6 +56,7 @@ class DepthNet(nn.Module):
             self.cost_regs.append(CostRegNet(self.feat_dims[self.vol_levels[i]], voxel_dim, base))
         # coarse NeRFs exist in every reference checkpoint (module is in training mode at construction, :40-47)
         self.num_samples = list(config.mvs.num_samples)
+        self.fold_depth = True          # eval: stages with <= 8 hypotheses run their U-Net depth-folded on 2-D kernels (cnn.py)
         self.nerfs = nn.ModuleList([
             CoarseNeRF(config.nerf.nerf_hidden_dims, voxel_dim, self.feat_dims[i], config.nerf.viewdir_agg)
             for i in range(self.num_stages - 1)])
@@ -103,9 +104,14 @@ class DepthNet(nn.Module):
             Hi, Wi = int(H * self.vol_scales[s]), int(W * self.vol_scales[s])
             proj = ops.homography_mats(src_exts, src_ints, tar_exts, tar_ints, self.feat_scales[s], self.vol_scales[s])
             feat_cl = ops.to_channels_last(feats.flatten(0, 1)).unflatten(0, (B, V))
+            # few hypotheses (the refinement stages): depth folded into the channels, the U-Net runs on 2-D convolutions
+            folded = fused_cnn and self.fold_depth and self.num_depth[s] <= 8 and self.num_depth[s] % 8 == 0
             variance = ops.warp_variance(feat_cl, proj, depth_range, self.num_depth[s], Hi, Wi, self.inv_depth[s],
-                                         out_channels_last=fused_cnn)
-            if fused_cnn:
+                                         out_channels_last=fused_cnn, depth_folded=folded)
+            if folded:
+                volume, logits = cost_reg_folded(self.cost_regs[s], variance, self.num_depth[s])
+                depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])
+            elif fused_cnn:
                 # the feature head of every stage but the last only feeds the training-time coarse render
                 volume, logits = cost_reg_fused(self.cost_regs[s], variance, want_volume=(s == self.num_stages - 1))
                 depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])

@@ -90,21 +90,27 @@ def depth_values(depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_dept
 
 
 def warp_variance(feat_cl: Tensor, proj: Tensor, depth_range: Tensor, num_depth: int, Ht: int, Wt: int, inv_depth: bool,
-                  out_channels_last: bool = False) -> Tensor:
+                  out_channels_last: bool = False, depth_folded: bool = False) -> Tensor:
     """feat_cl (B,V,Hs,Ws,C) channels-last -> variance volume of SHAPE (B,C,D,Ht,Wt); with ``out_channels_last``
-    the memory behind it is (B,D,Ht,Wt,C), i.e. torch.channels_last_3d strides."""
+    the memory behind it is (B,D,Ht,Wt,C), i.e. torch.channels_last_3d strides; with ``depth_folded`` the result is
+    the (B,D*C,Ht,Wt)-shaped channels-last 2-D map over (B,Ht,Wt,D,C) memory (channel = d*C + c)."""
     _dev(feat_cl, proj, depth_range)
     feat_cl, proj, depth_range = _f32(feat_cl), _f32(proj), _f32(depth_range)
     B, V, Hs, Ws, Cc = feat_cl.shape
     _, _, rh, rw = depth_range.shape
-    if out_channels_last:
+    if depth_folded:
+        out = torch.empty((B, Ht, Wt, num_depth * Cc), device=feat_cl.device, dtype=torch.float32)
+    elif out_channels_last:
         out = torch.empty((B, num_depth, Ht, Wt, Cc), device=feat_cl.device, dtype=torch.float32)
     else:
         out = torch.empty((B, Cc, num_depth, Ht, Wt), device=feat_cl.device, dtype=torch.float32)
     lib = _lib.load()
+    layout = 2 if depth_folded else int(out_channels_last)
     _lib.check(lib.gdb_warp_variance_fwd(feat_cl.data_ptr(), proj.data_ptr(), depth_range.data_ptr(), rh, rw, B, V, Cc, Hs, Ws,
-                                         num_depth, Ht, Wt, int(inv_depth), int(out_channels_last), out.data_ptr(), _stream()),
+                                         num_depth, Ht, Wt, int(inv_depth), layout, out.data_ptr(), _stream()),
                "gdb_warp_variance_fwd")
+    if depth_folded:
+        return out.permute(0, 3, 1, 2)
     return out.permute(0, 4, 1, 2, 3) if out_channels_last else out
 
 
@@ -304,12 +310,17 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     depth_range, vol_range = _f32(depth_range), _f32(vol_range)
     Hb, Wb = H // bundle_size, W // bundle_size
     D = vol_cl.shape[1]
-    # (B,D,Hb,Wb,8) view whose voxels are vol_stride floats apart (the leading channels of a wider channels-last
-    # convolution output) is consumed in place
+    # a (B,D,Hb,Wb,8) view whose voxels are vol_stride floats apart (the leading channels of a wider channels-last
+    # convolution output) is consumed in place, in either memory order: (B,D,Hb,Wb,.) or depth-folded (B,Hb,Wb,D,.)
+    vol_layout = 0
+    ok = vol_cl.dtype == torch.float32 and vol_cl.shape[-1] == 8 and vol_cl.stride(4) == 1 and vol_cl.data_ptr() % 16 == 0
     vs = vol_cl.stride(3)
-    if not (vol_cl.dtype == torch.float32 and vol_cl.shape[-1] == 8 and vol_cl.stride(4) == 1 and vs >= 8 and vs % 4 == 0
-            and vol_cl.stride(2) == vs * Wb and vol_cl.stride(1) == vs * Wb * Hb and vol_cl.stride(0) == vs * Wb * Hb * D
-            and vol_cl.data_ptr() % 16 == 0):
+    if ok and vs >= 8 and vs % 4 == 0 and vol_cl.stride(2) == vs * Wb and vol_cl.stride(1) == vs * Wb * Hb and vol_cl.stride(0) == vs * Wb * Hb * D:
+        vol_layout = 0
+    elif ok and vol_cl.stride(1) >= 8 and vol_cl.stride(1) % 4 == 0 and vol_cl.stride(3) == vol_cl.stride(1) * D \
+            and vol_cl.stride(2) == vol_cl.stride(3) * Wb and vol_cl.stride(0) == vol_cl.stride(2) * Hb:
+        vol_layout, vs = 1, vol_cl.stride(1)
+    else:
         vol_cl = _f32(vol_cl)
         vs = 8
     bb = bundle_size * bundle_size
@@ -339,7 +350,7 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
     lib = _lib.load()
     _lib.check(lib.gdb_render_fused_fwd(src.rgba.data_ptr(), src.tex.data_ptr(), vol_cl.data_ptr(), depth_range.data_ptr(),
                                         vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], mlp.data_ptr(), B, V, H, W, bundle_size,
-                                        src.feat_dim, D, vs, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
+                                        src.feat_dim, D, vs, vol_layout, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
                                         int(out_channels_last), out_feat.data_ptr(), _p(out_dec), out_depth.data_ptr(), out_opac.data_ptr(),
                                         C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
     return res

@@ -63,8 +63,10 @@ int gdb_depth_values(const float* depth_range, int rh, int rw, int B, int D, int
  * build_feature_volume depth_net.py:424-476 fused with get_depth_values.
  * feat_cl (B,V,Hs,Ws,C) channels-last, C in {8,16,32}; proj (B,V,3,4);
  * depth_range as above -> variance (B,C,D,Ht,Wt) (NCDHW, the reference's
- * layout) or, with out_channels_last != 0, (B,D,Ht,Wt,C) (NDHWC: what cuDNN's
- * channels-last 3-D convolutions consume without a layout conversion).        */
+ * layout); out_channels_last = 1: (B,D,Ht,Wt,C) (NDHWC: what cuDNN's
+ * channels-last 3-D convolutions consume without a layout conversion);
+ * out_channels_last = 2: (B,Ht,Wt,D,C), depth folded into the channels of a
+ * channels-last 2-D map (the cost-regularisation net run on 2-D kernels).     */
 int gdb_warp_variance_fwd(const float* feat_cl, const float* proj, const float* depth_range, int rh, int rw,
                           int B, int V, int C, int Hs, int Ws, int D, int Ht, int Wt, int inv_depth,
                           int out_channels_last, float* variance, void* stream);
@@ -157,8 +159,10 @@ typedef struct gdb_render_taps {
 
 int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_cl, const float* depth_range,
                          const float* vol_range, const float* cam, int cam_stride, const float* mlp,
-                         int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int max_samples,
-                         int max_mip_level, int inv_depth, int adaptive,
+                         int B, int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride,
+                         int vol_layout /* 0: vol_cl is (B,D,Hb,Wb,vol_stride); 1: (B,Hb,Wb,D,vol_stride) - the depth-folded
+                                           output of the cost-regularisation net run on 2-D convolutions */,
+                         int max_samples, int max_mip_level, int inv_depth, int adaptive,
                          int precision /* 0 = fp32 SIMT MLP (1e-4 class); 1 = fp16-operand tcgen05 MLP, fp32 accumulate (2e-3 class);
                                           2 = split-fp16 (hi+lo) tcgen05 MLP, three MMAs per K step, fp32 accumulate (1e-4 class);
                                           3 = the first-generation kernel of class 1 (kept for A/B measurements) */,
