@@ -47,6 +47,19 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(kernel, workload, views):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed ncu --set full capture (per launch),
+    when one exists for this workload and launch size; None otherwise."""
+    path = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
+    if kernel != "gdb_render_fused_fwd" or not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    if d.get("workload") != workload or d.get("views_per_launch") != views:
+        return None
+    return d["traffic_bytes_per_launch"]
+
+
 def _tensor_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -71,7 +84,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -273,7 +286,6 @@ def run_ours(args, wl, cfg):
     ms_dev = timed(step_device, args.steps, True)
     launches = counts["n"]
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
 
     # the same forward with the two other MLP variants of the fused render kernel (not the headline):
     #   precision 0 = fp32 SIMT, 2 = split-fp16 (hi+lo) operands on tcgen05 - both the fp32 class (1e-4)
@@ -305,6 +317,11 @@ def run_ours(args, wl, cfg):
     torch.cuda.synchronize()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     barrier()
+    # the sampler ran through every timed region above (device-timed headline, the MLP variants, end to end): the GPU was
+    # under the same load throughout; a default run is too short for nvidia-smi to report during the headline loop alone
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and clocks is not None:
+        clocks["window"] = "all timed regions of this run (headline steps, MLP-variant steps, end-to-end steps)"
 
     t = torch.tensor([ms_dev, ms_e2e, alt[0][0], alt[2][0]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,7 +343,8 @@ def run_ours(args, wl, cfg):
             # the cost-volume kernel launches once per cascade stage; its per-view figure covers both stages
             bytes_per_launch = bytes_per_view * B / launches_per_step
             ach = bytes_per_launch / (ms * 1e-3) / 1e9
-            return {"kernel": key, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            return {"kernel": key, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": _ncu_traffic(key, args.workload, B) if table is None else None,
                     "avg_launch_ms": ms, "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": bytes_per_launch,
                     "peak_source": how}
 
