@@ -117,7 +117,7 @@ def test_full_size_sampling_properties_and_counts():
     assert torch.equal(idx, torch.repeat_interleave(torch.arange(NB), counts))
 
 
-@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("dtu", 2), ("nerf", 0), ("nerf", 1), ("nerf", 2)])
+@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("dtu", 2), ("nerf", 0), ("nerf", 1), ("nerf", 2), ("llff", 1)])
 def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
     """BASELINE.json sizes (DTU 512x640 2x2 bundles, NeRF-synthetic 800x800 4x4 bundles): parity with the oracle on
     identical inputs plus size-independent properties.  precision 1 = tensor-core MLP (2e-3 class)."""
@@ -216,7 +216,7 @@ def test_full_size_warp_variance_against_oracle():
         assert _md(var, truth) <= 1e-4 * max(1.0, float(truth.abs().max()))
 
 
-@pytest.mark.parametrize("workload", ["dtu", "nerf"])
+@pytest.mark.parametrize("workload", ["dtu", "nerf", "llff"])
 def test_default_mlp_arithmetic_meets_fp32_class_end_to_end(workload):
     """The default MLP arithmetic (tcgen05, fp16 operands, fp32 accumulation) against the fp32 SIMT arithmetic through the
     whole Network.forward at BASELINE.json sizes: the north star's fp32-class tolerance (1e-4 absolute on rgb and depth)
