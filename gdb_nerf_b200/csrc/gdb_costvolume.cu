@@ -114,12 +114,13 @@ __global__ void depth_values_kernel(const float* __restrict__ range, int rh, int
 // NCDHW (the reference's layout) through a shared-memory transpose.
 // ---------------------------------------------------------------------------
 struct WarpTap {
-  int xy;        // (y0 + 2) << 16 | (x0 + 2), clamped so that the packing is safe
-  float tx, ty;
+  int xx, yy;                 // clamped tap columns x0 | x1 << 16 and rows y0 | y1 << 16 (always inside the map)
+  float wx0, wx1, wy0, wy1;   // bilinear weights with the zero padding folded in (0 for a tap outside the map)
 };
 
-__device__ __forceinline__ WarpTap warp_tap(const float* __restrict__ P, float rx, float ry, float rz, float depth, float fWs,
-                                            float fHs) {
+// grid_sample(bilinear, zeros, align_corners=False) of depth_net.py:469-472 for one (pixel, view, depth): taps outside the
+// source map contribute zero, so their weight is zeroed and their address clamped - the loads need no predicate.
+__device__ __forceinline__ WarpTap warp_tap(const float* __restrict__ P, float rx, float ry, float rz, float depth, int Ws, int Hs) {
   float X = fmaf(rx, depth, P[3]);
   float Y = fmaf(ry, depth, P[7]);
   float Z = fmaxf(fmaf(rz, depth, P[11]), 1e-6f);
@@ -127,12 +128,17 @@ __device__ __forceinline__ WarpTap warp_tap(const float* __restrict__ P, float r
   // pixel-space coordinate u = X/Z maps to texel space u - 0.5 (normalise + grid_sample un-normalise cancel)
   float ix = fmaf(X, iz, -0.5f), iy = fmaf(Y, iz, -0.5f);
   float x0f = floorf(ix), y0f = floorf(iy);
+  const float tx = ix - x0f, ty = iy - y0f;
+  x0f = fminf(fmaxf(x0f, -2.f), (float)Ws + 1.f);    // also maps NaN to -2 (fully outside)
+  y0f = fminf(fmaxf(y0f, -2.f), (float)Hs + 1.f);
+  const int x0 = (int)x0f, y0 = (int)y0f;
   WarpTap t;
-  t.tx = ix - x0f;
-  t.ty = iy - y0f;
-  x0f = fminf(fmaxf(x0f, -2.f), fWs + 1.f);    // also maps NaN to -2 (fully outside)
-  y0f = fminf(fmaxf(y0f, -2.f), fHs + 1.f);
-  t.xy = (((int)y0f + 2) << 16) | ((int)x0f + 2);
+  t.wx0 = (unsigned)x0 < (unsigned)Ws ? 1.f - tx : 0.f;
+  t.wx1 = (unsigned)(x0 + 1) < (unsigned)Ws ? tx : 0.f;
+  t.wy0 = (unsigned)y0 < (unsigned)Hs ? 1.f - ty : 0.f;
+  t.wy1 = (unsigned)(y0 + 1) < (unsigned)Hs ? ty : 0.f;
+  t.xx = min(max(x0, 0), Ws - 1) | (min(max(x0 + 1, 0), Ws - 1) << 16);
+  t.yy = min(max(y0, 0), Hs - 1) | (min(max(y0 + 1, 0), Hs - 1) << 16);
   return t;
 }
 
@@ -175,7 +181,6 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
   const int ryi = rh == 1 ? 0 : py, rxi = rw == 1 ? 0 : px;
   const float near_ = range[((size_t)(b * 2 + 0) * rh + ryi) * rw + rxi];
   const float far_ = range[((size_t)(b * 2 + 1) * rh + ryi) * rw + rxi];
-  const float fWs = (float)Ws, fHs = (float)Hs;
   const size_t view_stride = (size_t)Hs * Ws * C;
   const float* fbase = feat + (size_t)b * V * view_stride + q * 4;
 
@@ -186,36 +191,36 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
     float dv = hypothesis(near_, far_, d, D, inv_depth);
     float depth = inv_depth ? fdiv(1.f, dv) : dv;
     WarpTap mine;
-    if (SHARE) mine = warp_tap(sproj + min(q, V - 1) * 12, rx[0], ry[0], rz[0], depth, fWs, fHs);
+    if (SHARE) mine = warp_tap(sproj + min(q, V - 1) * 12, rx[0], ry[0], rz[0], depth, Ws, Hs);
     float4 val[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       WarpTap t;
       if (SHARE) {
-        t.xy = __shfl_sync(0xffffffffu, mine.xy, group_base + v);
-        t.tx = __shfl_sync(0xffffffffu, mine.tx, group_base + v);
-        t.ty = __shfl_sync(0xffffffffu, mine.ty, group_base + v);
+        t.xx = __shfl_sync(0xffffffffu, mine.xx, group_base + v);
+        t.yy = __shfl_sync(0xffffffffu, mine.yy, group_base + v);
+        t.wx0 = __shfl_sync(0xffffffffu, mine.wx0, group_base + v);
+        t.wx1 = __shfl_sync(0xffffffffu, mine.wx1, group_base + v);
+        t.wy0 = __shfl_sync(0xffffffffu, mine.wy0, group_base + v);
+        t.wy1 = __shfl_sync(0xffffffffu, mine.wy1, group_base + v);
       } else {
-        t = warp_tap(sproj + v * 12, rx[SHARE ? 0 : v], ry[SHARE ? 0 : v], rz[SHARE ? 0 : v], depth, fWs, fHs);
+        t = warp_tap(sproj + v * 12, rx[SHARE ? 0 : v], ry[SHARE ? 0 : v], rz[SHARE ? 0 : v], depth, Ws, Hs);
       }
-      const int x0 = (t.xy & 0xffff) - 2, y0 = (t.xy >> 16) - 2;
-      const bool vx0 = (unsigned)x0 < (unsigned)Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)Ws;
-      const bool vy0 = (unsigned)y0 < (unsigned)Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)Hs;
-      const float* vb = fbase + v * view_stride + ((ptrdiff_t)y0 * Ws + x0) * C;
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 t00 = zero, t10 = zero, t01 = zero, t11 = zero;
-      if (live) {
-        if (vx0 && vy0) t00 = ldg4(vb);
-        if (vx1 && vy0) t10 = ldg4(vb + C);
-        if (vx0 && vy1) t01 = ldg4(vb + (size_t)Ws * C);
-        if (vx1 && vy1) t11 = ldg4(vb + (size_t)Ws * C + C);
+      const int r0 = (t.yy & 0xffff) * Ws, r1 = (t.yy >> 16) * Ws;
+      const int c0 = t.xx & 0xffff, c1 = t.xx >> 16;
+      const float4* vb = reinterpret_cast<const float4*>(fbase + v * view_stride);
+      constexpr int CQ = C / 4;
+      // dead pixels of the last tile read pixel (0, 0)'s taps: in bounds, never stored
+      const float4 t00 = __ldg(vb + (r0 + c0) * CQ), t10 = __ldg(vb + (r0 + c1) * CQ);
+      const float4 t01 = __ldg(vb + (r1 + c0) * CQ), t11 = __ldg(vb + (r1 + c1) * CQ);
+      float4 acc;
+      {
+        const float w = t.wx0 * t.wy0;
+        acc = make_float4(t00.x * w, t00.y * w, t00.z * w, t00.w * w);
       }
-      const float wx1 = t.tx, wx0 = 1.f - t.tx, wy1 = t.ty, wy0 = 1.f - t.ty;
-      float4 acc = zero;
-      acc = f4_scale_add(acc, t00, wx0 * wy0);
-      acc = f4_scale_add(acc, t10, wx1 * wy0);
-      acc = f4_scale_add(acc, t01, wx0 * wy1);
-      acc = f4_scale_add(acc, t11, wx1 * wy1);
+      acc = f4_scale_add(acc, t10, t.wx1 * t.wy0);
+      acc = f4_scale_add(acc, t01, t.wx0 * t.wy1);
+      acc = f4_scale_add(acc, t11, t.wx1 * t.wy1);
       val[v] = acc;
     }
     float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
