@@ -323,6 +323,35 @@ def run_ours(args, wl, cfg):
     if rank == 0 and clocks is not None:
         clocks["window"] = "all timed regions of this run (headline steps, MLP-variant steps, end-to-end steps)"
 
+    # latency of ONE target view per call (the "ms/target-view" half of the metric for an interactive caller): eager launches
+    # vs the whole forward replayed as one CUDA graph (gdb_nerf_b200/graphed.py); rank 0 only, not the headline
+    latency = None
+    if rank == 0:
+        from gdb_nerf_b200.graphed import GraphedForward
+        one = batch_to(workload_batch(args.workload, B=1, V=3, seed=0), dev)
+        with torch.no_grad():
+            for _ in range(5):
+                net(one)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            for _ in range(20):
+                net(one)
+        torch.cuda.synchronize()
+        eager_ms = (time.perf_counter() - t1) / 20 * 1e3
+        runner = GraphedForward(net, one)
+        for _ in range(3):
+            runner(one)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(20):
+            runner(one)
+        torch.cuda.synchronize()
+        latency = {"what": "Network.forward on ONE target view per call, inputs resident, wall clock per call, mean of 20",
+                   "eager_ms": eager_ms, "cuda_graph_ms": (time.perf_counter() - t1) / 20 * 1e3}
+        del runner
+    barrier()
+
     t = torch.tensor([ms_dev, ms_e2e, alt[0][0], alt[2][0]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,6 +407,7 @@ def run_ours(args, wl, cfg):
                     "ms_per_step": ms_e2e / args.steps, "what": "pinned host batch -> H2D -> Network.forward -> D2H of ret['rgb'] into pinned memory, every step; two steps in "
                             "flight on two streams (copies overlap kernels); wall clock over all steps"},
             "gpu_launches": launches,
+            "single_view_latency": latency,
             "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload]),
             "roofline_warp_variance": roof("gdb_warp_variance_fwd", K1_BYTES_PER_VIEW[args.workload]),
             "roofline_mlp_tensor": roof_tensor("gdb_render_fused_fwd", K3_MLP_FLOP_PER_VIEW[args.workload]),

@@ -238,3 +238,23 @@ def test_default_mlp_arithmetic_meets_fp32_class_end_to_end(workload):
     assert _md(outs[1]["mvs_depth"], outs[0]["mvs_depth"]) <= 1e-5 * (w["far"] - w["near"])     # same CNNs; cuDNN run-to-run noise only
     mse = float(((outs[1]["rgb"].double() - outs[0]["rgb"].double()) ** 2).mean())
     assert mse < 1e-9
+
+
+def test_cuda_graph_forward_matches_eager():
+    """the eval forward has no host synchronisation, so it captures into one CUDA graph; the replay on new
+    inputs reproduces the eager forward (same kernels, same order)."""
+    from gdb_nerf_b200.graphed import GraphedForward
+    cfg = make_cfg("dtu_eval")
+    torch.manual_seed(0)
+    net = Network(cfg).to(DEV).eval()
+    mk = lambda seed: batch_to(make_batch(2, 3, 64, 96, 425.0, 905.0, 180.0, seed=seed, images="smooth", tilt=0.03), DEV)
+    runner = GraphedForward(net, mk(0))
+    for seed in (1, 2):
+        batch = mk(seed)
+        with torch.no_grad():
+            want = net(batch)[0]
+        got = runner(batch)[0]
+        torch.cuda.synchronize()
+        for k in ("rgb", "nerf_depth", "mvs_depth", "opacity"):
+            scale = 480.0 if "depth" in k else 1.0
+            assert _md(got[k], want[k]) <= 1e-5 * scale, k
