@@ -411,9 +411,21 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
     for blk in dec.blocks:
         zb = _cached(blk, "_gdb_zero", (blk.conv1.weight,), lambda: torch.zeros(blk.conv1.weight.shape[0], device=x.device))
         a = torch.cudnn_convolution_relu(h, blk.conv1.weight, zb, (1, 1), (1, 1), (1, 1), 1)
-        b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
-        c = blk.conv3(torch.cat((h, a, b), 1))
-        gate = blk.se.fc(c.mean((2, 3)))
+        if ops._is_cl(h) and ops._is_cl(a) and h.shape[1] % 4 == 0 and a.shape[1] % 4 == 0:
+            # conv2(cat(h, a)) = relu(conv(a; W_a) + conv(h; W_h)): the second term is cuDNN's fused conv + add + ReLU, so
+            # the first concatenation of the block is never materialised; the second one is one streaming pass
+            ch = h.shape[1]
+            wh, wa = _cached(blk, "_gdb_split2", (blk.conv2.weight,), lambda: (
+                blk.conv2.weight[:, :ch].contiguous(memory_format=torch.channels_last),
+                blk.conv2.weight[:, ch:].contiguous(memory_format=torch.channels_last)))
+            z = torch.cudnn_convolution(h, wh, (1, 1), (1, 1), (1, 1), 1, False, False, torch.backends.cudnn.allow_tf32)
+            b = torch.cudnn_convolution_add_relu(a, wa, z, 1.0, zb, (1, 1), (1, 1), (1, 1), 1)
+            c = blk.conv3(ops.concat_channels(h, a, b))
+            gate = blk.se.fc(ops.channel_mean(c) if ops._is_cl(c) else c.mean((2, 3)))
+        else:
+            b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
+            c = blk.conv3(torch.cat((h, a, b), 1))
+            gate = blk.se.fc(c.mean((2, 3)))
         h = ops.gate_add(h, c, gate) if ops._is_cl(h) and ops._is_cl(c) else h + c * gate[:, :, None, None]
     y = y + h
     mods = list(dec.up)

@@ -7,6 +7,8 @@
 //                      cost_reg_net.py:108-110 (y = s + relu(bn(deconv)))  and the
 //                      FPN top-down step feature_net.py:52-58
 //   gdb_gate_add     : out = x + y * gate[n, c]      decoder_rdn.py squeeze-excite residual
+//   gdb_concat3      : channel concatenation of up to three maps (dense block inputs, decoder_rdn.py:36-41)
+//   gdb_channel_mean : per-image channel means (squeeze step of the squeeze-excite gate), deterministic two-stage sum
 #include <algorithm>
 
 #include "gdb_common.cuh"
@@ -52,6 +54,55 @@ __global__ void gate_add_kernel(const float4* __restrict__ x, const float4* __re
   }
 }
 
+
+__global__ void concat3_kernel(const float4* __restrict__ a, int a4, const float4* __restrict__ b, int b4, const float4* __restrict__ c,
+                               int c4, int64_t n4, float4* __restrict__ out) {
+  const int t4 = a4 + b4 + c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / t4;
+    const int q = (int)(i - pix * t4);
+    float4 v;
+    if (q < a4) v = __ldcs(a + pix * a4 + q);
+    else if (q < a4 + b4) v = __ldcs(b + pix * b4 + (q - a4));
+    else v = __ldcs(c + pix * c4 + (q - a4 - b4));
+    out[i] = v;
+  }
+}
+
+// stage 1: CTA (chunk, n) sums its pixels per channel; 256 threads = (256 / C4) pixel lanes x C4 channel quads
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restrict__ x, int C4, int64_t S, int chunks, float4* __restrict__ partial) {
+  __shared__ float4 red[256];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int q = threadIdx.x % C4, pl = threadIdx.x / C4, PL = 256 / C4;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = chunk * per, p1 = min(p0 + per, S);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < PL)
+    for (int64_t p = p0 + pl; p < p1; p += PL) {
+      const float4 v = __ldg(x + ((int64_t)n * S + p) * C4 + q);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (pl == 0) {
+    for (int k = 1; k < PL; ++k) {
+      const float4 v = red[k * C4 + q];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    partial[((int64_t)n * chunks + chunk) * C4 + q] = acc;
+  }
+}
+// stage 2: fixed-order sum over the chunks
+__global__ void channel_mean_finish_kernel(const float* __restrict__ partial, int C, int chunks, int64_t N, float inv_S, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int64_t n = i / C;
+  const int c = (int)(i - n * C);
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[((int64_t)n * chunks + k) * C + c];
+  out[i] = s * inv_S;
+}
+
 }  // namespace gdb
 
 using namespace gdb;
@@ -78,4 +129,26 @@ extern "C" int gdb_gate_add(const float* x, const float* y, const float* gate, i
   gate_add_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), gate,
                                                          C / 4, S * (C / 4), n4, reinterpret_cast<float4*>(out));
   return cuda_check("gdb_gate_add");
+}
+
+extern "C" int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream) {
+  GDB_REQUIRE(a && b && out && npix > 0 && Ca > 0 && Cb > 0 && Cc >= 0 && (Cc == 0 || c), GDB_E_BADARG, "gdb_concat3: bad argument");
+  GDB_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && Cc % 4 == 0, GDB_E_BADARG, "gdb_concat3: channel counts must be multiples of 4");
+  GDB_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out) && (!c || aligned16(c)), GDB_E_ALIGN, "gdb_concat3: pointers must be 16-byte aligned");
+  const int64_t n4 = npix * ((Ca + Cb + Cc) / 4);
+  int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 16);
+  concat3_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), Ca / 4, reinterpret_cast<const float4*>(b), Cb / 4,
+                                                        reinterpret_cast<const float4*>(c), Cc / 4, n4, reinterpret_cast<float4*>(out));
+  return cuda_check("gdb_concat3");
+}
+
+extern "C" int gdb_channel_mean(const float* x, int64_t N, int64_t S, int C, int chunks, float* partial, float* out, void* stream) {
+  GDB_REQUIRE(x && partial && out && N > 0 && S > 0 && chunks > 0, GDB_E_BADARG, "gdb_channel_mean: bad argument");
+  GDB_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, GDB_E_BADARG, "gdb_channel_mean: C must be a multiple of 4 in [4, 1024]");
+  GDB_REQUIRE(aligned16(x) && aligned16(partial), GDB_E_ALIGN, "gdb_channel_mean: pointers must be 16-byte aligned");
+  dim3 grid(chunks, (unsigned)N);
+  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), C / 4, S, chunks, reinterpret_cast<float4*>(partial));
+  const int64_t n = N * C;
+  channel_mean_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, C, chunks, N, 1.f / (float)S, out);
+  return cuda_check("gdb_channel_mean");
 }

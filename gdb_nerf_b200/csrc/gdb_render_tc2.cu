@@ -390,6 +390,23 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
 #pragma unroll
         for (int j = 0; j < 4; ++j) dir[j] = __shfl_sync(full, d_dir[v][j], src);
         const bool act = ok && (pk >> 31);
+#ifdef GDB_TC2_UNCOND
+        const int dy0 = pk & 0x3FFF, dy1 = (pk >> 14) & 0x3FFF;
+        const int dx0 = ((pk >> 28) & 1) * QL, dx1 = ((pk >> 29) & 1) * QL;
+        const int i0 = a0 + gq;
+        float4 f = bilerp4(__ldg(tex4 + i0), __ldg(tex4 + (i0 + dx0)), __ldg(tex4 + (i0 + dy0)), __ldg(tex4 + (i0 + dy0 + dx0)), fu0, fv0);
+        if ((pk >> 30) & 1) {
+          const int i1 = a1 + gq;
+          float4 bq = bilerp4(__ldg(tex4 + i1), __ldg(tex4 + (i1 + dx1)), __ldg(tex4 + (i1 + dy1)), __ldg(tex4 + (i1 + dy1 + dx1)), fu1, fv1);
+          f.x = lerpf(f.x, bq.x, frac); f.y = lerpf(f.y, bq.y, frac); f.z = lerpf(f.z, bq.z, frac); f.w = lerpf(f.w, bq.w, frac);
+        }
+        if (!act) f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TAPS && p.tap_rfd && act) {
+          float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
+          tp[0] = f.x; tp[1] = f.y; tp[2] = f.z;
+          if (!last_quad) tp[3] = f.w;
+        }
+#else
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
           const int dy0 = pk & 0x3FFF, dy1 = (pk >> 14) & 0x3FFF;
@@ -407,6 +424,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             if (!last_quad) tp[3] = f.w;
           }
         }
+#endif
         // view_fc + residual, my four channels
         float fe[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
@@ -474,10 +492,15 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       for (int v = 0; v < V; ++v) {
         float gv[32];
         tmem_ld32(tmem_row + v * 32, gv);
-        float s = vec[C::X_SCAL + 0];
+        float s0 = vec[C::X_SCAL + 0], s1 = 0.f, s2_ = 0.f, s3 = 0.f;     // four independent chains (FMA latency)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) s = fmaf(fmaxf(gv[k], 0.f), vec[C::X_AGG_W + k], s);
-        s = fmaxf(s, 0.f);
+        for (int k = 0; k < 32; k += 4) {
+          s0 = fmaf(fmaxf(gv[k + 0], 0.f), vec[C::X_AGG_W + k + 0], s0);
+          s1 = fmaf(fmaxf(gv[k + 1], 0.f), vec[C::X_AGG_W + k + 1], s1);
+          s2_ = fmaf(fmaxf(gv[k + 2], 0.f), vec[C::X_AGG_W + k + 2], s2_);
+          s3 = fmaf(fmaxf(gv[k + 3], 0.f), vec[C::X_AGG_W + k + 3], s3);
+        }
+        float s = fmaxf((s0 + s1) + (s2_ + s3), 0.f);
 #pragma unroll
         for (int u = 0; u < V; ++u)
           if (u == v) aw[u] = s;
@@ -588,15 +611,20 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
 #pragma unroll 1
       for (int i = 0; i < nv; ++i) {
-        float s2 = vec[C::X_SCAL + 2];
+        float q0 = vec[C::X_SCAL + 2], q1 = 0.f, q2 = 0.f, q3 = 0.f;        // four independent chains (FMA latency)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float hid[32];
           tmem_ld32(tmem_row + i * 64 + half * 32, hid);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) s2 = fmaf(fmaxf(hid[k], 0.f), vec[C::X_W2_W + half * 32 + k], s2);
+          for (int k = 0; k < 32; k += 4) {
+            q0 = fmaf(fmaxf(hid[k + 0], 0.f), vec[C::X_W2_W + half * 32 + k + 0], q0);
+            q1 = fmaf(fmaxf(hid[k + 1], 0.f), vec[C::X_W2_W + half * 32 + k + 1], q1);
+            q2 = fmaf(fmaxf(hid[k + 2], 0.f), vec[C::X_W2_W + half * 32 + k + 2], q2);
+            q3 = fmaf(fmaxf(hid[k + 3], 0.f), vec[C::X_W2_W + half * 32 + k + 3], q3);
+          }
         }
-        s2 = fmaxf(s2, 0.f);
+        const float s2 = fmaxf((q0 + q1) + (q2 + q3), 0.f);
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (v == v0 + i) wv[v] = s2;

@@ -198,6 +198,34 @@ def gate_add(x: Tensor, y: Tensor, gate: Tensor) -> Tensor:
     return out
 
 
+def concat_channels(a: Tensor, b: Tensor, c: Optional[Tensor] = None) -> Tensor:
+    """torch.cat((a, b[, c]), 1) for dense channels-last (N,C,H,W)-shaped fp32 maps, one streaming pass."""
+    _dev(a, b, c)
+    ts = [t for t in (a, b, c) if t is not None]
+    if not all(_is_cl(t) and t.shape[1] % 4 == 0 and t.shape[0] == a.shape[0] and t.shape[2:] == a.shape[2:] for t in ts):
+        raise _lib.GdbError("concat_channels needs dense channels-last fp32 maps of one size with C % 4 == 0")
+    N, _, H, W = a.shape
+    Ct = sum(t.shape[1] for t in ts)
+    out = torch.empty((N, H, W, Ct), device=a.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_concat3(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], _p(c), 0 if c is None else c.shape[1], N * H * W,
+                               out.data_ptr(), _stream()), "gdb_concat3")
+    return out.permute(0, 3, 1, 2)
+
+
+def channel_mean(x: Tensor, chunks: int = 64) -> Tensor:
+    """x.mean((2, 3)) for a dense channels-last (N,C,H,W)-shaped fp32 map -> (N, C); fixed summation order."""
+    _dev(x)
+    if not (_is_cl(x) and x.shape[1] % 4 == 0):
+        raise _lib.GdbError("channel_mean needs a dense channels-last fp32 map with C % 4 == 0")
+    N, Cc, H, W = x.shape
+    partial = torch.empty((N, chunks, Cc), device=x.device, dtype=torch.float32)
+    out = torch.empty((N, Cc), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_channel_mean(x.data_ptr(), N, H * W, Cc, chunks, partial.data_ptr(), out.data_ptr(), _stream()), "gdb_channel_mean")
+    return out
+
+
 # ---------------------------------------------------------------- sampling --
 def camera_block(tar_exts: Tensor, tar_ints: Tensor, src_exts: Tensor, src_ints: Tensor, near_far: Tensor, bundle_size: int,
                  global_num_depth: int, inv_depth: bool) -> Tensor:

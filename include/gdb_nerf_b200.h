@@ -250,6 +250,12 @@ int gdb_bias_act_add(const float* x, const float* bias, const float* skip, int64
 /* out = x + y * gate[n,c]: squeeze-excite residual of the decoder's dense
  * blocks (decoder_rdn.py:31-41).  gate (N,C).                                 */
 int gdb_gate_add(const float* x, const float* y, const float* gate, int64_t N, int64_t S, int C, float* out, void* stream);
+/* Channel concatenation of channels-last maps over npix pixels: out (npix, Ca+Cb+Cc) = [a | b | c] (c may be null with
+ * Cc = 0): the inputs of the dense block's second and third convolutions (decoder_rdn.py:36-41).                          */
+int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream);
+/* Per-image channel means of a channels-last map x (N, S, C) -> out (N, C): the squeeze of the squeeze-excite gate
+ * (modules.py, AdaptiveAvgPool2d(1)).  partial (N, chunks, C) is scratch; the summation order is fixed.                    */
+int gdb_channel_mean(const float* x, int64_t N, int64_t S, int C, int chunks, float* partial, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -340,6 +340,14 @@ def test_glue_epilogues_match_torch():
     assert _md(ops.gate_add(lat, y, gate), lat + y * gate[:, :, None, None]) <= 1e-6
     with pytest.raises(ops._lib.GdbError):
         ops.bias_act_add(lat.contiguous(), b2, None, relu=False)                                 # planar memory is refused, not converted
+    # dense-block concatenation and the squeeze of the squeeze-excite gate (decoder_rdn.py:36-41, modules.py)
+    a8 = torch.randn(3, 8, 8, 12, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    cat3 = ops.concat_channels(lat, a8, y)
+    assert torch.equal(cat3, torch.cat((lat, a8, y), 1)) and ops._is_cl(cat3)
+    assert torch.equal(ops.concat_channels(lat, a8), torch.cat((lat, a8), 1))
+    big = torch.randn(2, 64, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    assert _md(ops.channel_mean(big), big.double().mean((2, 3))) <= 1e-6
+    assert _md(ops.channel_mean(big, chunks=7), big.double().mean((2, 3))) <= 1e-6
 
 
 def test_assemble_output_pre_shuffle_decoder(golden):
