@@ -432,7 +432,12 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
     if not mods:
         raise ValueError("decoder_fused needs upscale_factor >= 2")
     for i in range(0, len(mods) - 2, 2):
-        y = mods[i + 1](mods[i](y))
+        conv = mods[i]
+        if ops._is_cl(y) and conv.weight.shape[0] % 16 == 0:
+            # up-sampling stage: convolution without its bias, then bias + PixelShuffle(2) in one channels-last pass
+            y = ops.pixel_shuffle2_bias(F.conv2d(y, conv.weight, None, 1, 1), conv.bias)
+        else:
+            y = mods[i + 1](conv(y))
     up, oc = mods[-2], dec.out_conv
 
     def make():

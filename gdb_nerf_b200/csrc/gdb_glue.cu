@@ -8,6 +8,7 @@
 //                      FPN top-down step feature_net.py:52-58
 //   gdb_gate_add     : out = x + y * gate[n, c]      decoder_rdn.py squeeze-excite residual
 //   gdb_concat3      : channel concatenation of up to three maps (dense block inputs, decoder_rdn.py:36-41)
+//   gdb_pixel_shuffle2: PixelShuffle(2) + the producing convolution's bias on channels-last maps (decoder_rdn.py:76-80)
 //   gdb_channel_mean : per-image channel means (squeeze step of the squeeze-excite gate), deterministic two-stage sum
 #include <algorithm>
 
@@ -103,6 +104,35 @@ __global__ void channel_mean_finish_kernel(const float* __restrict__ partial, in
   out[i] = s * inv_S;
 }
 
+// PixelShuffle(2) of a channels-last map with the producing convolution's bias: in (N,H,W,4C) -> out (N,2H,2W,C),
+// out[n, 2y+dy, 2x+dx, c] = in[n, y, x, 4c + 2dy + dx] + bias[4c + 2dy + dx]   (decoder_rdn.py:76-80)
+// thread = (input pixel, four output channels): 64 contiguous bytes in, a 4x4 transpose, one float4 to each of the 4 output pixels
+__global__ void pixel_shuffle2_kernel(const float4* __restrict__ in, const float* __restrict__ bias, int C4, int H, int W, int64_t n,
+                                      float4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C4;
+    const int q = (int)(i - pix * C4);                 // output channels 4q .. 4q+3
+    const int x = (int)(pix % W);
+    const int64_t t = pix / W;
+    const int y = (int)(t % H);
+    const int64_t img = t / H;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                      // v[k] = input channels 4(4q+k) .. +3 = (dy,dx) of output channel 4q+k
+      v[k] = __ldcs(in + (pix * C4 + q) * 4 + k);
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q * 4 + k);
+        v[k].x += b.x; v[k].y += b.y; v[k].z += b.z; v[k].w += b.w;
+      }
+    }
+    const int64_t o00 = ((img * 2 * H + 2 * y) * 2 * W + 2 * x) * C4 + q;
+    out[o00] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+    out[o00 + C4] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+    out[o00 + (int64_t)2 * W * C4] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+    out[o00 + (int64_t)2 * W * C4 + C4] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+  }
+}
+
 }  // namespace gdb
 
 using namespace gdb;
@@ -151,4 +181,13 @@ extern "C" int gdb_channel_mean(const float* x, int64_t N, int64_t S, int C, int
   const int64_t n = N * C;
   channel_mean_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, C, chunks, N, 1.f / (float)S, out);
   return cuda_check("gdb_channel_mean");
+}
+
+extern "C" int gdb_pixel_shuffle2(const float* in, const float* bias, int64_t N, int H, int W, int C, float* out, void* stream) {
+  GDB_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, GDB_E_BADARG, "gdb_pixel_shuffle2: bad argument (C %% 4 must be 0)");
+  GDB_REQUIRE(aligned16(in) && aligned16(out) && (!bias || aligned16(bias)), GDB_E_ALIGN, "gdb_pixel_shuffle2: pointers must be 16-byte aligned");
+  const int64_t n = N * H * W * (C / 4);
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
+  pixel_shuffle2_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(in), bias, C / 4, H, W, n, reinterpret_cast<float4*>(out));
+  return cuda_check("gdb_pixel_shuffle2");
 }

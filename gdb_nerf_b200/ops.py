@@ -213,6 +213,20 @@ def concat_channels(a: Tensor, b: Tensor, c: Optional[Tensor] = None) -> Tensor:
     return out.permute(0, 3, 1, 2)
 
 
+def pixel_shuffle2_bias(x: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """F.pixel_shuffle(x + bias, 2) for a dense channels-last (N,4C,H,W)-shaped fp32 map -> (N,C,2H,2W) channels-last."""
+    _dev(x, bias)
+    N, C4, H, W = x.shape
+    if not (_is_cl(x) and C4 % 16 == 0):
+        raise _lib.GdbError("pixel_shuffle2_bias needs a dense channels-last fp32 map with C % 16 == 0")
+    Cc = C4 // 4
+    out = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.gdb_pixel_shuffle2(x.data_ptr(), _p(None if bias is None else _f32(bias)), N, H, W, Cc, out.data_ptr(), _stream()),
+               "gdb_pixel_shuffle2")
+    return out.permute(0, 3, 1, 2)
+
+
 def channel_mean(x: Tensor, chunks: int = 64) -> Tensor:
     """x.mean((2, 3)) for a dense channels-last (N,C,H,W)-shaped fp32 map -> (N, C); fixed summation order."""
     _dev(x)

@@ -253,6 +253,9 @@ int gdb_gate_add(const float* x, const float* y, const float* gate, int64_t N, i
 /* Channel concatenation of channels-last maps over npix pixels: out (npix, Ca+Cb+Cc) = [a | b | c] (c may be null with
  * Cc = 0): the inputs of the dense block's second and third convolutions (decoder_rdn.py:36-41).                          */
 int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream);
+/* PixelShuffle(2) of a channels-last map fused with the producing convolution's bias (decoder_rdn.py:76-80):
+ * in (N,H,W,4C), bias (4C) or null -> out (N,2H,2W,C), out[n,2y+dy,2x+dx,c] = in[n,y,x,4c+2dy+dx] + bias[4c+2dy+dx].          */
+int gdb_pixel_shuffle2(const float* in, const float* bias, int64_t N, int H, int W, int C, float* out, void* stream);
 /* Per-image channel means of a channels-last map x (N, S, C) -> out (N, C): the squeeze of the squeeze-excite gate
  * (modules.py, AdaptiveAvgPool2d(1)).  partial (N, chunks, C) is scratch; the summation order is fixed.                    */
 int gdb_channel_mean(const float* x, int64_t N, int64_t S, int C, int chunks, float* partial, float* out, void* stream);

@@ -345,6 +345,10 @@ def test_glue_epilogues_match_torch():
     cat3 = ops.concat_channels(lat, a8, y)
     assert torch.equal(cat3, torch.cat((lat, a8, y), 1)) and ops._is_cl(cat3)
     assert torch.equal(ops.concat_channels(lat, a8), torch.cat((lat, a8), 1))
+    ps_in = torch.randn(2, 32, 6, 10, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    ps_b = torch.randn(32, generator=g).to(DEV)
+    ps = ops.pixel_shuffle2_bias(ps_in, ps_b)
+    assert torch.equal(ps, F_.pixel_shuffle(ps_in + ps_b.view(1, -1, 1, 1), 2)) and ops._is_cl(ps)
     big = torch.randn(2, 64, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
     assert _md(ops.channel_mean(big), big.double().mean((2, 3))) <= 1e-6
     assert _md(ops.channel_mean(big, chunks=7), big.double().mean((2, 3))) <= 1e-6

@@ -37,7 +37,7 @@ def main():
     cfg = make_cfg(wl["recipe"])
     torch.manual_seed(0)
     net = Network(cfg).to(dev).eval()
-    net.mlp_precision = 1 if args.tc else 0
+    net.mlp_precision = 0 if args.tc is False and False else net.mlp_precision
     if args.channels_last:
         net.feature_net.to(memory_format=torch.channels_last)
         net.upsampler.to(memory_format=torch.channels_last)
