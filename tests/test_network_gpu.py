@@ -258,3 +258,38 @@ def test_cuda_graph_forward_matches_eager():
         for k in ("rgb", "nerf_depth", "mvs_depth", "opacity"):
             scale = 480.0 if "depth" in k else 1.0
             assert _md(got[k], want[k]) <= 1e-5 * scale, k
+
+
+@pytest.mark.parametrize("max_samples,adaptive", [(1, False), (2, True), (4, True), (5, False), (8, True), (32, False)])
+def test_sample_counts_and_ragged_tiles(max_samples, adaptive):
+    """Every legal samples-per-bundle limit (the C ABI takes 1..32; the shipped recipes use 3 and 6), a bundle map whose
+    size is not a multiple of the kernel's tile (partial last tile), two target views with different cameras in one launch,
+    fixed and adaptive sampling: every MLP arithmetic against the oracle, indices bit-exact."""
+    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs("dtu", V=3, seed=11, hw=(48, 112))
+    b = cfg.nerf.bundle_size
+    H, W = w["H"], w["W"]
+    Hb, Wb = H // b, W // b
+    B = 2
+    rig = camera_rig(B, 3, H, W, w["near"], w["far"], w["focal"], tilt=0.03)
+    g = torch.Generator().manual_seed(5)
+    data = {k: torch.cat((v, v.flip(-1) * 0.9 + 0.05 * torch.rand(v.shape, generator=g)), 0) for k, v in data.items()}
+    min_iv = (w["far"] - w["near"]) / cfg.nerf.global_num_depth
+    mid = w["near"] + (w["far"] - w["near"]) * (0.3 + 0.4 * torch.rand(B, 1, Hb, Wb, generator=g))
+    half = torch.rand(B, 1, Hb, Wb, generator=g) * (0.55 * max_samples * min_iv)
+    data["depth_range"] = torch.cat((mid - half, mid + half), 1)
+    data["vol_range"] = torch.cat((mid - 2.5 * min_iv, mid + 2.5 * min_iv), 1)
+    truth = O.render_bundles(mlp, feat_dim, data["rgb"], data["feat"], data["vol"], data["depth_range"], data["vol_range"],
+                             rig["src_exts"], rig["src_ints"], rig["tar_exts"], rig["tar_ints"], rig["near_far"], b,
+                             max_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, False, adaptive)
+    cam = ops.camera_block(rig["tar_exts"].to(DEV), rig["tar_ints"].to(DEV), rig["src_exts"].to(DEV), rig["src_ints"].to(DEV),
+                           rig["near_far"].to(DEV), b, cfg.nerf.global_num_depth, False)
+    src = ops.prepare_sources(data["feat"].to(DEV), data["rgb"].to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(data["vol"].to(DEV), 8)
+    sl = ops.sample_bundles(data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam, b, max_samples, False, adaptive)
+    assert torch.equal(sl.indices.cpu(), truth["indices"])
+    for precision in (0, 1, 2):
+        out = ops.render_fused(src, vol_cl, data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam,
+                               ops.pack_mlp(mlp, feat_dim, device=DEV), B, 3, H, W, b, max_samples, False, adaptive, precision=precision)
+        assert _md(out["feat"], truth["bundle_feat"]) <= (2e-3 if precision == 1 else 1e-4), precision
+        assert _md(out["depth"], truth["bundle_depth"]) <= 1e-4 * (w["far"] - w["near"]), precision
+        assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
