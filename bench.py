@@ -479,12 +479,14 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("gdb_timed")
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(stream)
     for _ in range(args.steps):
         loss, nbytes = step()
     e.record(stream)
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
     ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

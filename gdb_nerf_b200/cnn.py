@@ -130,8 +130,20 @@ def _cached(mod: nn.Module, name: str, tensors, make):
 
 def feature_net_fused(net: "FeatureNet", x: torch.Tensor, levels: int = 3) -> List[torch.Tensor]:
     from . import ops
-    x = x.contiguous(memory_format=torch.channels_last)
-    f0 = run_block(net.conv0[1], run_block(net.conv0[0], x))
+    blk0 = net.conv0[0]
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[1] < 8 and blk0[0].groups == 1:
+        # RGB planes -> 8-channel channels-last pixels (zero pad) in one pass; the first convolution gets zero weights for
+        # the pad: cuDNN then needs no layout conversion and picks a 1.6x faster kernel than for 3 input channels
+        c_in = x.shape[1]
+        x = ops.to_channels_last(x.contiguous(), 8).permute(0, 3, 1, 2)
+        w, b = _folded(blk0)
+        w8 = _cached(blk0, "_gdb_pad8", (w,), lambda: F.pad(w, (0, 0, 0, 0, 0, 8 - c_in)).contiguous(memory_format=torch.channels_last))
+        conv = blk0[0]
+        f0 = torch.cudnn_convolution_relu(x, w8, b, conv.stride, conv.padding, conv.dilation, 1)
+    else:
+        x = x.contiguous(memory_format=torch.channels_last)
+        f0 = run_block(blk0, x)
+    f0 = run_block(net.conv0[1], f0)
     f1 = run_block(net.conv1[1], run_block(net.conv1[0], f0))
     f2 = run_block(net.conv2[1], run_block(net.conv2[0], f1))
     outs = [net.out0(f2)]
@@ -406,7 +418,11 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
     output convolution are all linear, so the 1x1 is folded into the 3x3 (64 -> 3*4 channels instead of 64 -> 256,
     no 256-channel intermediate); ``gdb_assemble_output`` performs the pending shuffle."""
     from . import ops
-    y = dec.in_conv(x)
+    if ops._is_cl(x) or x.is_cuda:
+        y = F.conv2d(x, dec.in_conv.weight, None, 1, dec.in_conv.padding)
+        y = ops.bias_act_add(y, dec.in_conv.bias, None, relu=False) if ops._is_cl(y) and y.shape[1] % 4 == 0 else y + dec.in_conv.bias.view(1, -1, 1, 1)
+    else:
+        y = dec.in_conv(x)
     h = y
     for blk in dec.blocks:
         zb = _cached(blk, "_gdb_zero", (blk.conv1.weight,), lambda: torch.zeros(blk.conv1.weight.shape[0], device=x.device))
