@@ -419,7 +419,11 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
     no 256-channel intermediate); ``gdb_assemble_output`` performs the pending shuffle."""
     from . import ops
     if ops._is_cl(x) or x.is_cuda:
-        y = F.conv2d(x, dec.in_conv.weight, None, 1, dec.in_conv.padding)
+        w_in = dec.in_conv.weight
+        if x.shape[1] > w_in.shape[1]:        # decoder input with zero pad channels (float4-aligned pixels from the render kernel)
+            extra = x.shape[1] - w_in.shape[1]
+            w_in = _cached(dec, f"_gdb_inpad{extra}", (w_in,), lambda: F.pad(dec.in_conv.weight, (0, 0, 0, 0, 0, extra)).contiguous(memory_format=torch.channels_last))
+        y = F.conv2d(x, w_in, None, 1, dec.in_conv.padding)
         y = ops.bias_act_add(y, dec.in_conv.bias, None, relu=False) if ops._is_cl(y) and y.shape[1] % 4 == 0 else y + dec.in_conv.bias.view(1, -1, 1, 1)
     else:
         y = dec.in_conv(x)

@@ -362,7 +362,9 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
     // planar: channel c at of[c * ostr]; channels-last: fine colours in out_feat (R per bundle), the rest in out_dec
     const size_t ostr = p.out_cl ? 1 : (size_t)HW;
     float* of = p.out_cl ? p.out_feat + (size_t)bidx * R : p.out_feat + (size_t)b * CT * HW + pix;
-    float* od = p.out_cl ? p.out_dec + (size_t)bidx * (F + 8) - R : of;
+    float* od = p.out_cl ? p.out_dec + (size_t)bidx * p.dec_stride - R : of;
+    if (writer && p.out_cl)
+      for (int k = F + 8; k < p.dec_stride; ++k) od[R + k] = 0.f;                                // pad channels of the decoder input
     float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     // -- fine colours: project every ray of the bundle into every view, bilinear on the full-res image,
@@ -478,7 +480,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
                                     const float* vol_range, const float* cam, int cam_stride, const float* mlp, int B,
                                     int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int vol_layout, int max_samples,
                                     int max_mip_level, int inv_depth, int adaptive, int precision, int out_channels_last,
-                                    float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
+                                    int dec_stride, float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
                                     const gdb_render_taps* taps, void* stream) {
   GDB_REQUIRE(rgba && tex && vol_cl && depth_range && vol_range && cam && mlp && out_feat && out_depth && out_opacity,
               GDB_E_BADARG, "gdb_render_fused_fwd: null pointer");
@@ -497,6 +499,10 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   RenderParams p{};
   p.rgba = rgba; p.tex = tex; p.vol = vol_cl; p.depth_range = depth_range; p.vol_range = vol_range; p.cam = cam; p.mlp = mlp;
   GDB_REQUIRE(!out_channels_last || out_dec, GDB_E_BADARG, "gdb_render_fused_fwd: channels-last output needs out_dec");
+  const int dec_min = feat_dim + 3 + 8;
+  GDB_REQUIRE(dec_stride == 0 || (dec_stride >= dec_min && dec_stride <= dec_min + 3), GDB_E_BADARG,
+              "gdb_render_fused_fwd: dec_stride %d outside [%d, %d]", dec_stride, dec_min, dec_min + 3);
+  p.dec_stride = dec_stride ? dec_stride : dec_min;
   p.out_feat = out_feat; p.out_dec = out_dec; p.out_depth = out_depth; p.out_opacity = out_opacity; p.out_cl = out_channels_last ? 1 : 0;
   if (taps && (taps->rgbs_feat_dir || taps->vox_feat || taps->sigma || taps->feat || taps->weights)) {
     GDB_REQUIRE(taps->offsets && taps->S_total > 0, GDB_E_BADARG, "gdb_render_fused_fwd: taps need offsets and S_total");

@@ -717,8 +717,10 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             a = k == 0 ? o : a + o;
           }
           if (c < F + 8) {
-            float* odb = p.out_cl ? p.out_dec + (size_t)(b * HW + pixb) * (F + 8) + c : p.out_feat + ((size_t)b * CT + R + c) * HW + pixb;
+            float* odb = p.out_cl ? p.out_dec + (size_t)(b * HW + pixb) * p.dec_stride + c : p.out_feat + ((size_t)b * CT + R + c) * HW + pixb;
             *odb = a;
+            if (p.out_cl && c == F + 7)
+              for (int k = F + 8; k < p.dec_stride; ++k) odb[k - c] = 0.f;                   // pad channels of the decoder input
           } else if (c == F + 8) {
             p.out_depth[(size_t)b * HW + pixb] = p.inv_depth ? fdiv(1.f, a) : a;
           } else {

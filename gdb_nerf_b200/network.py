@@ -275,7 +275,7 @@ class Network(nn.Module):
         vol_cl = feat_volume if fused else ops.to_channels_last(feat_volume, 8)    # fused: already a (B,D,Hb,Wb,8) view
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
                                self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
-                               precision=self.mlp_precision)
+                               precision=self.mlp_precision, pad_dec=fused)
         if fused:
             dec12 = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2))   # NCHW shape over channels-last memory
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], dec12, out['depth'], out['opacity'], b,
