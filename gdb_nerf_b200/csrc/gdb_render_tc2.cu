@@ -290,9 +290,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       for (int k = 0; k < 8; ++k) {
         int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
         float w = ((k & 1) ? tx : 1.f - tx) * ((k & 2) ? ty : 1.f - ty) * ((k & 4) ? tz : 1.f - tz);
-        const float* tp = vb_ + zz * p.vol_sz + yy * p.vol_sy + xx * p.vol_sx;
-        lo = f4_scale_add(lo, ldg4(tp), w);
-        hi = f4_scale_add(hi, ldg4(tp + 4), w);
+        // a bundle centre sits on a voxel centre whenever the cost volume has the bundle map's resolution: the x / y
+        // fractions are then exactly zero for most bundles and six of the eight taps carry weight 0 - not fetched
+        if (w != 0.f) {
+          const float* tp = vb_ + zz * p.vol_sz + yy * p.vol_sy + xx * p.vol_sx;
+          lo = f4_scale_add(lo, ldg4(tp), w);
+          hi = f4_scale_add(hi, ldg4(tp + 4), w);
+        }
       }
       voxh = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
       if (TAPS && p.tap_vox) {

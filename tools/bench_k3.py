@@ -16,6 +16,7 @@ ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--workload", default="dtu")
 ap.add_argument("--lib", default="", help="alternative build of the library (A/B measurements)")
+ap.add_argument("--folded", action="store_true", help="volume in the depth-folded (B,Hb,Wb,D,12) layout of the 2-D cost-regularisation head")
 ap.add_argument("--narrow", action="store_true", help="narrow depth ranges (adaptive counts 1..max) instead of saturated")
 args = ap.parse_args()
 if args.lib:
@@ -42,6 +43,10 @@ mlp = ops.pack_mlp({k: v.detach() for k, v in NeRF(64, fd, 8, True).state_dict()
 cam = ops.camera_block(rig["tar_exts"].to(dev), rig["tar_ints"].to(dev), rig["src_exts"].to(dev), rig["src_ints"].to(dev), rig["near_far"].to(dev), b, cfg.nerf.global_num_depth, False)
 src = ops.prepare_sources(feat, rgb, b, cfg.nerf.max_mipmap_level)
 vol_cl = ops.to_channels_last(vol, 8)
+if args.folded:
+    buf = torch.zeros(B, Hb, Wb, vol_cl.shape[1], 12, device=dev)
+    buf[..., :8] = vol_cl.permute(0, 2, 3, 1, 4)
+    vol_cl = buf[..., :8].permute(0, 3, 1, 2, 4)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for prec in ([0, 1, 2, 3] if args.precision < 0 else [args.precision]):
     ts = []
