@@ -19,9 +19,12 @@
 //  * Fine colours are fetched after the view weights are known with lane = (row, ray): the four rays of a bundle read
 //    neighbouring source pixels, the blend over views and the compositing weight are applied in registers and the
 //    sum over a bundle's samples runs per (bundle, ray) from a small shared-memory stash (no shuffles).
-//  * All biases ride in the GEMMs (a constant-one K slot), the [var|mean] product is not repeated per view, and the
-//    loops over gather iterations / rays are rolled: the kernel is ~4x smaller than the first tcgen05 variant, whose
-//    top stall reason was instruction fetch.
+//  * The biases of global_fc, lr0 and weight.0 ride in the GEMMs (a constant-one K slot fed from a shared constant chunk),
+//    odd chunk counts pair with a shared zero chunk, the per-channel compositing goes through a swizzled shared-memory
+//    transpose (lane = (bundle, channel), coalesced stores), zero-weight voxel taps are skipped, and the loops over
+//    gather iterations / rays / views of the epilogues are rolled: 7.3 k SASS instructions instead of 13.3 k in the first
+//    tcgen05 variant, whose top stall reason was instruction fetch.  The production instantiation (TAPS = false)
+//    carries none of the per-sample parity outputs.
 #include <cuda_fp16.h>
 
 #include "gdb_render_common.cuh"
