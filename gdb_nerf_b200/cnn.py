@@ -168,7 +168,8 @@ def _deconv_skip(block: nn.Sequential, x: torch.Tensor, skip: torch.Tensor) -> t
     return skip + (d + b.view(1, -1, 1, 1, 1)).relu_()
 
 
-def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True,
+                   defer_prob_head: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Same data flow as CostRegNet(Small).forward with folded blocks; x is NCDHW-shaped, channels_last_3d strides.
     Returns (volume, logits): volume is a (B,D,H,W,8) channels-last VIEW of the joint head output (or None when the
     caller does not consume it: the stage-0 feature head only feeds the training-time coarse render), logits a
@@ -187,6 +188,9 @@ def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True) -
         y = _deconv_skip(net.conv8, y, s1)
         y = _deconv_skip(net.conv9, y, s0)
     if not want_volume:
+        # the caller fuses the 1-channel probability head into the depth-range kernel when it can (ops.prob_head_depth_range)
+        if defer_prob_head:
+            return None, y
         return None, F.conv3d(y, net.prob_head.weight, None, 1, 1).squeeze(1)
     # both heads as ONE convolution (identical arithmetic per output channel), padded to 12 output channels so the
     # channels-last voxel stays float4-addressable: channels 0-7 feature volume, 8 probability logits

@@ -390,6 +390,118 @@ __global__ void depth_range_logits_kernel(const float* __restrict__ range, int r
 }
 
 // ---------------------------------------------------------------------------
+// K2 fused with the probability head itself: logits = Conv3d(C -> 1, 3x3x3, padding 1, no bias) of the U-Net's last
+// feature volume (cost_reg_net.py:62-63), then the soft-max over depth and the depth regression as above.
+// y (B,D,H,W,8) channels-last.  A CTA owns a 4 x 32 pixel tile and walks the depth axis with a rolling window of three
+// haloed planes in shared memory (each voxel is read from global once per CTA); the D logits of a pixel are parked in
+// shared memory and reduced by the pixel's own thread with the K2 arithmetic.  Exact fp32 (the cuDNN head this
+// replaces ran a 1-output-channel convolution 20x off the memory roofline).
+// ---------------------------------------------------------------------------
+constexpr int PH_TY = 4, PH_TX = 32, PH_PW = PH_TX + 2, PH_PH = PH_TY + 2, PH_PLANE = 2 * PH_PH * PH_PW;   // float4 per plane
+
+__global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float* __restrict__ y, const float* __restrict__ wgt,
+                                                                    const float* __restrict__ range, int rh, int rw, int B, int D,
+                                                                    int H, int W, float ci_scale, int inv_depth,
+                                                                    float* __restrict__ depth, float* __restrict__ ci,
+                                                                    float* __restrict__ vol_range, float* __restrict__ prob_out) {
+  extern __shared__ __align__(16) unsigned char ph_smem[];
+  float4* plane = reinterpret_cast<float4*>(ph_smem);                  // [3][2 halves][PH_PH][PH_PW]
+  float4* wsm = plane + 3 * PH_PLANE;                                  // [27][2]
+  float* lsm = reinterpret_cast<float*>(wsm + 54);                     // [D][128]
+  const int tid = threadIdx.x, ty = tid / PH_TX, tx = tid % PH_TX;
+  const int b = blockIdx.z, y0 = blockIdx.y * PH_TY, x0 = blockIdx.x * PH_TX;
+  const int HW = H * W;
+  if (tid < 54) wsm[tid] = __ldg(reinterpret_cast<const float4*>(wgt) + tid);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_plane = [&](int d, int slot) {
+    float4* dst = plane + slot * PH_PLANE;
+    for (int i = tid; i < PH_PH * PH_PW; i += 128) {
+      const int py = i / PH_PW, px = i - py * PH_PW;
+      const int gy = y0 + py - 1, gx = x0 + px - 1;
+      float4 a = zero4, c = zero4;
+      if (d >= 0 && d < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const float4* src = reinterpret_cast<const float4*>(y + ((((size_t)b * D + d) * H + gy) * W + gx) * 8);
+        a = __ldg(src);
+        c = __ldg(src + 1);
+      }
+      dst[i] = a;
+      dst[PH_PH * PH_PW + i] = c;
+    }
+  };
+  load_plane(-1, 2);
+  load_plane(0, 0);
+  for (int d = 0; d < D; ++d) {
+    load_plane(d + 1, (d + 1) % 3);                                    // slot (d+1)%3 held plane d-2: no longer read
+    __syncthreads();
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const float4* pl = plane + ((d + kd + 2) % 3) * PH_PLANE;       // plane d - 1 + kd
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int o = (ty + ky) * PH_PW + tx + kx;
+          const float4 a = pl[o], c = pl[PH_PH * PH_PW + o];
+          const float4 wa = wsm[((kd * 3 + ky) * 3 + kx) * 2], wc = wsm[((kd * 3 + ky) * 3 + kx) * 2 + 1];
+          acc0 = fmaf(a.x, wa.x, acc0); acc1 = fmaf(a.y, wa.y, acc1);
+          acc0 = fmaf(a.z, wa.z, acc0); acc1 = fmaf(a.w, wa.w, acc1);
+          acc0 = fmaf(c.x, wc.x, acc0); acc1 = fmaf(c.y, wc.y, acc1);
+          acc0 = fmaf(c.z, wc.z, acc0); acc1 = fmaf(c.w, wc.w, acc1);
+        }
+    }
+    lsm[d * 128 + tid] = acc0 + acc1;
+    __syncthreads();                                                   // plane (d+2)%3 is overwritten next
+  }
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy >= H || gx >= W) return;
+  const int pix = gy * W + gx;
+  const int ry = rh == 1 ? 0 : gy, rx = rw == 1 ? 0 : gx;
+  const float near_ = range[((size_t)(b * 2 + 0) * rh + ry) * rw + rx];
+  const float far_ = range[((size_t)(b * 2 + 1) * rh + ry) * rw + rx];
+  // soft-max over depth in ATen's order, then depth_regression (depth_net.py:479-514): same arithmetic as depth_range_logits_kernel
+  float m = -INFINITY;
+  for (int d = 0; d < D; ++d) m = fmaxf(m, lsm[d * 128 + tid]);
+  float sum = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float e = expf(lsm[d * 128 + tid] - m);
+    lsm[d * 128 + tid] = e;
+    sum += e;
+  }
+  float mean = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float pr = fdiv(lsm[d * 128 + tid], sum);
+    lsm[d * 128 + tid] = pr;
+    mean = fadd(mean, fmul(pr, hypothesis(near_, far_, d, D, inv_depth)));
+  }
+  float var = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float t = fsub(hypothesis(near_, far_, d, D, inv_depth), mean);
+    var = fadd(var, fmul(lsm[d * 128 + tid], fmul(t, t)));
+    if (prob_out) prob_out[((size_t)b * D + d) * HW + pix] = lsm[d * 128 + tid];
+  }
+  const float half = fmul(ci_scale, sqrtf(fmaxf(var, 1e-12f)));
+  const float first = hypothesis(near_, far_, 0, D, inv_depth), last = hypothesis(near_, far_, D - 1, D, inv_depth);
+  float lo, hi, dep;
+  if (inv_depth) {
+    lo = fdiv(1.f, fminf(fadd(mean, half), first));
+    hi = fdiv(1.f, fmaxf(fsub(mean, half), last));
+    dep = fdiv(1.f, mean);
+  } else {
+    lo = fmaxf(fsub(mean, half), first);
+    hi = fminf(fadd(mean, half), last);
+    dep = mean;
+  }
+  depth[(size_t)b * HW + pix] = dep;
+  ci[(size_t)(b * 2 + 0) * HW + pix] = lo;
+  ci[(size_t)(b * 2 + 1) * HW + pix] = hi;
+  if (vol_range) {
+    vol_range[(size_t)(b * 2 + 0) * HW + pix] = first;
+    vol_range[(size_t)(b * 2 + 1) * HW + pix] = last;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // planar -> channels-last
 // ---------------------------------------------------------------------------
 template <int CP>
@@ -500,4 +612,27 @@ extern "C" int gdb_depth_range_from_logits_fwd(const float* depth_range, int rh,
     depth_range_logits_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(depth_range, rh, rw, logits, stride_b, stride_d, stride_pix, B, D, h, w,
                                                                    ci_scale, inv_depth, depth, ci, vol_range, prob_out);
   return cuda_check("gdb_depth_range_from_logits_fwd");
+}
+
+extern "C" int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* weight, const float* depth_range, int rh, int rw, int B,
+                                             int C, int D, int h, int w, float ci_scale, int inv_depth, float* depth, float* ci,
+                                             float* vol_range, float* prob_out, void* stream) {
+  GDB_REQUIRE(y_cl && weight && depth_range && depth && ci && B > 0 && D > 0 && h > 0 && w > 0, GDB_E_BADARG,
+              "gdb_prob_head_depth_range_fwd: bad argument");
+  GDB_REQUIRE(C == 8, GDB_E_UNSUPPORTED, "gdb_prob_head_depth_range_fwd: C=%d not instantiated (8)", C);
+  GDB_REQUIRE((rh == 1 && rw == 1) || (rh == h && rw == w), GDB_E_BADARG,
+              "gdb_prob_head_depth_range_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", h, w, rh, rw);
+  GDB_REQUIRE(aligned16(y_cl) && aligned16(weight), GDB_E_ALIGN, "gdb_prob_head_depth_range_fwd: y / weight must be 16-byte aligned");
+  const int smem = (3 * PH_PLANE + 54) * 16 + D * 128 * 4;
+  GDB_REQUIRE(smem <= 227 * 1024, GDB_E_UNSUPPORTED, "gdb_prob_head_depth_range_fwd: D=%d needs %d B of shared memory", D, smem);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(prob_head_depth_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "gdb_prob_head_depth_range_fwd: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  dim3 grid((w + PH_TX - 1) / PH_TX, (h + PH_TY - 1) / PH_TY, B);
+  prob_head_depth_range_kernel<<<grid, 128, smem, as_stream(stream)>>>(y_cl, weight, depth_range, rh, rw, B, D, h, w, ci_scale, inv_depth,
+                                                                      depth, ci, vol_range, prob_out);
+  return cuda_check("gdb_prob_head_depth_range_fwd");
 }

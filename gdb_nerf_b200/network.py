@@ -113,8 +113,14 @@ class DepthNet(nn.Module):
                 depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])
             elif fused_cnn:
                 # the feature head of every stage but the last only feeds the training-time coarse render
-                volume, logits = cost_reg_fused(self.cost_regs[s], variance, want_volume=(s == self.num_stages - 1))
-                depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])
+                last = s == self.num_stages - 1
+                head = self.cost_regs[s].prob_head
+                fuse_head = (not last) and head.weight.shape[1] == 8 and self.num_depth[s] <= 256
+                volume, logits = cost_reg_fused(self.cost_regs[s], variance, want_volume=last, defer_prob_head=fuse_head)
+                if fuse_head:      # `logits` is the U-Net's last feature volume: 1-channel head + soft-max + regression in one kernel
+                    depth, ci, vol_range, _ = ops.prob_head_depth_range(logits, head.weight, depth_range, self.ci_scales[s], self.inv_depth[s])
+                else:
+                    depth, ci, vol_range, _ = ops.depth_range_from_logits(depth_range, logits, self.ci_scales[s], self.inv_depth[s])
             else:
                 volume, prob = self.cost_regs[s](variance)
                 depth, ci, vol_range = ops.depth_range_from_prob(depth_range, prob, self.ci_scales[s], self.inv_depth[s])

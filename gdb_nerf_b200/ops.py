@@ -156,6 +156,30 @@ def depth_range_from_logits(depth_range: Tensor, logits: Tensor, ci_scale: float
     return depth, ci, vol, prob
 
 
+def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_scale: float, inv_depth: bool,
+                          want_prob: bool = False) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """K2 fused with the probability head: ``y`` is the U-Net's last feature volume, (B,8,D,h,w)-shaped over channels-last
+    (B,D,h,w,8) memory, ``weight`` the head's (1,8,3,3,3) Conv3d weight (padding 1, no bias).
+    -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w), prob (B,D,h,w) or None."""
+    _dev(y, weight, depth_range)
+    if not (_is_cl(y) and y.shape[1] == 8 and tuple(weight.shape) == (1, 8, 3, 3, 3)):
+        raise _lib.GdbError("prob_head_depth_range needs a dense channels-last (B,8,D,h,w) volume and a (1,8,3,3,3) weight")
+    depth_range = _f32(depth_range)
+    B, Cc, D, h, w = y.shape
+    _, _, rh, rw = depth_range.shape
+    wk = _f32(weight)[0].permute(1, 2, 3, 0).contiguous()             # [kd][ky][kx][c]
+    dev = y.device
+    depth = torch.empty((B, 1, h, w), device=dev, dtype=torch.float32)
+    ci = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
+    vol = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
+    prob = torch.empty((B, D, h, w), device=dev, dtype=torch.float32) if want_prob else None
+    lib = _lib.load()
+    _lib.check(lib.gdb_prob_head_depth_range_fwd(y.data_ptr(), wk.data_ptr(), depth_range.data_ptr(), rh, rw, B, Cc, D, h, w,
+                                                 float(ci_scale), int(inv_depth), depth.data_ptr(), ci.data_ptr(), vol.data_ptr(),
+                                                 _p(prob), _stream()), "gdb_prob_head_depth_range_fwd")
+    return depth, ci, vol, prob
+
+
 # -------------------------------------------------------------------- glue --
 def _is_cl(x: Tensor) -> bool:
     """Shape (N, C, *spatial) over channels-last memory (N, *spatial, C), dense."""

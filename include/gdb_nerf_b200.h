@@ -172,6 +172,13 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
                          const gdb_render_taps* taps, void* stream);
 
+/* K2 fused with the probability head it follows (cost_reg_net.py:62-63 -> depth_net.py:172,479-514): logits =
+ * Conv3d(C -> 1, 3x3x3, padding 1, no bias) of y_cl (B,D,h,w,C) channels-last, C = 8, weight (27, C) in [kd][ky][kx][c]
+ * order; then the soft-max over depth and the depth regression of gdb_depth_range_fwd.  prob_out (B,D,h,w) may be null. */
+int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* weight, const float* depth_range, int rh, int rw, int B,
+                                  int C, int D, int h, int w, float ci_scale, int inv_depth, float* depth, float* ci,
+                                  float* vol_range, float* prob_out, void* stream);
+
 /* Output assembly, replaces network.py:175-182 minus the decoder CNN:
  * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
  * and the bilinear xb up-sampling of depth and opacity.

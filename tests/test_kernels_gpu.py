@@ -432,3 +432,30 @@ def test_render_fused_split_precision_tensor_core(golden, prefix):
     R = 3 * b * b
     assert torch.equal(split["fine"].permute(0, 3, 1, 2), sp["feat"][:, :R])
     assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), sp["feat"][:, R:])
+
+
+@pytest.mark.parametrize("D,h,w,inv,per_pixel", [(64, 12, 40, True, False), (36, 9, 33, True, False), (8, 10, 70, False, True)])
+def test_prob_head_fused_into_depth_range(D, h, w, inv, per_pixel):
+    """1-channel probability head (Conv3d 8 -> 1, 3x3x3, padding 1) + soft-max + depth regression in one kernel against the
+    two-step path (true-fp32 cuDNN convolution, then the logits variant of K2), including ragged tiles."""
+    g = torch.Generator().manual_seed(D + h)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B = 2
+        y = (torch.randn(B, 8, D, h, w, generator=g) * 0.7).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+        wt = (torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2).to(DEV)
+        if per_pixel:
+            near = 425.0 + 100.0 * torch.rand(B, 1, h, w, generator=g)
+            rng = torch.cat((near, near + 40.0 + 40.0 * torch.rand(B, 1, h, w, generator=g)), 1).to(DEV)
+        else:
+            rng = torch.tensor([[425.0, 905.0]] * B).view(B, 2, 1, 1).to(DEV)
+        logits = torch.nn.functional.conv3d(y, wt, None, 1, 1).squeeze(1)
+        want = ops.depth_range_from_logits(rng, logits, 1.0, inv, want_prob=True)
+        got = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, want_prob=True)
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert _md(got[3], want[3]) <= 2e-6                               # probabilities
+    for k in range(3):                                                # depth, confidence interval, volume range
+        assert _md(got[k], want[k]) <= 1e-5 * 480.0, k

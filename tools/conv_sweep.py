@@ -16,6 +16,8 @@ def timeit(fn, n=6):
     return min(ts) * 1e3
 
 LAYERS = [  # name, dims, N, cin, cout, spatial, k, stride
+    ("cr0.prob_head", 3, 8, 8, 1, (64, 64, 80), 3, 1),
+    ("cr0.conv6 (deconv out) as conv", 3, 8, 8, 8, (64, 64, 80), 3, 1),
     ("fpn.conv0.0", 2, 24, 3, 8, (512, 640), 3, 1),
     ("fpn.conv0.1", 2, 24, 8, 8, (512, 640), 3, 1),
     ("fpn.conv1.0", 2, 24, 8, 16, (512, 640), 5, 2),
@@ -24,11 +26,12 @@ LAYERS = [  # name, dims, N, cin, cout, spatial, k, stride
     ("cr1.conv1", 3, 8, 8, 16, (8, 256, 320), 3, 2),
     ("cr1.heads", 3, 8, 8, 12, (8, 256, 320), 3, 1),
 ]
-for name, nd, N, cin, cout, sp, k, st in LAYERS:
+import sys
+for name, nd, N, cin, cout, sp, k, st in LAYERS[:int(sys.argv[1]) if len(sys.argv) > 1 else None]:
     conv = F.conv2d if nd == 2 else F.conv3d
     fmt = torch.channels_last if nd == 2 else torch.channels_last_3d
     res = []
-    for ci, co in itertools.product(sorted({cin, (cin + 3) // 4 * 4, (cin + 7) // 8 * 8, (cin + 15) // 16 * 16}), sorted({cout, (cout + 7) // 8 * 8, (cout + 15) // 16 * 16, (cout + 31) // 32 * 32})):
+    for ci, co in itertools.product(sorted({cin, (cin + 3) // 4 * 4, (cin + 7) // 8 * 8, (cin + 15) // 16 * 16}), sorted({cout, (cout + 3) // 4 * 4, (cout + 7) // 8 * 8, (cout + 15) // 16 * 16, (cout + 31) // 32 * 32})):
         for cl in (True, False):
             x = torch.randn(N, ci, *sp, device=dev)
             w = torch.randn(co, ci, *([k] * nd), device=dev) * 0.05
