@@ -417,8 +417,8 @@ class Decoder(nn.Module):
 
 
 def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
-    """Eval-time decoder (decoder_rdn.py:44-82) on channels-last data.  Returns the output BEFORE the last pixel
-    shuffle as (B, H/2, W/2, 12) channels-last: the last up-sampling convolution, the pixel shuffle and the 1x1
+    """Eval-time decoder (decoder_rdn.py:44-82) on channels-last data.  Returns (out, bias): the output BEFORE the last pixel
+    shuffle and WITHOUT its bias as (B, H/2, W/2, 12) channels-last plus that bias (12,), applied by ``gdb_assemble_output``: the last up-sampling convolution, the pixel shuffle and the 1x1
     output convolution are all linear, so the 1x1 is folded into the 3x3 (64 -> 3*4 channels instead of 64 -> 256,
     no 256-channel intermediate); ``gdb_assemble_output`` performs the pending shuffle."""
     from . import ops
@@ -450,8 +450,17 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
             b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
             c = blk.conv3(torch.cat((h, a, b), 1))
             gate = blk.se.fc(c.mean((2, 3)))
-        h = ops.gate_add(h, c, gate) if ops._is_cl(h) and ops._is_cl(c) else h + c * gate[:, :, None, None]
-    y = y + h
+        last = blk is dec.blocks[-1]
+        if ops._is_cl(h) and ops._is_cl(c):
+            # the last block also adds the decoder's global residual y (decoder_rdn.py: y + blocks(y)) in the same pass
+            h = ops.gate_add(h, c, gate, extra=y if last and ops._is_cl(y) else None)
+            if last and not ops._is_cl(y):
+                h = h + y
+        else:
+            h = h + c * gate[:, :, None, None]
+            if last:
+                h = h + y
+    y = h
     mods = list(dec.up)
     if not mods:
         raise ValueError("decoder_fused needs upscale_factor >= 2")
@@ -472,6 +481,6 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
         return w.contiguous(memory_format=torch.channels_last), b.reshape(-1).contiguous()
 
     w, b = _cached(dec, "_gdb_tail", (up.weight, up.bias, oc.weight, oc.bias), make)
-    out = F.conv2d(y, w, b, 1, 1)                                                 # (B,12,h,w) over NHWC memory
-    return out.permute(0, 2, 3, 1).contiguous()
+    out = F.conv2d(y, w, None, 1, 1)                                              # (B,12,h,w) over NHWC memory; bias applied by the consumer
+    return out.permute(0, 2, 3, 1).contiguous(), b
 

@@ -44,14 +44,19 @@ __global__ void bias_act_add_kernel(const float4* __restrict__ x, const float* _
   }
 }
 
-__global__ void gate_add_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float* __restrict__ gate, int C4,
-                                int64_t per_image4, int64_t n4, float4* __restrict__ out) {
+__global__ void gate_add_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float* __restrict__ gate,
+                                const float4* __restrict__ extra, int C4, int64_t per_image4, int64_t n4, float4* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     int c4 = (int)(i % C4);
     int64_t n = i / per_image4;
     float4 g = __ldg(reinterpret_cast<const float4*>(gate) + n * C4 + c4);
     float4 a = x[i], b = y[i];
-    out[i] = make_float4(fmaf(b.x, g.x, a.x), fmaf(b.y, g.y, a.y), fmaf(b.z, g.z, a.z), fmaf(b.w, g.w, a.w));
+    float4 r = make_float4(fmaf(b.x, g.x, a.x), fmaf(b.y, g.y, a.y), fmaf(b.z, g.z, a.z), fmaf(b.w, g.w, a.w));
+    if (extra) {                      // the decoder's global residual (decoder_rdn.py: y + blocks(y)) folded into the last block
+      const float4 e = extra[i];
+      r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+    }
+    out[i] = r;
   }
 }
 
@@ -151,13 +156,15 @@ extern "C" int gdb_bias_act_add(const float* x, const float* bias, const float* 
   return cuda_check("gdb_bias_act_add");
 }
 
-extern "C" int gdb_gate_add(const float* x, const float* y, const float* gate, int64_t N, int64_t S, int C, float* out, void* stream) {
+extern "C" int gdb_gate_add(const float* x, const float* y, const float* gate, const float* extra, int64_t N, int64_t S, int C, float* out,
+                            void* stream) {
   GDB_REQUIRE(x && y && gate && out && N > 0 && S > 0 && C > 0 && C % 4 == 0, GDB_E_BADARG, "gdb_gate_add: bad argument");
-  GDB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gate) && aligned16(out), GDB_E_ALIGN, "gdb_gate_add: pointers must be 16-byte aligned");
+  GDB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gate) && aligned16(out) && (!extra || aligned16(extra)), GDB_E_ALIGN, "gdb_gate_add: pointers must be 16-byte aligned");
   int64_t n4 = N * S * (C / 4);
   int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 16);
   gate_add_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), gate,
-                                                         C / 4, S * (C / 4), n4, reinterpret_cast<float4*>(out));
+                                                         reinterpret_cast<const float4*>(extra), C / 4, S * (C / 4), n4,
+                                                         reinterpret_cast<float4*>(out));
   return cuda_check("gdb_gate_add");
 }
 

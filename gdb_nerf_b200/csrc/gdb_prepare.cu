@@ -121,8 +121,8 @@ __device__ __forceinline__ void up_axis(int o, int n_in, float inv_scale, int& i
 
 __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot, const float* __restrict__ dec,
                                        const float* __restrict__ bdepth, const float* __restrict__ bopac, int B, int Hb,
-                                       int Wb, int BS, int reweighting, int layout, float* __restrict__ rgb,
-                                       float* __restrict__ depth, float* __restrict__ opacity) {
+                                       int Wb, int BS, int reweighting, int layout, const float* __restrict__ dec_bias,
+                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ opacity) {
   const bool feat_cl = layout & 1, dec_cl = layout & 2, dec_ps = layout & 4;
   const int H = Hb * BS, W = Wb * BS;
   const size_t HW = (size_t)H * W, hw = (size_t)Hb * Wb;
@@ -136,8 +136,10 @@ __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot,
       float fine = feat_cl ? feat[((size_t)b * hw + (size_t)yb * Wb + xb) * Ctot + c * BS * BS + j]
                            : feat[((size_t)b * Ctot + c * BS * BS + j) * hw + (size_t)yb * Wb + xb];
       float dv;
-      if (dec_ps)   // (B, H/2, W/2, 12): the decoder's last convolution before its pixel shuffle, channel = c*4 + (y%2)*2 + x%2
-        dv = dec[((size_t)b * (HW / 4) + (size_t)(y >> 1) * (W >> 1) + (x >> 1)) * 12 + c * 4 + (y & 1) * 2 + (x & 1)];
+      if (dec_ps) { // (B, H/2, W/2, 12): the decoder's last convolution before its pixel shuffle, channel = c*4 + (y%2)*2 + x%2
+        const int ch = c * 4 + (y & 1) * 2 + (x & 1);
+        dv = dec[((size_t)b * (HW / 4) + (size_t)(y >> 1) * (W >> 1) + (x >> 1)) * 12 + ch] + (dec_bias ? __ldg(dec_bias + ch) : 0.f);
+      }
       else
         dv = dec_cl ? dec[((size_t)b * HW + (size_t)y * W + x) * 3 + c] : dec[((size_t)b * 3 + c) * HW + (size_t)y * W + x];
       float v = dv + fine;
@@ -196,13 +198,13 @@ extern "C" int gdb_prepare_sources(const float* feat, int feat_channels_last, co
 }
 
 extern "C" int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
-                                   int B, int Hb, int Wb, int bundle_size, int reweighting, int layout, float* rgb,
-                                   float* depth, float* opacity, void* stream) {
+                                   int B, int Hb, int Wb, int bundle_size, int reweighting, int layout, const float* dec_bias,
+                                   float* rgb, float* depth, float* opacity, void* stream) {
   GDB_REQUIRE(feat && dec && bdepth && bopacity && rgb && depth && opacity, GDB_E_BADARG, "gdb_assemble_output: null pointer");
   GDB_REQUIRE(B > 0 && Hb > 0 && Wb > 0 && bundle_size > 0 && Ctot >= 3 * bundle_size * bundle_size, GDB_E_BADARG, "gdb_assemble_output: bad size");
   size_t n = (size_t)B * Hb * Wb * bundle_size * bundle_size;
   int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
   assemble_output_kernel<<<blocks, 256, 0, as_stream(stream)>>>(feat, Ctot, dec, bdepth, bopacity, B, Hb, Wb, bundle_size,
-                                                               reweighting, layout, rgb, depth, opacity);
+                                                               reweighting, layout, (layout & 4) ? dec_bias : nullptr, rgb, depth, opacity);
   return cuda_check("gdb_assemble_output");
 }

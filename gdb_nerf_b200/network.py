@@ -283,9 +283,9 @@ class Network(nn.Module):
                                self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
                                precision=self.mlp_precision, pad_dec=fused)
         if fused:
-            dec12 = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2))   # NCHW shape over channels-last memory
+            dec12, dec_b = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2))   # NCHW shape over channels-last memory
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], dec12, out['depth'], out['opacity'], b,
-                                                                self.reweighting, feat_channels_last=True, dec_pre_shuffle=True)
+                                                                self.reweighting, feat_channels_last=True, dec_pre_shuffle=True, dec_bias=dec_b)
         else:
             rgb_c = self.upsampler(out['feat'][:, 3 * b * b:])
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['feat'], rgb_c, out['depth'], out['opacity'], b, self.reweighting)

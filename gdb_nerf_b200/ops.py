@@ -209,16 +209,18 @@ def bias_act_add(x: Tensor, bias: Optional[Tensor], skip: Optional[Tensor], relu
     return out
 
 
-def gate_add(x: Tensor, y: Tensor, gate: Tensor) -> Tensor:
-    """out = x + y * gate[n, c] (channels-last (N,C,H,W)-shaped x, y; gate (N,C))."""
-    _dev(x, y, gate)
+def gate_add(x: Tensor, y: Tensor, gate: Tensor, extra: Optional[Tensor] = None) -> Tensor:
+    """out = x + y * gate[n, c] (+ extra) (channels-last (N,C,H,W)-shaped x, y, extra; gate (N,C))."""
+    _dev(x, y, gate, extra)
+    if extra is not None and not (_is_cl(extra) and extra.shape == x.shape):
+        raise _lib.GdbError("gate_add: extra must be a dense channels-last fp32 tensor of x's shape")
     N, Cc = x.shape[:2]
     if not (_is_cl(x) and _is_cl(y) and Cc % 4 == 0 and x.shape == y.shape):
         raise _lib.GdbError("gate_add needs dense channels-last fp32 tensors with C % 4 == 0")
     S = x.numel() // (N * Cc)
     out = torch.empty_like(x)
     lib = _lib.load()
-    _lib.check(lib.gdb_gate_add(x.data_ptr(), y.data_ptr(), _f32(gate).data_ptr(), N, S, Cc, out.data_ptr(), _stream()), "gdb_gate_add")
+    _lib.check(lib.gdb_gate_add(x.data_ptr(), y.data_ptr(), _f32(gate).data_ptr(), _p(extra), N, S, Cc, out.data_ptr(), _stream()), "gdb_gate_add")
     return out
 
 
@@ -426,7 +428,7 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
 
 
 def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bundle_size: int, reweighting: bool,
-                    feat_channels_last: bool = False, dec_pre_shuffle: bool = False):
+                    feat_channels_last: bool = False, dec_pre_shuffle: bool = False, dec_bias: Optional[Tensor] = None):
     """rgb = dec + pixel_shuffle(feat[:, :3b^2]) (network.py:175-182).  ``feat`` is (B,CT,Hb,Wb) planar or, with
     ``feat_channels_last``, (B,Hb,Wb,C) holding at least the 3b^2 fine-colour channels; ``dec`` (B,3,H,W) in either
     memory format."""
@@ -437,6 +439,8 @@ def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bu
         if not (dec.dtype == torch.float32 and dec.is_contiguous() and dec.shape[-1] == 12):
             raise ValueError("dec_pre_shuffle needs a contiguous (B,H/2,W/2,12) fp32 tensor")
         layout |= 4
+    if dec_bias is not None and not (layout & 4):
+        raise ValueError("dec_bias is the bias of the pre-shuffle decoder output (dec_pre_shuffle=True)")
     elif dec.dtype == torch.float32 and not dec.is_contiguous() and dec.permute(0, 2, 3, 1).is_contiguous():
         layout |= 2
     else:
@@ -452,6 +456,7 @@ def assemble_output(feat: Tensor, dec: Tensor, bdepth: Tensor, bopac: Tensor, bu
     opac = torch.empty((B, H, W), device=feat.device, dtype=torch.float32)
     lib = _lib.load()
     _lib.check(lib.gdb_assemble_output(feat.data_ptr(), CT, dec.data_ptr(), bdepth.data_ptr(), bopac.data_ptr(), B, Hb, Wb, bundle_size,
-                                       int(reweighting), layout, rgb.data_ptr(), depth.data_ptr(), opac.data_ptr(), _stream()),
+                                       int(reweighting), layout, _p(None if dec_bias is None else _f32(dec_bias)), rgb.data_ptr(), depth.data_ptr(),
+                                       opac.data_ptr(), _stream()),
                "gdb_assemble_output")
     return rgb, depth, opac

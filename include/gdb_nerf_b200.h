@@ -188,7 +188,7 @@ int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* weight, const 
  * composed with its 1x1 output convolution, pixel shuffle (decoder_rdn.py:78-81)
  * still pending: channel c*4 + (y%2)*2 + (x%2).                               */
 int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
-                        int B, int Hb, int Wb, int bundle_size, int reweighting, int layout,
+                        int B, int Hb, int Wb, int bundle_size, int reweighting, int layout, const float* dec_bias /* bias of the composed last convolution (12), layout bit 2 only; may be null */,
                         float* rgb, float* depth, float* opacity, void* stream);
 
 /* --------------------------------------------------------- backward ------- */
@@ -257,9 +257,10 @@ int gdb_coarse_render_bwd(const float* tex, const float* vol_cl, const float* ra
  * and the FPN top-down step feature_net.py:52-58.                             */
 int gdb_bias_act_add(const float* x, const float* bias, const float* skip, int64_t N, int64_t S, int C, int relu,
                      int skip_up2, int Hs, int Ws, float* out, void* stream);
-/* out = x + y * gate[n,c]: squeeze-excite residual of the decoder's dense
+/* out = x + y * gate[n,c] (+ extra): squeeze-excite residual of the decoder's dense
  * blocks (decoder_rdn.py:31-41).  gate (N,C).                                 */
-int gdb_gate_add(const float* x, const float* y, const float* gate, int64_t N, int64_t S, int C, float* out, void* stream);
+int gdb_gate_add(const float* x, const float* y, const float* gate, const float* extra /* optional addend, same shape as x */,
+                 int64_t N, int64_t S, int C, float* out, void* stream);
 /* Channel concatenation of channels-last maps over npix pixels: out (npix, Ca+Cb+Cc) = [a | b | c] (c may be null with
  * Cc = 0): the inputs of the dense block's second and third convolutions (decoder_rdn.py:36-41).                          */
 int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream);

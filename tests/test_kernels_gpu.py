@@ -338,6 +338,7 @@ def test_glue_epilogues_match_torch():
     y = torch.randn(3, 32, 8, 12, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
     gate = torch.rand(3, 32, generator=g).to(DEV)
     assert _md(ops.gate_add(lat, y, gate), lat + y * gate[:, :, None, None]) <= 1e-6
+    assert _md(ops.gate_add(lat, y, gate, extra=y), lat + y * gate[:, :, None, None] + y) <= 1e-6
     with pytest.raises(ops._lib.GdbError):
         ops.bias_act_add(lat.contiguous(), b2, None, relu=False)                                 # planar memory is refused, not converted
     # dense-block concatenation and the squeeze of the squeeze-excite gate (decoder_rdn.py:36-41, modules.py)
@@ -372,6 +373,14 @@ def test_assemble_output_pre_shuffle_decoder(golden):
         if rew:
             want = 0.5 * (want + fine)
         assert _md(rgb, want) <= 1e-6
+        # with the composed convolution's bias applied inside the assembly
+        bias12 = torch.rand(12, generator=torch.Generator().manual_seed(7))
+        rgb_b, _, _ = ops.assemble_output(feat.to(DEV), dec12.to(DEV), bd.to(DEV), bo.to(DEV), b, rew, feat_channels_last=True,
+                                          dec_pre_shuffle=True, dec_bias=bias12.to(DEV))
+        want_b = torch.nn.functional.pixel_shuffle((dec12 + bias12).permute(0, 3, 1, 2), 2) + fine
+        if rew:
+            want_b = 0.5 * (want_b + fine)
+        assert _md(rgb_b, want_b) <= 1e-6
 
 
 def test_render_fused_reads_strided_volume(golden):
