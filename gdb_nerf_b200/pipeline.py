@@ -1,0 +1,157 @@
+"""Input pipeline and sweep driver around ``Network.forward``.
+
+Mirrors the three pieces of the reference a caller of ``run.py evaluate`` touches outside the model:
+
+* ``to_cuda``        - utils/data_utils.py:579-596 (recursive move of the batch dict, ``meta`` left on the host)
+* ``load_network``   - utils/net_utils.py:79-111 (checkpoint file or directory with ``latest.pth`` / ``<epoch>.pth``,
+                       weights under the ``'net'`` key, strict loading)
+* the evaluation loop of run.py:53-66 as ``render_sweep``: target views sharded round-robin over ranks
+  (sharding.shard_views), batches staged through pinned host memory and uploaded on a side stream so the copy of view
+  i+1 overlaps the kernels of view i, results returned on the host.
+
+Nothing here computes: it is host plumbing around the hand-written path.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Callable, Dict, Iterable, Iterator, List, Mapping, Optional, Sequence, Tuple
+
+import torch
+
+from .sharding import shard_views
+
+
+def to_cuda(batch: Any, device: torch.device | str = "cuda:0", non_blocking: bool = False) -> Any:
+    """utils/data_utils.py:579-596: tuples / lists / dicts are walked, tensors moved, ``batch['meta']`` is kept as is."""
+    if isinstance(batch, (tuple, list)):
+        return [to_cuda(b, device, non_blocking) for b in batch]
+    if isinstance(batch, Mapping):
+        return {k: (v if k == "meta" else to_cuda(v, device, non_blocking)) for k, v in batch.items()}
+    if torch.is_tensor(batch):
+        return batch.to(device, non_blocking=non_blocking)
+    return batch
+
+
+def _checkpoint_path(model_dir: str, epoch: int = -1) -> Optional[str]:
+    if not os.path.isdir(model_dir):
+        return model_dir if os.path.exists(model_dir) else None
+    names = os.listdir(model_dir)
+    pths = [int(n.split(".")[0]) for n in names if n.endswith(".pth") and n != "latest.pth" and n.split(".")[0].isdigit()]
+    if not pths and "latest.pth" not in names:
+        return None
+    if epoch == -1:
+        pth = "latest" if "latest.pth" in names else str(max(pths))
+    else:
+        pth = str(epoch)
+    return os.path.join(model_dir, f"{pth}.pth")
+
+
+def load_network(net: torch.nn.Module, model_dir: str, resume: bool = True, epoch: int = -1, strict: bool = True) -> int:
+    """utils/net_utils.py:79-111.  Returns the epoch to resume from (0 when nothing was loaded).  The file is read with
+    ``weights_only=True`` (tensors and plain containers only): a checkpoint is data, not code."""
+    if not resume:
+        return 0
+    path = _checkpoint_path(model_dir, epoch)
+    if path is None:
+        return 0
+    ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    state = ckpt["net"] if isinstance(ckpt, Mapping) and "net" in ckpt else ckpt
+    net.load_state_dict(state, strict=strict)
+    return int(ckpt["epoch"]) + 1 if isinstance(ckpt, Mapping) and "epoch" in ckpt else 0
+
+
+def _record_stream(batch: Any, stream: torch.cuda.Stream) -> None:
+    if isinstance(batch, Mapping):
+        for k, v in batch.items():
+            if k != "meta":
+                _record_stream(v, stream)
+    elif isinstance(batch, (tuple, list)):
+        for v in batch:
+            _record_stream(v, stream)
+    elif torch.is_tensor(batch) and batch.is_cuda:
+        batch.record_stream(stream)
+
+
+class PinnedUploader:
+    """Double-buffered staging of batch dicts: tensors are copied into page-locked host buffers (allocated once per shape)
+    and uploaded with ``non_blocking=True`` on a side stream; ``upload`` returns the device batch and the event that marks
+    its arrival.  Non-tensor entries and ``meta`` pass through."""
+
+    def __init__(self, device: torch.device | str = "cuda:0", slots: int = 2) -> None:
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = slots
+        self._host: List[Dict[str, torch.Tensor]] = [dict() for _ in range(slots)]
+        self._free: List[Optional[torch.cuda.Event]] = [None] * slots
+        self._turn = 0
+
+    def _stage(self, slot: int, key: str, t: torch.Tensor) -> torch.Tensor:
+        buf = self._host[slot].get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._host[slot][key] = buf
+        buf.copy_(t)
+        return buf
+
+    def _walk(self, slot: int, batch: Any, prefix: str) -> Any:
+        if isinstance(batch, Mapping):
+            return {k: (v if k == "meta" else self._walk(slot, v, f"{prefix}{k}.")) for k, v in batch.items()}
+        if isinstance(batch, (tuple, list)):
+            return [self._walk(slot, v, f"{prefix}{i}.") for i, v in enumerate(batch)]
+        if torch.is_tensor(batch):
+            if batch.is_cuda:
+                return batch
+            return self._stage(slot, prefix, batch).to(self.device, non_blocking=True)
+        return batch
+
+    def upload(self, batch: Mapping) -> Tuple[Dict[str, Any], torch.cuda.Event]:
+        slot = self._turn % self.slots
+        self._turn += 1
+        if self._free[slot] is not None:
+            self._free[slot].synchronize()          # the previous upload from this slot's host buffers has completed
+        with torch.cuda.stream(self.stream):
+            dev = self._walk(slot, batch, "")
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._free[slot] = done
+        return dev, done
+
+
+def render_sweep(net: torch.nn.Module, batches: Sequence[Mapping] | Callable[[int], Mapping], n_views: Optional[int] = None,
+                 rank: int = 0, world: int = 1, device: torch.device | str = "cuda:0",
+                 keys: Sequence[str] = ("rgb",)) -> Iterator[Tuple[int, Dict[str, torch.Tensor]]]:
+    """The evaluation loop of run.py:53-66 for this rank's share of a sweep: yields ``(view_index, {key: host tensor})`` in
+    order.  ``batches`` is a sequence of (host) batch dicts or a function ``index -> batch``; view ``i`` goes to rank
+    ``i % world``.  The upload of the next batch overlaps the kernels of the current one; results come back through pinned
+    buffers.  There is no collective: ranks are independent."""
+    n = len(batches) if n_views is None else n_views       # type: ignore[arg-type]
+    get = batches if callable(batches) else (lambda i: batches[i])      # type: ignore[index]
+    mine = shard_views(n, rank, world)
+    if not mine:
+        return
+    up = PinnedUploader(device)
+    compute = torch.cuda.current_stream(torch.device(device))
+    nxt = up.upload(get(mine[0]))
+    out_host: Dict[str, List[torch.Tensor]] = {}
+    for j, idx in enumerate(mine):
+        dev_batch, arrived = nxt
+        if j + 1 < len(mine):
+            nxt = up.upload(get(mine[j + 1]))
+        compute.wait_event(arrived)
+        _record_stream(dev_batch, compute)      # allocated on the upload stream, consumed on the compute stream
+        with torch.no_grad():
+            ret, _, _ = net(dev_batch)
+        res = {}
+        for k in keys:
+            bufs = out_host.setdefault(k, [])
+            slot = j % 2
+            if len(bufs) <= slot or bufs[slot].shape != ret[k].shape:
+                buf = torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory()
+                if len(bufs) <= slot:
+                    bufs.append(buf)
+                else:
+                    bufs[slot] = buf
+            bufs[slot].copy_(ret[k], non_blocking=True)
+            res[k] = bufs[slot]
+        compute.synchronize()
+        yield idx, {k: v.clone() for k, v in res.items()}

@@ -293,3 +293,25 @@ def test_sample_counts_and_ragged_tiles(max_samples, adaptive):
         assert _md(out["feat"], truth["bundle_feat"]) <= (2e-3 if precision == 1 else 1e-4), precision
         assert _md(out["depth"], truth["bundle_depth"]) <= 1e-4 * (w["far"] - w["near"]), precision
         assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
+
+
+def test_render_sweep_matches_direct_forward():
+    """gdb_nerf_b200.pipeline.render_sweep (run.py:53-66 mirror): pinned double-buffered uploads on a side stream, this rank's
+    share of the views, results identical to calling the network on each batch."""
+    from gdb_nerf_b200.pipeline import render_sweep
+    cfg = make_cfg("dtu_eval")
+    torch.manual_seed(0)
+    net = Network(cfg).to(DEV).eval()
+    batches = [make_batch(1, 3, 64, 96, 425.0, 905.0, 180.0, seed=s, images="smooth", tilt=0.03) for s in range(5)]
+    for b in batches:
+        b["meta"] = {"scene": "synthetic"}
+    want = []
+    with torch.no_grad():
+        for b in batches:
+            want.append(net(batch_to(b, DEV))[0]["rgb"].cpu())
+    got = dict(render_sweep(net, batches, device=DEV))
+    assert sorted(got) == [0, 1, 2, 3, 4]
+    for i in range(5):
+        assert _md(got[i]["rgb"], want[i]) <= 1e-5
+    part = dict(render_sweep(net, batches, rank=1, world=2, device=DEV))
+    assert sorted(part) == [1, 3] and _md(part[3]["rgb"], want[3]) <= 1e-5
