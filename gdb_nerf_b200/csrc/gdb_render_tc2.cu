@@ -397,23 +397,6 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
 #pragma unroll
         for (int j = 0; j < 4; ++j) dir[j] = __shfl_sync(full, d_dir[v][j], src);
         const bool act = ok && (pk >> 31);
-#ifdef GDB_TC2_UNCOND
-        const int dy0 = pk & 0x3FFF, dy1 = (pk >> 14) & 0x3FFF;
-        const int dx0 = ((pk >> 28) & 1) * QL, dx1 = ((pk >> 29) & 1) * QL;
-        const int i0 = a0 + gq;
-        float4 f = bilerp4(__ldg(tex4 + i0), __ldg(tex4 + (i0 + dx0)), __ldg(tex4 + (i0 + dy0)), __ldg(tex4 + (i0 + dy0 + dx0)), fu0, fv0);
-        if ((pk >> 30) & 1) {
-          const int i1 = a1 + gq;
-          float4 bq = bilerp4(__ldg(tex4 + i1), __ldg(tex4 + (i1 + dx1)), __ldg(tex4 + (i1 + dy1)), __ldg(tex4 + (i1 + dy1 + dx1)), fu1, fv1);
-          f.x = lerpf(f.x, bq.x, frac); f.y = lerpf(f.y, bq.y, frac); f.z = lerpf(f.z, bq.z, frac); f.w = lerpf(f.w, bq.w, frac);
-        }
-        if (!act) f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (TAPS && p.tap_rfd && act) {
-          float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
-          tp[0] = f.x; tp[1] = f.y; tp[2] = f.z;
-          if (!last_quad) tp[3] = f.w;
-        }
-#else
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
           const int dy0 = pk & 0x3FFF, dy1 = (pk >> 14) & 0x3FFF;
@@ -431,7 +414,6 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             if (!last_quad) tp[3] = f.w;
           }
         }
-#endif
         // view_fc + residual, my four channels
         float fe[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
@@ -853,10 +835,7 @@ static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
 
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
   if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4>(p, st);
-#ifndef GDB_TC2_NG
-#define GDB_TC2_NG 4
-#endif
-  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, GDB_TC2_NG>(p, st);
+  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4>(p, st);
   if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2>(p, st);
   if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2>(p, st);
   if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2>(p, st);
