@@ -315,3 +315,25 @@ def test_render_sweep_matches_direct_forward():
         assert _md(got[i]["rgb"], want[i]) <= 1e-5
     part = dict(render_sweep(net, batches, rank=1, world=2, device=DEV))
     assert sorted(part) == [1, 3] and _md(part[3]["rgb"], want[3]) <= 1e-5
+
+
+@pytest.mark.parametrize("recipe,hw", [("dtu_eval", (64, 96)), ("nerf_eval_4x4", (128, 160))])
+def test_depth_folded_cost_regularisation_matches_3d(recipe, hw):
+    """Stage-1 U-Net run depth-folded on 2-D convolutions (K1 layout 2, block-Toeplitz weights, K3 vol_layout 1) against the same
+    network on cuDNN's 3-D convolutions: same products, only the summation order differs (true-fp32 convolutions here)."""
+    cfg = make_cfg(recipe)
+    torch.manual_seed(0)
+    net = Network(cfg).to(DEV).eval()
+    H, W = hw
+    batch = batch_to(make_batch(2, 3, H, W, 425.0, 905.0, 180.0 * H / 64, seed=4, images="smooth", tilt=0.03), DEV)
+    outs = []
+    with torch.no_grad():
+        for fold in (True, False):
+            net.depth_net.fold_depth = fold
+            ret, mvs, _ = net(batch)
+            outs.append((ret, mvs))
+    (a, ma), (b_, mb) = outs
+    assert _md(a["rgb"], b_["rgb"]) <= 2e-5
+    assert _md(a["nerf_depth"], b_["nerf_depth"]) <= 2e-5 * 480.0
+    for x, y in zip(ma, mb):
+        assert _md(x, y) <= 2e-5 * 480.0
