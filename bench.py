@@ -458,8 +458,10 @@ def run_train(args):
     if world > 1:
         net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)            # as trainer.py:16
     net.train()
+    import copy
+    net_g = None if args.no_graph else copy.deepcopy(net)                  # captured as a CUDA graph below; never run eagerly
     params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=5e-4)
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=True)
     crop, B, V = 64, 1, 3
     batch = batch_to(make_batch(B, V, crop, crop, 425.0, 905.0, 1446.0 * crop / 512.0, seed=100 + rank, images="smooth", tilt=0.03), dev)
     stream = torch.cuda.current_stream()
@@ -477,6 +479,36 @@ def run_train(args):
     for _ in range(max(args.warmup, 3)):
         loss, nbytes = step()
     torch.cuda.synchronize()
+    # eager launches (reported next to the headline) on a copy of the model: the AccumulateGrad nodes of the captured model
+    # must be created on the capture stream, so the model that is captured never runs eagerly on the default stream
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(args.steps):
+        loss, nbytes = step()
+    e0.record(stream)
+    torch.cuda.synchronize()
+    ms_eager = s0.elapsed_time(e0) / args.steps
+    graphed = None
+    if net_g is not None:
+        try:
+            from gdb_nerf_b200.graphed import GraphedTrainStep
+            params_g = [p for p in net_g.parameters() if p.requires_grad]
+            opt_g = torch.optim.Adam(params_g, lr=5e-4, capturable=True)
+            graphed = GraphedTrainStep(net_g, opt_g, batch, lambda out: out[0]["rgb"].square().mean() + sum(b.square().mean() for b in out[2]),
+                                       params_g, clip_value=40.0, allreduce=allreduce_gradients)
+
+            def step():                                                    # noqa: F811
+                return graphed(batch), nbytes
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        except Exception:                                                  # capture is an optimisation, never a requirement
+            import traceback
+            sys.stderr.write("[bench] CUDA-graph capture of the training step failed, timing eager launches:\n" + traceback.format_exc()[-1500:] + "\n")
+            graphed = None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -496,7 +528,9 @@ def run_train(args):
         print(json.dumps({
             "metric": "training step (fwd+bwd+allreduce+Adam), DTU pretrain, 64x64 crop = 1024 bundles per GPU", "value": world * B * crop * crop / (ms_step * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "loss": float(loss),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "loss": float(loss.detach()),
+            "step_execution": "whole step (forward, loss, backward, all-reduce, clip, Adam) replayed as one CUDA graph" if graphed is not None
+                              else "eager launches", "eager_ms_per_step": ms_eager,
             "config": {"workload": "dtu_pretrain training step, 3 source views, fixed 6 samples/bundle, 1 crop of 64x64 px per GPU "
                                    "(BASELINE.json configs[4])", "allreduce_bytes": nbytes,
                        "parallelism": f"data parallel over {world} GPU(s): one flat-bucket NCCL all-reduce of the gradients per step, SyncBN"},
@@ -514,6 +548,7 @@ def main():
     ap.add_argument("--workload", choices=["dtu", "llff", "nerf"], default="dtu")
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: time eager launches only")
     ap.add_argument("--mode", choices=["eval", "train"], default="eval", help="train: BASELINE.json configs[4] (not the headline)")
     args = ap.parse_args()
     if args.mode == "train":

@@ -81,3 +81,56 @@ class GraphedForward:
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self._out
+
+
+class GraphedTrainStep:
+    """One whole training step - forward, loss, backward, gradient all-reduce, value clipping, optimiser update
+    (train/trainers/trainer.py:44-66) - captured once and replayed as a CUDA graph.  At the reference's training size
+    (a 64x64 crop: 1024 bundles, ~1 000 small kernels) the step is bound by host launch overhead, not by the GPU; the
+    replay removes it.  Requirements: static batch geometry, an optimiser constructed with ``capturable=True``, no host
+    synchronisation in the step (the forward / backward kernel pairs of this package have none), and a model that has not
+    run a backward pass on the default stream before (autograd creates each parameter's AccumulateGrad node on the stream of
+    its first backward; the capture needs them on its own stream - construct the stepper first, it warms up by itself).
+
+        stepper = GraphedTrainStep(net, opt, example_batch, loss_fn, params)
+        loss = stepper(batch)          # device scalar, overwritten by the next call
+    """
+
+    def __init__(self, net: torch.nn.Module, opt: torch.optim.Optimizer, example_batch: Mapping, loss_fn, params,
+                 clip_value: float = 40.0, allreduce=None, warmup: int = 3) -> None:
+        if not net.training:
+            raise ValueError("GraphedTrainStep captures the training step; call net.train() first")
+        flat = {k: v for k, v in _flatten(example_batch).items() if torch.is_tensor(v) and v.is_cuda}
+        self._static_in = {k: v.clone() for k, v in flat.items()}
+        self._batch = _rebuild(example_batch, {**_flatten(example_batch), **self._static_in})
+        self.params = list(params)
+
+        def one_step():
+            out = net(self._batch)
+            loss = loss_fn(out)
+            loss.backward()
+            if allreduce is not None:
+                allreduce(self.params)
+            torch.nn.utils.clip_grad_value_(self.params, clip_value)          # trainer.py:64
+            opt.step()
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                opt.zero_grad(set_to_none=True)
+                one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self._loss = one_step()
+
+    def __call__(self, batch: Mapping) -> torch.Tensor:
+        flat = _flatten(batch)
+        for k, dst in self._static_in.items():
+            dst.copy_(flat[k], non_blocking=True)
+        self.graph.replay()
+        return self._loss

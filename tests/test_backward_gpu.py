@@ -274,3 +274,38 @@ def test_coarse_render_forward_and_backward(inv_depth, V):
     scale = max(float(p.grad.abs().max()) for p in ref_p.values())
     for k, p in nd.named_parameters():
         assert _rel(p.grad, ref_p[k].grad, floor=1e-3 * scale) <= RTOL, k
+
+
+def test_training_step_as_cuda_graph_matches_eager():
+    """The whole training step (forward, loss, backward, clip, Adam; trainer.py:44-66) captured as one CUDA graph reproduces the
+    eager step from the same state on new batches (atomics in the weight-gradient accumulation: agreement to fp32 noise)."""
+    import copy
+    from gdb_nerf_b200.config import make_cfg
+    from gdb_nerf_b200.graphed import GraphedTrainStep
+    from gdb_nerf_b200.network import Network
+    from gdb_nerf_b200.synthetic import batch_to, make_batch
+    cfg = make_cfg("dtu_pretrain")
+    torch.manual_seed(0)
+    net_a = Network(cfg).to("cuda").train()
+    net_b = copy.deepcopy(net_a)
+    loss_fn = lambda out: out[0]["rgb"].square().mean() + sum(b.square().mean() for b in out[2])
+    mk = lambda s: batch_to(make_batch(1, 3, 64, 64, 425.0, 905.0, 1446.0 * 64 / 512.0, seed=s, images="smooth", tilt=0.03), "cuda")
+    pa = [p for p in net_a.parameters() if p.requires_grad]
+    pb = [p for p in net_b.parameters() if p.requires_grad]
+    opt_a = torch.optim.Adam(pa, lr=5e-4)
+    opt_b = torch.optim.Adam(pb, lr=5e-4, capturable=True)
+
+    def eager(batch):
+        opt_a.zero_grad(set_to_none=True)
+        loss = loss_fn(net_a(batch))
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(pa, 40)
+        opt_a.step()
+        return float(loss.detach())
+
+    for _ in range(3):                 # the stepper's three warm-up steps on its example batch (capturing executes nothing)
+        eager(mk(0))
+    stepper = GraphedTrainStep(net_b, opt_b, mk(0), loss_fn, pb)
+    for s in (1, 2):
+        la, lb = eager(mk(s)), float(stepper(mk(s)))
+        assert abs(la - lb) <= 2e-3 * abs(la), (s, la, lb)
