@@ -459,7 +459,10 @@ def run_train(args):
         net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)            # as trainer.py:16
     net.train()
     import copy
-    net_g = None if args.no_graph else copy.deepcopy(net)                  # captured as a CUDA graph below; never run eagerly
+    # single GPU: the step is also captured as a CUDA graph (never run eagerly).  With more ranks the capture would have to
+    # include the NCCL all-reduce and SyncBN's collectives on every rank in lock-step; a 2-GPU attempt hung, so multi-GPU
+    # training steps are timed with eager launches
+    net_g = None if (args.no_graph or world > 1) else copy.deepcopy(net)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=5e-4, capturable=True)
     crop, B, V = 64, 1, 3
