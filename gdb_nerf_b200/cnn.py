@@ -228,12 +228,18 @@ def feature_net_fused(net: "FeatureNet", x: torch.Tensor, levels: int = 3) -> Li
     return outs
 
 
-def _deconv_skip(block: nn.Sequential, x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
-    """skip + relu(bn(deconv(x))) (cost_reg_net.py:108-110): library transposed convolution, one fused epilogue."""
+def _deconv_skip(block: nn.Sequential, x: torch.Tensor, skip: torch.Tensor, wfold: int = 0) -> torch.Tensor:
+    """skip + relu(bn(deconv(x))) (cost_reg_net.py:108-110): library transposed convolution, one fused epilogue.  With
+    ``wfold`` = f the input arrives in the f-fold width view and skip / result are in the 2f-fold view."""
     from . import ops
     conv = block[0]
     w, b = _folded(block)
-    d = F.conv_transpose3d(x, w, None, conv.stride, conv.padding, conv.output_padding)
+    if wfold:
+        w, b = _cached(block, f"_gdb_wfoldT{wfold}", (w, b), lambda: (
+            fold_width_weight_transposed(w, wfold)[0].contiguous(memory_format=torch.channels_last_3d), b.repeat(2 * wfold).contiguous()))
+        d = F.conv_transpose3d(x, w, None, tuple(conv.stride[:-1]) + (1,), conv.padding, tuple(conv.output_padding[:-1]) + (0,))
+    else:
+        d = F.conv_transpose3d(x, w, None, conv.stride, conv.padding, conv.output_padding)
     if ops._is_cl(d) and ops._is_cl(skip) and d.shape[1] % 4 == 0:
         return ops.bias_act_add(d, b, skip, relu=True)
     return skip + (d + b.view(1, -1, 1, 1, 1)).relu_()
@@ -251,21 +257,24 @@ def cost_reg_fused(net: "_CostReg", x: torch.Tensor, want_volume: bool = True,
         s0 = r(net.conv0, _wview(x, 4), wfold=4)                       # 8 ch x 4 px
         s1 = r(net.conv2, r(net.conv1, s0, wfold=4), wfold=2)          # 16 ch x 2 px
         t3 = r(net.conv3, s1, wfold=2)                                 # 32 ch
-        s0, s1 = _wview(s0, 0.25), _wview(s1, 0.5)
+        f1, f2 = 1, 2     # the two finest up-sampling layers stay in the folded views (16 ch x 2 px, 8 ch x 4 px)
     else:
         s0 = r(net.conv0, x)
         s1 = r(net.conv2, r(net.conv1, s0))
         t3 = r(net.conv3, s1)
+        f1 = f2 = 0
     if isinstance(net, CostRegNetSmall):
         y = r(net.conv4, t3)
-        y = _deconv_skip(net.conv5, y, s1)
-        y = _deconv_skip(net.conv6, y, s0)
+        y = _deconv_skip(net.conv5, y, s1, f1)
+        y = _deconv_skip(net.conv6, y, s0, f2)
     else:
         s2 = r(net.conv4, t3)
         y = r(net.conv6, r(net.conv5, s2))
         y = _deconv_skip(net.conv7, y, s2)
-        y = _deconv_skip(net.conv8, y, s1)
-        y = _deconv_skip(net.conv9, y, s0)
+        y = _deconv_skip(net.conv8, y, s1, f1)
+        y = _deconv_skip(net.conv9, y, s0, f2)
+    if f2:
+        y = _wview(y, 0.25)
     if not want_volume:
         # the caller fuses the 1-channel probability head into the depth-range kernel when it can (ops.prob_head_depth_range)
         if defer_prob_head:
