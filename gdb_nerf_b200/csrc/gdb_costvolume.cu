@@ -1,6 +1,7 @@
 // Cost-volume side of the path: homography matrices, depth hypotheses,
 // fused homography-warp + variance (K1) and depth regression (K2).
 // Reference: networks/gdb_nerf/depth_net.py:399-514.
+#include <stdlib.h>
 #include "gdb_common.cuh"
 
 namespace gdb {
@@ -258,6 +259,129 @@ warp_variance_kernel(const float* __restrict__ feat, const float* __restrict__ p
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1, second generation (channels-last outputs): thread = (target pixel, 8-channel slice).  ncu showed the 4-channel
+// kernel issue-bound (360 warp instructions per depth plane for 12 taps, 80 % issue utilisation, L1 at 53-67 %): the
+// per-tap work that does not depend on the channel (projection, clamps, weights, addresses) was repeated by C/4 lanes.
+// Here C/8 lanes share a pixel, every tap is ONE 256-bit load (LDG.E.ENL2.256: the lanes of a pixel still cover whole
+// 128-byte lines, so the L1 wavefront count per tap is unchanged), the bilinear blend and the variance run as packed
+// FFMA2 / FADD2 / FMUL2 on the four 64-bit pairs the load delivers, and the result leaves as one 256-bit store.  The
+// (pixel, view) projections of a lane group are spread over its lanes (lane q projects views q, q + LPP, ..) and
+// broadcast by shuffles.  Same operation order per channel as the first kernel: bit-identical results.
+// ---------------------------------------------------------------------------
+typedef unsigned long long u64;
+struct U4 { u64 a, b, c, d; };
+__device__ __forceinline__ U4 ldg256(const float* p) {
+  U4 r;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stcs256(float* p, const U4& r) {
+  asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(r.a), "l"(r.b), "l"(r.c), "l"(r.d) : "memory");
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ U4 u4_mul(const U4& v, u64 w) { return U4{mul2(v.a, w), mul2(v.b, w), mul2(v.c, w), mul2(v.d, w)}; }
+__device__ __forceinline__ U4 u4_fma(const U4& v, u64 w, const U4& acc) { return U4{fma2(v.a, w, acc.a), fma2(v.b, w, acc.b), fma2(v.c, w, acc.c), fma2(v.d, w, acc.d)}; }
+__device__ __forceinline__ U4 u4_add(const U4& x, const U4& y) { return U4{add2(x.a, y.a), add2(x.b, y.b), add2(x.c, y.c), add2(x.d, y.d)}; }
+__device__ __forceinline__ U4 u4_sub(const U4& x, const U4& y) { return U4{sub2(x.a, y.a), sub2(x.b, y.b), sub2(x.c, y.c), sub2(x.d, y.d)}; }
+__device__ __forceinline__ U4 u4_sqacc(const U4& x, const U4& acc) { return U4{fma2(x.a, x.a, acc.a), fma2(x.b, x.b, acc.b), fma2(x.c, x.c, acc.c), fma2(x.d, x.d, acc.d)}; }
+
+template <int C, int V, int OUT_CL>      // 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
+__global__ void __launch_bounds__(256)
+warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
+                      int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
+                      float* __restrict__ out) {
+  constexpr int LPP = C / 8;                   // lanes per pixel
+  constexpr int PIX = 256 / LPP;               // pixels per CTA
+  constexpr int VPL = (V + LPP - 1) / LPP;     // projections per lane
+  __shared__ float sproj[V * 12];
+
+  const int b = blockIdx.z;
+  const int HW = Ht * Wt;
+  const int q = threadIdx.x % LPP;
+  const int pix = blockIdx.x * PIX + threadIdx.x / LPP;
+  const bool live = pix < HW;
+  const int px = live ? pix % Wt : 0, py = live ? pix / Wt : 0;
+  const int group_base = (threadIdx.x & 31) - q;
+
+  if (threadIdx.x < V * 12) sproj[threadIdx.x] = proj[(size_t)b * V * 12 + threadIdx.x];
+  __syncthreads();
+
+  const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+  float rx[VPL], ry[VPL], rz[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float* P = sproj + min(q + k * LPP, V - 1) * 12;
+    rx[k] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
+    ry[k] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
+    rz[k] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
+  }
+  const int ryi = rh == 1 ? 0 : py, rxi = rw == 1 ? 0 : px;
+  const float near_ = range[((size_t)(b * 2 + 0) * rh + ryi) * rw + rxi];
+  const float far_ = range[((size_t)(b * 2 + 1) * rh + ryi) * rw + rxi];
+  const size_t view_stride = (size_t)Hs * Ws * C;
+  const float* fbase = feat + (size_t)b * V * view_stride + q * 8;
+
+  const int d0 = blockIdx.y * DCH;
+  const int d1 = min(d0 + DCH, D);
+  for (int d = d0; d < d1; ++d) {
+    const float dv = hypothesis(near_, far_, d, D, inv_depth);
+    const float depth = inv_depth ? fdiv(1.f, dv) : dv;
+    WarpTap mine[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) mine[k] = warp_tap(sproj + min(q + k * LPP, V - 1) * 12, rx[k], ry[k], rz[k], depth, Ws, Hs);
+    U4 val[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int src = group_base + v % LPP;
+      const WarpTap m = mine[v / LPP];
+      WarpTap t;
+      if (LPP > 1) {
+        t.xx = __shfl_sync(0xffffffffu, m.xx, src);
+        t.yy = __shfl_sync(0xffffffffu, m.yy, src);
+        t.wx0 = __shfl_sync(0xffffffffu, m.wx0, src);
+        t.wx1 = __shfl_sync(0xffffffffu, m.wx1, src);
+        t.wy0 = __shfl_sync(0xffffffffu, m.wy0, src);
+        t.wy1 = __shfl_sync(0xffffffffu, m.wy1, src);
+      } else {
+        t = m;
+      }
+      const int r0 = (t.yy & 0xffff) * Ws, r1 = (t.yy >> 16) * Ws;
+      const int c0 = t.xx & 0xffff, c1 = t.xx >> 16;
+      const float* vb = fbase + v * view_stride;
+      // dead pixels of the last tile read pixel (0, 0)'s taps: in bounds, never stored
+      const U4 t00 = ldg256(vb + (size_t)(r0 + c0) * C), t10 = ldg256(vb + (size_t)(r0 + c1) * C);
+      const U4 t01 = ldg256(vb + (size_t)(r1 + c0) * C), t11 = ldg256(vb + (size_t)(r1 + c1) * C);
+      const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+      U4 acc = u4_mul(t00, pack2(w00, w00));
+      acc = u4_fma(t10, pack2(w10, w10), acc);
+      acc = u4_fma(t01, pack2(w01, w01), acc);
+      acc = u4_fma(t11, pack2(w11, w11), acc);
+      val[v] = acc;
+    }
+    U4 mean = val[0];                       // 0 + val[0] is exact: same sum order as the first kernel
+#pragma unroll
+    for (int v = 1; v < V; ++v) mean = u4_add(mean, val[v]);
+    const float invV = 1.f / (float)V;
+    const u64 iv = pack2(invV, invV);
+    mean = u4_mul(mean, iv);
+    U4 var{0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int v = 0; v < V; ++v) var = u4_sqacc(u4_sub(val[v], mean), var);
+    var = u4_mul(var, iv);
+    if (live)
+      stcs256(out + (OUT_CL == 2 ? (((size_t)b * HW + pix) * D + d) : (((size_t)b * D + d) * HW + pix)) * C + q * 8, var);
+  }
+}
+
+// GDB_K1_V1=1 keeps the first-generation kernel (A/B measurements, tools/bench_k1.py)
+static bool warp_variance_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GDB_K1_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 template <int C, int V>
 static int launch_warp_variance(const float* feat, const float* proj, const float* range, int rh, int rw, int B, int Hs,
                                 int Ws, int D, int Ht, int Wt, int inv_depth, int out_cl, float* out, cudaStream_t st) {
@@ -266,6 +390,18 @@ static int launch_warp_variance(const float* feat, const float* proj, const floa
   // depth chunk: enough CTAs for >= 4 waves of 148 SMs x 4 resident CTAs, but keep planes together for L1 reuse
   int DCH = D;
   while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
+  if (out_cl && C % 8 == 0 && (reinterpret_cast<uintptr_t>(feat) & 31u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0 && !warp_variance_v1()) {
+    constexpr int PIX8 = 256 / (C / 8);
+    tiles = (Ht * Wt + PIX8 - 1) / PIX8;
+    DCH = D;
+    while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
+    dim3 grid8(tiles, (D + DCH - 1) / DCH, B);
+    if (out_cl == 2)
+      warp_variance8_kernel<C, V, 2><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+    else
+      warp_variance8_kernel<C, V, 1><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+    return cuda_check("gdb_warp_variance_fwd");
+  }
   dim3 grid(tiles, (D + DCH - 1) / DCH, B);
   if (out_cl == 2)
     warp_variance_kernel<C, V, 2><<<grid, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
