@@ -337,3 +337,48 @@ def test_depth_folded_cost_regularisation_matches_3d(recipe, hw):
     assert _md(a["nerf_depth"], b_["nerf_depth"]) <= 2e-5 * 480.0
     for x, y in zip(ma, mb):
         assert _md(x, y) <= 2e-5 * 480.0
+
+
+@pytest.mark.parametrize("hw", [(24, 40), (32, 48), (20, 36), (64, 64)])
+def test_width_folded_fpn_matches_modules(hw):
+    """feature_net_fused (BN folded, width-folded 8/16-channel layers when W % 4 == 0, plain layers otherwise) equals the
+    plain module sequence of feature_net.py:40-64 in fp32."""
+    from gdb_nerf_b200.cnn import FeatureNet, feature_net_fused
+    torch.manual_seed(5)
+    net = FeatureNet().to(DEV).eval()
+    for m in net.modules():                                       # non-trivial batch-norm statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    x = torch.rand(3, 3, *hw, device=DEV)
+    with torch.no_grad():
+        want = net(x, levels=2)
+        got = feature_net_fused(net, x, levels=2)
+    assert len(got) == len(want) == 2
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert _md(a, b) <= 2e-5 * max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("small,dhw", [(True, (8, 8, 12)), (True, (16, 8, 16)), (True, (8, 12, 4)), (False, (8, 8, 16)),
+                                       (False, (16, 8, 8)), (False, (8, 16, 24))])
+def test_width_folded_cost_regularisation_matches_modules(small, dhw):
+    """cost_reg_fused (width-folded levels when W % 4 == 0) equals CostRegNet(Small).forward (cost_reg_net.py:40-117): feature
+    volume and the probability head before its soft-max."""
+    from gdb_nerf_b200.cnn import CostRegNet, CostRegNetSmall, cost_reg_fused
+    torch.manual_seed(6)
+    net = (CostRegNetSmall if small else CostRegNet)(32, 8, 8).to(DEV).eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    x = torch.randn(2, 32, *dhw, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    with torch.no_grad():
+        feat, prob = net(x)
+        vol, logits = cost_reg_fused(net, x, want_volume=True)
+    assert _md(vol.permute(0, 4, 1, 2, 3), feat) <= 2e-5 * max(1.0, float(feat.abs().max()))
+    assert _md(torch.softmax(logits, 1), prob) <= 2e-5
