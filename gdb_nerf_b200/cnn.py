@@ -580,7 +580,7 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
             z = torch.cudnn_convolution(h, wh, (1, 1), (1, 1), (1, 1), 1, False, False, torch.backends.cudnn.allow_tf32)
             b = torch.cudnn_convolution_add_relu(a, wa, z, 1.0, zb, (1, 1), (1, 1), (1, 1), 1)
             c = blk.conv3(ops.concat_channels(h, a, b))
-            gate = blk.se.fc(ops.channel_mean(c) if ops._is_cl(c) else c.mean((2, 3)))
+            gate = None if ops._is_cl(c) else blk.se.fc(c.mean((2, 3)))
         else:
             b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
             c = blk.conv3(torch.cat((h, a, b), 1))
@@ -588,7 +588,11 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
         last = blk is dec.blocks[-1]
         if ops._is_cl(h) and ops._is_cl(c):
             # the last block also adds the decoder's global residual y (decoder_rdn.py: y + blocks(y)) in the same pass
-            h = ops.gate_add(h, c, gate, extra=y if last and ops._is_cl(y) else None)
+            extra = y if last and ops._is_cl(y) else None
+            if gate is None:      # squeeze-excite gate finished in the prologue of the residual kernel
+                h = ops.se_gate_add(h, c, blk.se.fc[0].weight, blk.se.fc[2].weight, extra=extra)
+            else:
+                h = ops.gate_add(h, c, gate, extra=extra)
             if last and not ops._is_cl(y):
                 h = h + y
         else:

@@ -168,6 +168,71 @@ extern "C" int gdb_gate_add(const float* x, const float* y, const float* gate, c
   return cuda_check("gdb_gate_add");
 }
 
+// Squeeze-excite gate computed in the prologue of the gated residual: every CTA of image n reduces the channel-sum partials
+// (fixed order), runs the two tiny fully-connected layers (C -> R -> C, ReLU / sigmoid, modules.py:5-20) into shared memory and
+// then streams out = x + y * gate (+ extra).  Replaces five launch-bound kernels (finish, 2 GEMV, clamp, sigmoid) per block.
+__global__ void __launch_bounds__(256) se_gate_add_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
+                                                          const float* __restrict__ partial, int chunks, float inv_S,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2, int R,
+                                                          const float4* __restrict__ extra, int C, int64_t per_image4,
+                                                          float4* __restrict__ out) {
+  extern __shared__ float se_sm[];            // mean[C] | hid[R] | gate[C]
+  float* mean = se_sm;
+  float* hid = se_sm + C;
+  float* gate = hid + ((R + 3) & ~3);
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partial[((int64_t)n * chunks + k) * C + c];
+    mean[c] = s * inv_S;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], mean[c], s);
+    hid[r] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
+    gate[c] = 1.f / (1.f + expf(-s));
+  }
+  __syncthreads();
+  const int C4 = C / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(gate);
+  const int64_t base = (int64_t)n * per_image4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_image4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = g4[(int)(i % C4)];
+    const float4 a = x[base + i], b = y[base + i];
+    float4 r = make_float4(fmaf(b.x, g.x, a.x), fmaf(b.y, g.y, a.y), fmaf(b.z, g.z, a.z), fmaf(b.w, g.w, a.w));
+    if (extra) {
+      const float4 e = extra[base + i];
+      r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+    }
+    out[base + i] = r;
+  }
+}
+
+extern "C" int gdb_se_gate_add(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
+                               int64_t S, int C, int chunks, float* partial, float* out, void* stream) {
+  GDB_REQUIRE(x && y && w1 && w2 && partial && out && N > 0 && S > 0 && chunks > 0 && R > 0 && R <= 256, GDB_E_BADARG, "gdb_se_gate_add: bad argument");
+  GDB_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, GDB_E_BADARG, "gdb_se_gate_add: C must be a multiple of 4 in [4, 1024]");
+  GDB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(out) && aligned16(partial) && (!extra || aligned16(extra)), GDB_E_ALIGN,
+              "gdb_se_gate_add: pointers must be 16-byte aligned");
+  dim3 grid1(chunks, (unsigned)N);
+  channel_sum_kernel<<<grid1, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(y), C / 4, S, chunks, reinterpret_cast<float4*>(partial));
+  const int64_t per4 = S * (C / 4);
+  int bx = (int)std::min<int64_t>((per4 + 255) / 256, std::max<int64_t>(1, (int64_t)sm_count() * 16 / N));
+  dim3 grid2(bx, (unsigned)N);
+  const int smem = (2 * C + ((R + 3) & ~3)) * (int)sizeof(float);
+  // hid is padded to a multiple of 4 floats so that gate stays float4-aligned
+  se_gate_add_kernel<<<grid2, 256, smem, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), partial,
+                                                               chunks, 1.f / (float)S, w1, w2, R, reinterpret_cast<const float4*>(extra), C,
+                                                               per4, reinterpret_cast<float4*>(out));
+  return cuda_check("gdb_se_gate_add");
+}
+
 extern "C" int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream) {
   GDB_REQUIRE(a && b && out && npix > 0 && Ca > 0 && Cb > 0 && Cc >= 0 && (Cc == 0 || c), GDB_E_BADARG, "gdb_concat3: bad argument");
   GDB_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && Cc % 4 == 0, GDB_E_BADARG, "gdb_concat3: channel counts must be multiples of 4");

@@ -224,6 +224,25 @@ def gate_add(x: Tensor, y: Tensor, gate: Tensor, extra: Optional[Tensor] = None)
     return out
 
 
+def se_gate_add(x: Tensor, y: Tensor, w1: Tensor, w2: Tensor, extra: Optional[Tensor] = None, chunks: int = 64) -> Tensor:
+    """out = x + y * sigmoid(w2 @ relu(w1 @ mean_hw(y))) (+ extra): the squeeze-excite gate of a dense block and its residual
+    (decoder_rdn.py:31-41) as two launches - channel sums of y, then one kernel that finishes the gate in its prologue."""
+    _dev(x, y, w1, w2, extra)
+    N, Cc = x.shape[:2]
+    R = w1.shape[0]
+    if not (_is_cl(x) and _is_cl(y) and Cc % 4 == 0 and x.shape == y.shape and (extra is None or (_is_cl(extra) and extra.shape == x.shape))):
+        raise _lib.GdbError("se_gate_add needs dense channels-last fp32 tensors of one shape with C % 4 == 0")
+    if tuple(w1.shape) != (R, Cc) or tuple(w2.shape) != (Cc, R):
+        raise _lib.GdbError("se_gate_add: w1 must be (R, C) and w2 (C, R)")
+    S = x.numel() // (N * Cc)
+    partial = torch.empty((N, chunks, Cc), device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    _lib.check(lib.gdb_se_gate_add(x.data_ptr(), y.data_ptr(), _f32(w1).data_ptr(), _f32(w2).data_ptr(), R, _p(extra), N, S, Cc, chunks,
+                                   partial.data_ptr(), out.data_ptr(), _stream()), "gdb_se_gate_add")
+    return out
+
+
 def concat_channels(a: Tensor, b: Tensor, c: Optional[Tensor] = None) -> Tensor:
     """torch.cat((a, b[, c]), 1) for dense channels-last (N,C,H,W)-shaped fp32 maps, one streaming pass."""
     _dev(a, b, c)

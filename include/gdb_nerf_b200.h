@@ -261,6 +261,11 @@ int gdb_bias_act_add(const float* x, const float* bias, const float* skip, int64
  * blocks (decoder_rdn.py:31-41).  gate (N,C).                                 */
 int gdb_gate_add(const float* x, const float* y, const float* gate, const float* extra /* optional addend, same shape as x */,
                  int64_t N, int64_t S, int C, float* out, void* stream);
+/* Squeeze-excite block with its residual in two launches (decoder_rdn.py:31-41, modules.py:5-20):
+ * out = x + y * sigmoid(W2 relu(W1 mean_hw(y))) (+ extra).  x, y, extra, out channels-last (N,S,C); w1 (R,C), w2 (C,R)
+ * row-major (the nn.Linear weights, no bias); partial (N,chunks,C) is scratch for the fixed-order channel sums of y.    */
+int gdb_se_gate_add(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
+                    int64_t S, int C, int chunks, float* partial, float* out, void* stream);
 /* Channel concatenation of channels-last maps over npix pixels: out (npix, Ca+Cb+Cc) = [a | b | c] (c may be null with
  * Cc = 0): the inputs of the dense block's second and third convolutions (decoder_rdn.py:36-41).                          */
 int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream);

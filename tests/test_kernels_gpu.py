@@ -353,6 +353,16 @@ def test_glue_epilogues_match_torch():
     big = torch.randn(2, 64, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
     assert _md(ops.channel_mean(big), big.double().mean((2, 3))) <= 1e-6
     assert _md(ops.channel_mean(big, chunks=7), big.double().mean((2, 3))) <= 1e-6
+    # squeeze-excite gate finished inside the residual kernel (modules.py:5-20 + decoder_rdn.py:41)
+    hx = torch.randn(2, 64, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    w1 = (torch.randn(4, 64, generator=g) * 0.5).to(DEV)
+    w2 = (torch.randn(64, 4, generator=g) * 0.5).to(DEV)
+    gd = torch.sigmoid(torch.relu(big.double().mean((2, 3)) @ w1.double().t()) @ w2.double().t())
+    assert _md(ops.se_gate_add(hx, big, w1, w2), hx.double() + big.double() * gd[:, :, None, None]) <= 2e-6
+    assert _md(ops.se_gate_add(hx, big, w1, w2, extra=big, chunks=5), hx.double() + big.double() * gd[:, :, None, None] + big.double()) <= 2e-6
+    w1b, w2b = (torch.randn(2, 32, generator=g) * 0.5).to(DEV), (torch.randn(32, 2, generator=g) * 0.5).to(DEV)      # R = 2: padded hid
+    gd = torch.sigmoid(torch.relu(y.double().mean((2, 3)) @ w1b.double().t()) @ w2b.double().t())
+    assert _md(ops.se_gate_add(lat, y, w1b, w2b), lat.double() + y.double() * gd[:, :, None, None]) <= 2e-6
 
 
 def test_assemble_output_pre_shuffle_decoder(golden):
