@@ -551,19 +551,32 @@ class Decoder(nn.Module):
         return self.out_conv(self.up(y + self.blocks(y)))
 
 
-def decoder_fused(dec: "Decoder", x: torch.Tensor) -> torch.Tensor:
-    """Eval-time decoder (decoder_rdn.py:44-82) on channels-last data.  Returns (out, bias): the output BEFORE the last pixel
+def decoder_fused(dec: "Decoder", x: torch.Tensor, one_channel: int = -1) -> torch.Tensor:
+    """Eval-time decoder (decoder_rdn.py:44-82) on channels-last data.  ``one_channel``: index of a constant-one pad channel of x
+    that carries the first convolution's bias (-1: none, the bias is added by a separate pass).  Returns (out, bias): the output BEFORE the last pixel
     shuffle and WITHOUT its bias as (B, H/2, W/2, 12) channels-last plus that bias (12,), applied by ``gdb_assemble_output``: the last up-sampling convolution, the pixel shuffle and the 1x1
     output convolution are all linear, so the 1x1 is folded into the 3x3 (64 -> 3*4 channels instead of 64 -> 256,
     no 256-channel intermediate); ``gdb_assemble_output`` performs the pending shuffle."""
     from . import ops
     if ops._is_cl(x) or x.is_cuda:
         w_in = dec.in_conv.weight
-        if x.shape[1] > w_in.shape[1]:        # decoder input with zero pad channels (float4-aligned pixels from the render kernel)
-            extra = x.shape[1] - w_in.shape[1]
-            w_in = _cached(dec, f"_gdb_inpad{extra}", (w_in,), lambda: F.pad(dec.in_conv.weight, (0, 0, 0, 0, 0, extra)).contiguous(memory_format=torch.channels_last))
+        cin = w_in.shape[1]
+        if x.shape[1] > cin:        # decoder input with pad channels (float4-aligned pixels from the render kernel)
+            extra = x.shape[1] - cin
+
+            def make():
+                w = F.pad(dec.in_conv.weight, (0, 0, 0, 0, 0, extra))
+                if one_channel >= cin:
+                    # channel `one_channel` of x is the constant 1 (render kernel, out_channels_last = 2): its centre tap carries
+                    # the bias - the centre tap always lies inside the image, so the zero padding does not touch it
+                    kh, kw = w.shape[2] // 2, w.shape[3] // 2
+                    w[:, one_channel, kh, kw] = dec.in_conv.bias
+                return w.contiguous(memory_format=torch.channels_last)
+
+            w_in = _cached(dec, f"_gdb_inpad{extra}_{one_channel}", (w_in, dec.in_conv.bias), make)
         y = F.conv2d(x, w_in, None, 1, dec.in_conv.padding)
-        y = ops.bias_act_add(y, dec.in_conv.bias, None, relu=False) if ops._is_cl(y) and y.shape[1] % 4 == 0 else y + dec.in_conv.bias.view(1, -1, 1, 1)
+        if not (x.shape[1] > cin and one_channel >= cin):
+            y = ops.bias_act_add(y, dec.in_conv.bias, None, relu=False) if ops._is_cl(y) and y.shape[1] % 4 == 0 else y + dec.in_conv.bias.view(1, -1, 1, 1)
     else:
         y = dec.in_conv(x)
     h = y

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256, 1) render_fused_kernel(const RenderParams
     float* of = p.out_cl ? p.out_feat + (size_t)bidx * R : p.out_feat + (size_t)b * CT * HW + pix;
     float* od = p.out_cl ? p.out_dec + (size_t)bidx * p.dec_stride - R : of;
     if (writer && p.out_cl)
-      for (int k = F + 8; k < p.dec_stride; ++k) od[R + k] = 0.f;                                // pad channels of the decoder input
+      for (int k = F + 8; k < p.dec_stride; ++k) od[R + k] = k == F + 8 ? p.dec_pad0 : 0.f;                                // pad channels of the decoder input
     float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     // -- fine colours: project every ray of the bundle into every view, bilinear on the full-res image,
@@ -503,6 +503,10 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   GDB_REQUIRE(dec_stride == 0 || (dec_stride >= dec_min && dec_stride <= dec_min + 3), GDB_E_BADARG,
               "gdb_render_fused_fwd: dec_stride %d outside [%d, %d]", dec_stride, dec_min, dec_min + 3);
   p.dec_stride = dec_stride ? dec_stride : dec_min;
+  GDB_REQUIRE(out_channels_last >= 0 && out_channels_last <= 2, GDB_E_BADARG, "gdb_render_fused_fwd: out_channels_last must be 0, 1 or 2");
+  GDB_REQUIRE(out_channels_last != 2 || p.dec_stride > dec_min, GDB_E_BADARG,
+              "gdb_render_fused_fwd: out_channels_last = 2 (constant-one channel) needs a pad channel (dec_stride > %d)", dec_min);
+  p.dec_pad0 = out_channels_last == 2 ? 1.f : 0.f;
   p.out_feat = out_feat; p.out_dec = out_dec; p.out_depth = out_depth; p.out_opacity = out_opacity; p.out_cl = out_channels_last ? 1 : 0;
   if (taps && (taps->rgbs_feat_dir || taps->vox_feat || taps->sigma || taps->feat || taps->weights)) {
     GDB_REQUIRE(taps->offsets && taps->S_total > 0, GDB_E_BADARG, "gdb_render_fused_fwd: taps need offsets and S_total");

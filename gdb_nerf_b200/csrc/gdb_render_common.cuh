@@ -26,7 +26,8 @@ struct RenderParams {
   float* tap_w;
   int64_t tex_level[4];
   int cam_stride;
-  int dec_stride;      // floats per bundle of out_dec (>= F + 8; the pad channels are written as zeros)
+  int dec_stride;      // floats per bundle of out_dec (>= F + 8; the pad channels are written as zeros, the first as dec_pad0)
+  float dec_pad0;      // 0, or 1: a constant-one channel that carries the bias of the decoder's first convolution
   int vol_stride;      // floats between consecutive voxels of vol (>= 8, multiple of 4)
   int64_t vol_sb, vol_sz, vol_sy, vol_sx;   // float strides of vol over (batch, depth, row, column): layout 0 (B,D,Hb,Wb,.) or 1 (B,Hb,Wb,D,.)
   int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;

@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(256, 1) render_tc_kernel(const RenderParams p)
     float* of = p.out_cl ? p.out_feat + (size_t)bidx * R : p.out_feat + (size_t)b * CT * HW + pix;
     float* od = p.out_cl ? p.out_dec + (size_t)bidx * p.dec_stride - R : of;
     if (writer && p.out_cl)
-      for (int k = F + 8; k < p.dec_stride; ++k) od[R + k] = 0.f;                                // pad channels of the decoder input
+      for (int k = F + 8; k < p.dec_stride; ++k) od[R + k] = k == F + 8 ? p.dec_pad0 : 0.f;                                // pad channels of the decoder input
     float* tf = (p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     if constexpr (C::EARLY_RGB) {

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             float* odb = p.out_cl ? p.out_dec + (size_t)(b * HW + pixb) * p.dec_stride + c : p.out_feat + ((size_t)b * CT + R + c) * HW + pixb;
             *odb = a;
             if (p.out_cl && c == F + 7)
-              for (int k = F + 8; k < p.dec_stride; ++k) odb[k - c] = 0.f;                   // pad channels of the decoder input
+              for (int k = F + 8; k < p.dec_stride; ++k) odb[k - c] = k == F + 8 ? p.dec_pad0 : 0.f;                   // pad channels of the decoder input
           } else if (c == F + 8) {
             p.out_depth[(size_t)b * HW + pixb] = p.inv_depth ? fdiv(1.f, a) : a;
           } else {

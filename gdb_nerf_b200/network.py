@@ -279,11 +279,13 @@ class Network(nn.Module):
         cam = self.sampler.camera_block(src_exts, src_ints, b, self.inv_depth)
         sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
         vol_cl = feat_volume if fused else ops.to_channels_last(feat_volume, 8)    # fused: already a (B,D,Hb,Wb,8) view
+        dec_c = self.nerf.feat_dim + 3 + self.voxel_dim                              # channels of the decoder's input
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
                                self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
-                               precision=self.mlp_precision, pad_dec=fused)
+                               precision=self.mlp_precision, pad_dec=fused, dec_one=fused and dec_c % 4 != 0)
         if fused:
-            dec12, dec_b = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2))   # NCHW shape over channels-last memory
+            # NCHW shape over channels-last memory; the first pad channel (constant 1) carries the first convolution's bias
+            dec12, dec_b = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2), one_channel=dec_c if dec_c % 4 != 0 else -1)
             rgb, nerf_depth, nerf_opacity = ops.assemble_output(out['fine'], dec12, out['depth'], out['opacity'], b,
                                                                 self.reweighting, feat_channels_last=True, dec_pre_shuffle=True, dec_bias=dec_b)
         else:

@@ -166,7 +166,9 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          int precision /* 0 = fp32 SIMT MLP (1e-4 class); 1 = fp16-operand tcgen05 MLP, fp32 accumulate (2e-3 class);
                                           2 = split-fp16 (hi+lo) tcgen05 MLP, three MMAs per K step, fp32 accumulate (1e-4 class);
                                           3 = the first-generation kernel of class 1 (kept for A/B measurements) */,
-                         int out_channels_last,
+                         int out_channels_last /* 0: planar out_feat; 1: channels-last out_feat + out_dec; 2: as 1, and the first pad
+                                                  channel of out_dec is written as 1.0 instead of 0: a constant-one input channel whose
+                                                  centre-tap weights carry the bias of the decoder's first convolution (needs dec_stride > feat_dim + 11) */,
                          int dec_stride /* floats per bundle of out_dec: 0 = feat_dim + 11 (dense); up to +3 pad channels, written as zeros,
                                            so that the decoder's first convolution sees a float4-aligned pixel */,
                          float* out_feat, float* out_dec, float* out_depth, float* out_opacity,

@@ -179,6 +179,33 @@ def _render(golden, prefix, adaptive):
     assert torch.equal(split["fine"].permute(0, 3, 1, 2), plain["feat"][:, :R])
     assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), plain["feat"][:, R:])
     assert torch.equal(split["depth"], plain["depth"])
+    # padded decoder input: zero pad channels, or a constant-one first pad channel that carries the first convolution's bias
+    for prec in (0, 1, 2):
+        pad0 = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples,
+                                cfg.mvs.inv_depth[-1], adaptive, out_channels_last=True, pad_dec=True, precision=prec)
+        pad1 = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, spec["H"], spec["W"], b, cfg.nerf.max_num_samples,
+                                cfg.mvs.inv_depth[-1], adaptive, out_channels_last=True, pad_dec=True, dec_one=True, precision=prec)
+        nd = F + 8
+        assert pad0["dec_in"].shape[-1] == (nd + 3) // 4 * 4 > nd
+        assert torch.equal(pad0["dec_in"][..., :nd], pad1["dec_in"][..., :nd]) and torch.equal(pad0["fine"], pad1["fine"])
+        assert float(pad0["dec_in"][..., nd:].abs().max()) == 0.0
+        assert torch.equal(pad1["dec_in"][..., nd], torch.ones_like(pad1["dec_in"][..., nd]))
+        assert float(pad1["dec_in"][..., nd + 1:].abs().sum()) == 0.0
+        if prec == 0:
+            assert torch.equal(pad0["dec_in"][..., :nd], split["dec_in"])
+    # the decoder with its first bias inside the convolution (constant-one channel) = with the separate bias pass
+    from gdb_nerf_b200.cnn import Decoder, decoder_fused
+    torch.manual_seed(2)
+    dec = Decoder(nd, 3, num_feats=64, num_layers=1, upscale_factor=b).to(DEV).eval().to(memory_format=torch.channels_last)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ya, ba = decoder_fused(dec, pad0["dec_in"].permute(0, 3, 1, 2))
+            yb, bb = decoder_fused(dec, pad1["dec_in"].permute(0, 3, 1, 2), one_channel=nd)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    assert torch.equal(ba, bb) and _md(ya, yb) <= 1e-5 * max(1.0, float(ya.abs().max()))
     # channels-last feature input to the source preparation: same texture
     feat_nhwc = tex_ref[:, :, :feat_dim].to(DEV).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
     src2 = ops.prepare_sources(feat_nhwc, golden.t("in_rgb").to(DEV), b, cfg.nerf.max_mipmap_level)
