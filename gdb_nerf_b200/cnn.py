@@ -217,7 +217,10 @@ def feature_net_fused(net: "FeatureNet", x: torch.Tensor, levels: int = 3) -> Li
         f1 = run_block(net.conv1[1], run_block(net.conv1[0], f0))
         f2 = run_block(net.conv2[1], run_block(net.conv2[0], f1))
         lat1 = None
-    outs = [net.out0(f2)]
+    if ops._is_cl(f2) and net.out0.out_channels % 4 == 0:      # 1x1 output convolution, bias through the vectorised epilogue
+        outs = [ops.bias_act_add(F.conv2d(f2, net.out0.weight), net.out0.bias, None, relu=False)]
+    else:
+        outs = [net.out0(f2)]
     if levels >= 2:
         # top-down step (feature_net.py:52-58): nearest x2 + lateral 1x1 conv + its bias in one pass
         top = ops.bias_act_add(F.conv2d(f1, net.inner1.weight) if lat1 is None else lat1, net.inner1.bias, f2, relu=False, skip_up2=True)
