@@ -128,8 +128,15 @@ __global__ void assemble_output_kernel(const float* __restrict__ feat, int Ctot,
   const size_t HW = (size_t)H * W, hw = (size_t)Hb * Wb;
   size_t n = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int b = i / HW;
-    int y = (i % HW) / W, x = i % W;
+    int b, y, x;
+    if (n <= 0xffffffffull) {           // 32-bit index decomposition (64-bit divisions dominated this streaming kernel)
+      const unsigned u = (unsigned)i, hw32 = (unsigned)HW;
+      const unsigned bb = u / hw32, r = u - bb * hw32, yy = r / (unsigned)W;
+      b = (int)bb; y = (int)yy; x = (int)(r - yy * (unsigned)W);
+    } else {
+      b = i / HW;
+      y = (i % HW) / W; x = i % W;
+    }
     int yb = y / BS, xb = x / BS, j = (y % BS) * BS + (x % BS);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
