@@ -287,20 +287,14 @@ __device__ __forceinline__ U4 u4_add(const U4& x, const U4& y) { return U4{add2(
 __device__ __forceinline__ U4 u4_sub(const U4& x, const U4& y) { return U4{sub2(x.a, y.a), sub2(x.b, y.b), sub2(x.c, y.c), sub2(x.d, y.d)}; }
 __device__ __forceinline__ U4 u4_sqacc(const U4& x, const U4& acc) { return U4{fma2(x.a, x.a, acc.a), fma2(x.b, x.b, acc.b), fma2(x.c, x.c, acc.c), fma2(x.d, x.d, acc.d)}; }
 
-// PP = 2: two consecutive depth planes per iteration.  Between neighbouring hypotheses the sampling point of a view moves a
-// fraction of a texel (0.2-0.4 in the first cascade stage, < 0.1 in the refinement stages), so both planes mostly share
-// their 2x2 footprint: the second plane re-loads its four taps only when its (clamped) tap coordinates differ from the
-// first plane's - a per-lane predicate on the loads - and otherwise blends the registers again with its own weights.
-// The kernel is bound by the L1 data pipe (ncu: 74-84 %), i.e. by exactly these loads.
-template <int C, int V, int OUT_CL, int PP>      // OUT_CL 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
+template <int C, int V, int OUT_CL>      // 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
 __global__ void __launch_bounds__(256)
 warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
                       int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
                       float* __restrict__ out) {
   constexpr int LPP = C / 8;                   // lanes per pixel
   constexpr int PIX = 256 / LPP;               // pixels per CTA
-  constexpr int NI = PP * V;                   // (plane, view) projections per pixel and iteration, item k = plane * V + view
-  constexpr int VPL = (NI + LPP - 1) / LPP;    // projections per lane: lane q owns items q, q + LPP, ..
+  constexpr int VPL = (V + LPP - 1) / LPP;     // projections per lane
   __shared__ float sproj[V * 12];
 
   const int b = blockIdx.z;
@@ -318,7 +312,7 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
   float rx[VPL], ry[VPL], rz[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
-    const float* P = sproj + (min(q + k * LPP, NI - 1) % V) * 12;
+    const float* P = sproj + min(q + k * LPP, V - 1) * 12;
     rx[k] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
     ry[k] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
     rz[k] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
@@ -328,76 +322,56 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
   const float far_ = range[((size_t)(b * 2 + 1) * rh + ryi) * rw + rxi];
   const size_t view_stride = (size_t)Hs * Ws * C;
   const float* fbase = feat + (size_t)b * V * view_stride + q * 8;
-  const float invV = 1.f / (float)V;
-  const u64 iv = pack2(invV, invV);
 
   const int d0 = blockIdx.y * DCH;
   const int d1 = min(d0 + DCH, D);
-  for (int d = d0; d < d1; d += PP) {
+  for (int d = d0; d < d1; ++d) {
+    const float dv = hypothesis(near_, far_, d, D, inv_depth);
+    const float depth = inv_depth ? fdiv(1.f, dv) : dv;
     WarpTap mine[VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int item = min(q + k * LPP, NI - 1);
-      const int dd = min(d + item / V, d1 - 1);                  // an odd tail repeats the last plane (not stored twice)
-      const float dv = hypothesis(near_, far_, dd, D, inv_depth);
-      const float depth = inv_depth ? fdiv(1.f, dv) : dv;
-      mine[k] = warp_tap(sproj + (item % V) * 12, rx[k], ry[k], rz[k], depth, Ws, Hs);
-    }
-    U4 val[PP][V];
+    for (int k = 0; k < VPL; ++k) mine[k] = warp_tap(sproj + min(q + k * LPP, V - 1) * 12, rx[k], ry[k], rz[k], depth, Ws, Hs);
+    U4 val[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float* vb = fbase + v * view_stride;
-      U4 t00, t10, t01, t11;
-      int pxx = 0, pyy = 0;
-#pragma unroll
-      for (int pl = 0; pl < PP; ++pl) {
-        const int item = pl * V + v;
-        const int src = group_base + item % LPP;
-        const WarpTap m = mine[item / LPP];
-        WarpTap t;
-        if (LPP > 1) {
-          t.xx = __shfl_sync(0xffffffffu, m.xx, src);
-          t.yy = __shfl_sync(0xffffffffu, m.yy, src);
-          t.wx0 = __shfl_sync(0xffffffffu, m.wx0, src);
-          t.wx1 = __shfl_sync(0xffffffffu, m.wx1, src);
-          t.wy0 = __shfl_sync(0xffffffffu, m.wy0, src);
-          t.wy1 = __shfl_sync(0xffffffffu, m.wy1, src);
-        } else {
-          t = m;
-        }
-        if (pl == 0 || t.xx != pxx || t.yy != pyy) {               // footprint differs from the previous plane's: (re)load
-          const int r0 = (t.yy & 0xffff) * Ws, r1 = (t.yy >> 16) * Ws;
-          const int c0 = t.xx & 0xffff, c1 = t.xx >> 16;
-          // dead pixels of the last tile read pixel (0, 0)'s taps: in bounds, never stored
-          t00 = ldg256(vb + (size_t)(r0 + c0) * C);
-          t10 = ldg256(vb + (size_t)(r0 + c1) * C);
-          t01 = ldg256(vb + (size_t)(r1 + c0) * C);
-          t11 = ldg256(vb + (size_t)(r1 + c1) * C);
-        }
-        pxx = t.xx;
-        pyy = t.yy;
-        const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
-        U4 acc = u4_mul(t00, pack2(w00, w00));
-        acc = u4_fma(t10, pack2(w10, w10), acc);
-        acc = u4_fma(t01, pack2(w01, w01), acc);
-        acc = u4_fma(t11, pack2(w11, w11), acc);
-        val[pl][v] = acc;
+      const int src = group_base + v % LPP;
+      const WarpTap m = mine[v / LPP];
+      WarpTap t;
+      if (LPP > 1) {
+        t.xx = __shfl_sync(0xffffffffu, m.xx, src);
+        t.yy = __shfl_sync(0xffffffffu, m.yy, src);
+        t.wx0 = __shfl_sync(0xffffffffu, m.wx0, src);
+        t.wx1 = __shfl_sync(0xffffffffu, m.wx1, src);
+        t.wy0 = __shfl_sync(0xffffffffu, m.wy0, src);
+        t.wy1 = __shfl_sync(0xffffffffu, m.wy1, src);
+      } else {
+        t = m;
       }
+      const int r0 = (t.yy & 0xffff) * Ws, r1 = (t.yy >> 16) * Ws;
+      const int c0 = t.xx & 0xffff, c1 = t.xx >> 16;
+      const float* vb = fbase + v * view_stride;
+      // dead pixels of the last tile read pixel (0, 0)'s taps: in bounds, never stored
+      const U4 t00 = ldg256(vb + (size_t)(r0 + c0) * C), t10 = ldg256(vb + (size_t)(r0 + c1) * C);
+      const U4 t01 = ldg256(vb + (size_t)(r1 + c0) * C), t11 = ldg256(vb + (size_t)(r1 + c1) * C);
+      const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+      U4 acc = u4_mul(t00, pack2(w00, w00));
+      acc = u4_fma(t10, pack2(w10, w10), acc);
+      acc = u4_fma(t01, pack2(w01, w01), acc);
+      acc = u4_fma(t11, pack2(w11, w11), acc);
+      val[v] = acc;
     }
+    U4 mean = val[0];                       // 0 + val[0] is exact: same sum order as the first kernel
 #pragma unroll
-    for (int pl = 0; pl < PP; ++pl) {
-      U4 mean = val[pl][0];                   // 0 + val[0] is exact: same sum order as the first kernel
+    for (int v = 1; v < V; ++v) mean = u4_add(mean, val[v]);
+    const float invV = 1.f / (float)V;
+    const u64 iv = pack2(invV, invV);
+    mean = u4_mul(mean, iv);
+    U4 var{0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-      for (int v = 1; v < V; ++v) mean = u4_add(mean, val[pl][v]);
-      mean = u4_mul(mean, iv);
-      U4 var{0ull, 0ull, 0ull, 0ull};
-#pragma unroll
-      for (int v = 0; v < V; ++v) var = u4_sqacc(u4_sub(val[pl][v], mean), var);
-      var = u4_mul(var, iv);
-      const int dd = d + pl;
-      if (live && dd < d1)
-        stcs256(out + (OUT_CL == 2 ? (((size_t)b * HW + pix) * D + dd) : (((size_t)b * D + dd) * HW + pix)) * C + q * 8, var);
-    }
+    for (int v = 0; v < V; ++v) var = u4_sqacc(u4_sub(val[v], mean), var);
+    var = u4_mul(var, iv);
+    if (live)
+      stcs256(out + (OUT_CL == 2 ? (((size_t)b * HW + pix) * D + d) : (((size_t)b * D + d) * HW + pix)) * C + q * 8, var);
   }
 }
 
@@ -405,13 +379,6 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
 static bool warp_variance_v1() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GDB_K1_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-// GDB_K1_PAIR=1 selects the plane-pair variant (opt-in until measured faster; identical results either way)
-static bool warp_variance_single() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GDB_K1_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
 
@@ -429,15 +396,10 @@ static int launch_warp_variance(const float* feat, const float* proj, const floa
     DCH = D;
     while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
     dim3 grid8(tiles, (D + DCH - 1) / DCH, B);
-    const bool pair = !warp_variance_single();
-    if (out_cl == 2 && pair)
-      warp_variance8_kernel<C, V, 2, 2><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
-    else if (out_cl == 2)
-      warp_variance8_kernel<C, V, 2, 1><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
-    else if (pair)
-      warp_variance8_kernel<C, V, 1, 2><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+    if (out_cl == 2)
+      warp_variance8_kernel<C, V, 2><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
     else
-      warp_variance8_kernel<C, V, 1, 1><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+      warp_variance8_kernel<C, V, 1><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
     return cuda_check("gdb_warp_variance_fwd");
   }
   dim3 grid(tiles, (D + DCH - 1) / DCH, B);
