@@ -533,9 +533,9 @@ __global__ void depth_range_logits_kernel(const float* __restrict__ range, int r
 // shared memory and reduced by the pixel's own thread with the K2 arithmetic.  Exact fp32 (the cuDNN head this
 // replaces ran a 1-output-channel convolution 20x off the memory roofline).
 // ---------------------------------------------------------------------------
-constexpr int PH_TY = 4, PH_TX = 32, PH_PW = PH_TX + 2, PH_PH = PH_TY + 2, PH_PLANE = 2 * PH_PH * PH_PW;   // float4 per plane
+constexpr int PH_TY = 4, PH_TX = 16, PH_THREADS = PH_TY * PH_TX, PH_PW = PH_TX + 2, PH_PH = PH_TY + 2, PH_PLANE = 2 * PH_PH * PH_PW;   // float4 per plane
 
-__global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float* __restrict__ y, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(PH_THREADS) prob_head_depth_range_kernel(const float* __restrict__ y, const float* __restrict__ wgt,
                                                                     const float* __restrict__ range, int rh, int rw, int B, int D,
                                                                     int H, int W, float ci_scale, int inv_depth,
                                                                     float* __restrict__ depth, float* __restrict__ ci,
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float*
   extern __shared__ __align__(16) unsigned char ph_smem[];
   float4* plane = reinterpret_cast<float4*>(ph_smem);                  // [3][2 halves][PH_PH][PH_PW]
   float4* wsm = plane + 3 * PH_PLANE;                                  // [27][2]
-  float* lsm = reinterpret_cast<float*>(wsm + 54);                     // [D][128]
+  float* lsm = reinterpret_cast<float*>(wsm + 54);                     // [D][PH_THREADS]
   const int tid = threadIdx.x, ty = tid / PH_TX, tx = tid % PH_TX;
   const int b = blockIdx.z, y0 = blockIdx.y * PH_TY, x0 = blockIdx.x * PH_TX;
   const int HW = H * W;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float*
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load_plane = [&](int d, int slot) {
     float4* dst = plane + slot * PH_PLANE;
-    for (int i = tid; i < PH_PH * PH_PW; i += 128) {
+    for (int i = tid; i < PH_PH * PH_PW; i += PH_THREADS) {
       const int py = i / PH_PW, px = i - py * PH_PW;
       const int gy = y0 + py - 1, gx = x0 + px - 1;
       float4 a = zero4, c = zero4;
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float*
           acc0 = fmaf(c.z, wc.z, acc0); acc1 = fmaf(c.w, wc.w, acc1);
         }
     }
-    lsm[d * 128 + tid] = acc0 + acc1;
+    lsm[d * PH_THREADS + tid] = acc0 + acc1;
     __syncthreads();                                                   // plane (d+2)%3 is overwritten next
   }
   const int gy = y0 + ty, gx = x0 + tx;
@@ -597,24 +597,24 @@ __global__ void __launch_bounds__(128) prob_head_depth_range_kernel(const float*
   const float far_ = range[((size_t)(b * 2 + 1) * rh + ry) * rw + rx];
   // soft-max over depth in ATen's order, then depth_regression (depth_net.py:479-514): same arithmetic as depth_range_logits_kernel
   float m = -INFINITY;
-  for (int d = 0; d < D; ++d) m = fmaxf(m, lsm[d * 128 + tid]);
+  for (int d = 0; d < D; ++d) m = fmaxf(m, lsm[d * PH_THREADS + tid]);
   float sum = 0.f;
   for (int d = 0; d < D; ++d) {
-    const float e = expf(lsm[d * 128 + tid] - m);
-    lsm[d * 128 + tid] = e;
+    const float e = expf(lsm[d * PH_THREADS + tid] - m);
+    lsm[d * PH_THREADS + tid] = e;
     sum += e;
   }
   float mean = 0.f;
   for (int d = 0; d < D; ++d) {
-    const float pr = fdiv(lsm[d * 128 + tid], sum);
-    lsm[d * 128 + tid] = pr;
+    const float pr = fdiv(lsm[d * PH_THREADS + tid], sum);
+    lsm[d * PH_THREADS + tid] = pr;
     mean = fadd(mean, fmul(pr, hypothesis(near_, far_, d, D, inv_depth)));
   }
   float var = 0.f;
   for (int d = 0; d < D; ++d) {
     const float t = fsub(hypothesis(near_, far_, d, D, inv_depth), mean);
-    var = fadd(var, fmul(lsm[d * 128 + tid], fmul(t, t)));
-    if (prob_out) prob_out[((size_t)b * D + d) * HW + pix] = lsm[d * 128 + tid];
+    var = fadd(var, fmul(lsm[d * PH_THREADS + tid], fmul(t, t)));
+    if (prob_out) prob_out[((size_t)b * D + d) * HW + pix] = lsm[d * PH_THREADS + tid];
   }
   const float half = fmul(ci_scale, sqrtf(fmaxf(var, 1e-12f)));
   const float first = hypothesis(near_, far_, 0, D, inv_depth), last = hypothesis(near_, far_, D - 1, D, inv_depth);
@@ -759,7 +759,7 @@ extern "C" int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* wei
   GDB_REQUIRE((rh == 1 && rw == 1) || (rh == h && rw == w), GDB_E_BADARG,
               "gdb_prob_head_depth_range_fwd: depth_range must be 1x1 or %dx%d, got %dx%d", h, w, rh, rw);
   GDB_REQUIRE(aligned16(y_cl) && aligned16(weight), GDB_E_ALIGN, "gdb_prob_head_depth_range_fwd: y / weight must be 16-byte aligned");
-  const int smem = (3 * PH_PLANE + 54) * 16 + D * 128 * 4;
+  const int smem = (3 * PH_PLANE + 54) * 16 + D * PH_THREADS * 4;
   GDB_REQUIRE(smem <= 227 * 1024, GDB_E_UNSUPPORTED, "gdb_prob_head_depth_range_fwd: D=%d needs %d B of shared memory", D, smem);
   static int configured = 0;
   if (smem > configured) {
@@ -768,7 +768,7 @@ extern "C" int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* wei
     configured = smem;
   }
   dim3 grid((w + PH_TX - 1) / PH_TX, (h + PH_TY - 1) / PH_TY, B);
-  prob_head_depth_range_kernel<<<grid, 128, smem, as_stream(stream)>>>(y_cl, weight, depth_range, rh, rw, B, D, h, w, ci_scale, inv_depth,
+  prob_head_depth_range_kernel<<<grid, PH_THREADS, smem, as_stream(stream)>>>(y_cl, weight, depth_range, rh, rw, B, D, h, w, ci_scale, inv_depth,
                                                                       depth, ci, vol_range, prob_out);
   return cuda_check("gdb_prob_head_depth_range_fwd");
 }
