@@ -61,7 +61,8 @@ def _grad_worker(rank, world, port, q):
         if rank == 1:
             net[2].weight.grad = torch.ones(2, 2)       # ... except that rank 1 has a gradient for its weight
         nbytes = allreduce_gradients(net.parameters())
-        q.put((rank, nbytes, [p.grad.clone() for p in net.parameters()]))
+        # plain lists, not tensors: a tensor travels through the queue as a shared file descriptor that dies with this process
+        q.put((rank, nbytes, [p.grad.tolist() for p in net.parameters()]))
     finally:
         dist.destroy_process_group()
 
@@ -92,7 +93,7 @@ def test_two_rank_gradient_allreduce_gloo():
     assert res[0][1] == res[1][1] == 4 * sum(p.numel() for p in net.parameters())
     for r in range(world):
         for got, w in zip(res[r][2], want):
-            assert torch.allclose(got, w, atol=1e-6)
+            assert torch.allclose(torch.tensor(got), w, atol=1e-6)
 
 
 def test_shard_helpers_single_process():
