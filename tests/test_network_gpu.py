@@ -339,8 +339,9 @@ def test_depth_folded_cost_regularisation_matches_3d(recipe, hw):
         assert _md(x, y) <= 2e-5 * 480.0
 
 
+@pytest.mark.parametrize("levels", [1, 2, 3])
 @pytest.mark.parametrize("hw", [(24, 40), (32, 48), (20, 36), (64, 64)])
-def test_width_folded_fpn_matches_modules(hw):
+def test_width_folded_fpn_matches_modules(hw, levels):
     """feature_net_fused (BN folded, width-folded 8/16-channel layers when W % 4 == 0, plain layers otherwise) equals the
     plain module sequence of feature_net.py:40-64 in fp32."""
     from gdb_nerf_b200.cnn import FeatureNet, feature_net_fused
@@ -354,9 +355,9 @@ def test_width_folded_fpn_matches_modules(hw):
             m.bias.data.normal_(0, 0.2)
     x = torch.rand(3, 3, *hw, device=DEV)
     with torch.no_grad():
-        want = net(x, levels=2)
-        got = feature_net_fused(net, x, levels=2)
-    assert len(got) == len(want) == 2
+        want = net(x, levels=levels)
+        got = feature_net_fused(net, x, levels=levels)
+    assert len(got) == len(want) == levels
     for a, b in zip(got, want):
         assert a.shape == b.shape
         assert _md(a, b) <= 2e-5 * max(1.0, float(b.abs().max()))
