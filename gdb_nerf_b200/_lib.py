@@ -50,6 +50,9 @@ SIGNATURES = {
                                    c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, C.POINTER(RenderTaps), c_f]),
     "gdb_depth_range_from_logits_fwd": (c_i, [c_f, c_i, c_i, c_f, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f,
                                               c_f, c_f]),
+    "gdb_prob_head_depth_range_split_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "gdb_prob_head_split_scratch_floats": (c_i64, [c_i, c_i, c_i, c_i]),
+    "gdb_prob_head_split_counters": (c_i64, [c_i, c_i, c_i]),
     "gdb_prob_head_depth_range_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f]),
     "gdb_warp_variance_bwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f]),
     "gdb_depth_range_bwd": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),

@@ -156,8 +156,19 @@ def depth_range_from_logits(depth_range: Tensor, logits: Tensor, ci_scale: float
     return depth, ci, vol, prob
 
 
+_PH_COUNTERS: Dict = {}
+
+
+def _prob_head_chunks(D: int) -> int:
+    """Depth chunks of the split probability-head kernel: ~16 planes each, none empty."""
+    n = max(1, D // 16)
+    while n > 1 and (n - 1) * ((D + n - 1) // n) >= D:
+        n -= 1
+    return n
+
+
 def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_scale: float, inv_depth: bool,
-                          want_prob: bool = False) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
+                          want_prob: bool = False, split: bool = True) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
     """K2 fused with the probability head: ``y`` is the U-Net's last feature volume, (B,8,D,h,w)-shaped over channels-last
     (B,D,h,w,8) memory, ``weight`` the head's (1,8,3,3,3) Conv3d weight (padding 1, no bias).
     -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w), prob (B,D,h,w) or None."""
@@ -174,6 +185,20 @@ def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_sca
     vol = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
     prob = torch.empty((B, D, h, w), device=dev, dtype=torch.float32) if want_prob else None
     lib = _lib.load()
+    nch = _prob_head_chunks(D) if (split and not want_prob) else 1
+    if nch > 1 and B * nch <= 65535:
+        # depth axis split over nch CTAs per tile (on-line soft-max partials merged by the tile's last CTA)
+        scratch = torch.empty(int(lib.gdb_prob_head_split_scratch_floats(B, h, w, nch)), device=dev, dtype=torch.float32)
+        # one counter set per stream: launches on one stream are serialised, two streams must not share arrival counts
+        key = (dev, int(lib.gdb_prob_head_split_counters(B, h, w)), _stream())
+        counters = _PH_COUNTERS.get(key)
+        if counters is None:      # zero once; the kernel leaves the counters zero
+            counters = _PH_COUNTERS[key] = torch.zeros(key[1], device=dev, dtype=torch.int32)
+        _lib.check(lib.gdb_prob_head_depth_range_split_fwd(y.data_ptr(), wk.data_ptr(), depth_range.data_ptr(), rh, rw, B, Cc, D, h, w,
+                                                           nch, float(ci_scale), int(inv_depth), scratch.data_ptr(), counters.data_ptr(),
+                                                           depth.data_ptr(), ci.data_ptr(), vol.data_ptr(), _stream()),
+                   "gdb_prob_head_depth_range_split_fwd")
+        return depth, ci, vol, None
     _lib.check(lib.gdb_prob_head_depth_range_fwd(y.data_ptr(), wk.data_ptr(), depth_range.data_ptr(), rh, rw, B, Cc, D, h, w,
                                                  float(ci_scale), int(inv_depth), depth.data_ptr(), ci.data_ptr(), vol.data_ptr(),
                                                  _p(prob), _stream()), "gdb_prob_head_depth_range_fwd")

@@ -181,6 +181,17 @@ int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* weight, const 
                                   int C, int D, int h, int w, float ci_scale, int inv_depth, float* depth, float* ci,
                                   float* vol_range, float* prob_out, void* stream);
 
+/* The same operator with the depth axis split over `nchunks` CTAs per pixel tile (more parallelism for small maps): every CTA
+ * keeps the soft-max statistics of its chunk on line (running maximum, sum e, sum e x, sum e x^2 about the interval's
+ * midpoint), the last CTA of a tile merges them.  No probability output.  scratch: gdb_prob_head_split_scratch_floats
+ * floats (16-byte aligned); counters: gdb_prob_head_split_counters ints, ZERO before the first launch (the kernel leaves
+ * them zero).  Every chunk must hold a plane: (nchunks - 1) * ceil(D / nchunks) < D.                                     */
+int64_t gdb_prob_head_split_scratch_floats(int B, int h, int w, int nchunks);
+int64_t gdb_prob_head_split_counters(int B, int h, int w);
+int gdb_prob_head_depth_range_split_fwd(const float* y_cl, const float* weight, const float* depth_range, int rh, int rw, int B,
+                                        int C, int D, int h, int w, int nchunks, float ci_scale, int inv_depth, float* scratch,
+                                        int* counters, float* depth, float* ci, float* vol_range, void* stream);
+
 /* Output assembly, replaces network.py:175-182 minus the decoder CNN:
  * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
  * and the bilinear xb up-sampling of depth and opacity.

@@ -505,3 +505,12 @@ def test_prob_head_fused_into_depth_range(D, h, w, inv, per_pixel):
     assert _md(got[3], want[3]) <= 2e-6                               # probabilities
     for k in range(3):                                                # depth, confidence interval, volume range
         assert _md(got[k], want[k]) <= 1e-5 * 480.0, k
+    # depth axis split over several CTAs per tile (on-line soft-max partials); twice: the arrival counters reset themselves
+    for _ in range(2):
+        sp = ops.prob_head_depth_range(y, wt, rng, 1.0, inv)
+        assert sp[3] is None
+        for k in range(3):
+            assert _md(sp[k], want[k]) <= 1e-5 * 480.0, k
+    one = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, split=False)
+    for k in range(3):
+        assert torch.equal(one[k], got[k])
