@@ -157,6 +157,7 @@ def depth_range_from_logits(depth_range: Tensor, logits: Tensor, ci_scale: float
 
 
 _PH_COUNTERS: Dict = {}
+_PH_WEIGHTS: Dict = {}
 
 
 def _prob_head_chunks(D: int) -> int:
@@ -178,7 +179,14 @@ def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_sca
     depth_range = _f32(depth_range)
     B, Cc, D, h, w = y.shape
     _, _, rh, rw = depth_range.shape
-    wk = _f32(weight)[0].permute(1, 2, 3, 0).contiguous()             # [kd][ky][kx][c]
+    wkey = (weight.data_ptr(), weight._version, str(weight.device))
+    hit = _PH_WEIGHTS.get(wkey)
+    if hit is None:                                                   # [kd][ky][kx][c], re-laid out once per weight version
+        if len(_PH_WEIGHTS) >= 8:
+            _PH_WEIGHTS.clear()
+        # the entry keeps `weight` itself alive: its address cannot be handed to another tensor while the key exists
+        hit = _PH_WEIGHTS[wkey] = (weight, _f32(weight.detach())[0].permute(1, 2, 3, 0).contiguous())
+    wk = hit[1]
     dev = y.device
     depth = torch.empty((B, 1, h, w), device=dev, dtype=torch.float32)
     ci = torch.empty((B, 2, h, w), device=dev, dtype=torch.float32)
