@@ -86,3 +86,15 @@ def test_fpn_chain_in_folded_views():
 def test_stride_must_divide_fold():
     with pytest.raises(ValueError):
         fold_width_weight(torch.zeros(4, 4, 3, 3), 1, 2)
+
+
+def test_prob_head_depth_chunks_are_never_empty():
+    """ops._prob_head_chunks: chunks of ~16 planes; the C side counts one arrival per chunk, so none may be empty."""
+    from gdb_nerf_b200.ops import _prob_head_chunks
+    for D in range(1, 300):
+        n = _prob_head_chunks(D)
+        per = (D + n - 1) // n
+        assert n >= 1 and (n - 1) * per < D <= n * per
+        if D >= 32:
+            assert n >= 2
+    assert _prob_head_chunks(64) == 4 and _prob_head_chunks(36) == 2 and _prob_head_chunks(8) == 1
