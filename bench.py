@@ -216,7 +216,7 @@ def run_ours(args, wl, cfg):
     spans = {"gdb_render_fused_fwd": [], "gdb_warp_variance_fwd": []}
     recording = {"on": False}
     launches_per_call = {"to_channels_last": 1, "homography_mats": 1, "depth_values": 1, "warp_variance": 1, "depth_range_from_prob": 1,
-                         "depth_range_from_logits": 1, "bias_act_add": 1, "gate_add": 1, "se_gate_add": 2,
+                         "depth_range_from_logits": 1, "bias_act_add": 1, "gate_add": 1, "se_gate_add": 2, "concat_into": 1,
                          "camera_block": 1, "prepare_sources": 1, "render_fused": 1, "assemble_output": 1,
                          "prob_head_depth_range": 1, "concat_channels": 1, "channel_mean": 2, "pixel_shuffle2_bias": 1}
 

@@ -65,6 +65,8 @@ SIGNATURES = {
     "gdb_bias_act_add": (c_i, [c_f, c_f, c_f, c_i64, c_i64, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
     "gdb_gate_add": (c_i, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i, c_f, c_f]),
     "gdb_se_gate_add": (c_i, [c_f, c_f, c_f, c_f, c_i, c_f, c_i64, c_i64, c_i, c_i, c_f, c_f, c_f]),
+    "gdb_se_gate_add_cat": (c_i, [c_f, c_f, c_f, c_f, c_i, c_f, c_i64, c_i64, c_i, c_i, c_f, c_f, c_f, c_i, c_f]),
+    "gdb_concat2_into": (c_i, [c_f, c_i, c_f, c_i, c_i64, c_f, c_i, c_i, c_f]),
     "gdb_pixel_shuffle2": (c_i, [c_f, c_f, c_i64, c_i, c_i, c_i, c_f, c_f]),
     "gdb_concat3": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_i64, c_f, c_f]),
     "gdb_channel_mean": (c_i, [c_f, c_i64, c_i64, c_i, c_i, c_f, c_f, c_f]),

@@ -583,6 +583,7 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor, one_channel: int = -1) -> tor
     else:
         y = dec.in_conv(x)
     h = y
+    cat_buf = None
     for blk in dec.blocks:
         zb = _cached(blk, "_gdb_zero", (blk.conv1.weight,), lambda: torch.zeros(blk.conv1.weight.shape[0], device=x.device))
         a = torch.cudnn_convolution_relu(h, blk.conv1.weight, zb, (1, 1), (1, 1), (1, 1), 1)
@@ -595,9 +596,14 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor, one_channel: int = -1) -> tor
                 blk.conv2.weight[:, ch:].contiguous(memory_format=torch.channels_last)))
             z = torch.cudnn_convolution(h, wh, (1, 1), (1, 1), (1, 1), 1, False, False, torch.backends.cudnn.allow_tf32)
             b = torch.cudnn_convolution_add_relu(a, wa, z, 1.0, zb, (1, 1), (1, 1), (1, 1), 1)
-            c = blk.conv3(ops.concat_channels(h, a, b))
+            if cat_buf is not None:      # h already sits in the buffer's leading channels (written by the previous block)
+                c = blk.conv3(ops.concat_into(cat_buf, ch, a, b))
+            else:
+                c = blk.conv3(ops.concat_channels(h, a, b))
+            cat_buf = None
             gate = None if ops._is_cl(c) else blk.se.fc(c.mean((2, 3)))
         else:
+            cat_buf = None
             b = torch.cudnn_convolution_relu(torch.cat((h, a), 1), blk.conv2.weight, zb, (1, 1), (1, 1), (1, 1), 1)
             c = blk.conv3(torch.cat((h, a, b), 1))
             gate = blk.se.fc(c.mean((2, 3)))
@@ -606,7 +612,10 @@ def decoder_fused(dec: "Decoder", x: torch.Tensor, one_channel: int = -1) -> tor
             # the last block also adds the decoder's global residual y (decoder_rdn.py: y + blocks(y)) in the same pass
             extra = y if last and ops._is_cl(y) else None
             if gate is None:      # squeeze-excite gate finished in the prologue of the residual kernel
-                h = ops.se_gate_add(h, c, blk.se.fc[0].weight, blk.se.fc[2].weight, extra=extra)
+                if not last:      # ... which also writes the next block's h slice of its concatenation buffer
+                    N_, C_, H_, W_ = h.shape
+                    cat_buf = torch.empty((N_, H_, W_, C_ + 2 * blk.conv1.weight.shape[0]), device=h.device, dtype=h.dtype).permute(0, 3, 1, 2)
+                h = ops.se_gate_add(h, c, blk.se.fc[0].weight, blk.se.fc[2].weight, extra=extra, cat_out=cat_buf)
             else:
                 h = ops.gate_add(h, c, gate, extra=extra)
             if last and not ops._is_cl(y):

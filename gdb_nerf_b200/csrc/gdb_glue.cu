@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) se_gate_add_kernel(const float4* __restri
                                                           const float* __restrict__ partial, int chunks, float inv_S,
                                                           const float* __restrict__ w1, const float* __restrict__ w2, int R,
                                                           const float4* __restrict__ extra, int C, int64_t per_image4,
-                                                          float4* __restrict__ out) {
+                                                          float4* __restrict__ out, float4* __restrict__ out2, int out2_s4) {
   extern __shared__ float se_sm[];            // mean[C] | hid[R] | gate[C]
   float* mean = se_sm;
   float* hid = se_sm + C;
@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(256) se_gate_add_kernel(const float4* __restri
   const int C4 = C / 4;
   const float4* g4 = reinterpret_cast<const float4*>(gate);
   const int64_t base = (int64_t)n * per_image4;
+  const int64_t pix0 = (int64_t)n * (per_image4 / C4);        // first pixel of image n
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_image4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 g = g4[(int)(i % C4)];
+    const unsigned pl = (unsigned)i / (unsigned)C4, c4 = (unsigned)i - pl * (unsigned)C4;      // per_image4 < 2^32 (checked by the host)
+    const float4 g = g4[c4];
     const float4 a = x[base + i], b = y[base + i];
     float4 r = make_float4(fmaf(b.x, g.x, a.x), fmaf(b.y, g.y, a.y), fmaf(b.z, g.z, a.z), fmaf(b.w, g.w, a.w));
     if (extra) {
@@ -220,25 +222,64 @@ __global__ void __launch_bounds__(256) se_gate_add_kernel(const float4* __restri
       r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
     }
     out[base + i] = r;
+    if (out2) {        // second copy into the leading channels of the next block's concatenation buffer (row pitch out2_s4 float4)
+      out2[(pix0 + pl) * out2_s4 + c4] = r;
+    }
   }
+}
+
+// [a | b] written at channel offset `off4` of rows that are `stride4` float4 wide (the trailing slices of a concatenation
+// buffer whose leading slice was written by the producer of that tensor)
+__global__ void concat2_into_kernel(const float4* __restrict__ a, int a4, const float4* __restrict__ b, int b4, int64_t n4,
+                                    float4* __restrict__ out, int stride4, int off4) {
+  const int t4 = a4 + b4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / t4;
+    const int q = (int)(i - pix * t4);
+    const float4 v = q < a4 ? __ldcs(a + pix * a4 + q) : __ldcs(b + pix * b4 + (q - a4));
+    out[pix * stride4 + off4 + q] = v;
+  }
+}
+
+extern "C" int gdb_concat2_into(const float* a, int Ca, const float* b, int Cb, int64_t npix, float* out, int out_channels, int out_offset,
+                                void* stream) {
+  GDB_REQUIRE(a && b && out && npix > 0 && Ca > 0 && Cb > 0, GDB_E_BADARG, "gdb_concat2_into: bad argument");
+  GDB_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0 && out_channels % 4 == 0 && out_offset % 4 == 0 && out_offset >= 0 &&
+                  out_offset + Ca + Cb <= out_channels,
+              GDB_E_BADARG, "gdb_concat2_into: channel counts / offset must be multiples of 4 and fit the row");
+  GDB_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), GDB_E_ALIGN, "gdb_concat2_into: pointers must be 16-byte aligned");
+  const int64_t n4 = npix * ((Ca + Cb) / 4);
+  int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 16);
+  concat2_into_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), Ca / 4, reinterpret_cast<const float4*>(b),
+                                                             Cb / 4, n4, reinterpret_cast<float4*>(out), out_channels / 4, out_offset / 4);
+  return cuda_check("gdb_concat2_into");
 }
 
 extern "C" int gdb_se_gate_add(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
                                int64_t S, int C, int chunks, float* partial, float* out, void* stream) {
+  return gdb_se_gate_add_cat(x, y, w1, w2, R, extra, N, S, C, chunks, partial, out, nullptr, 0, stream);
+}
+
+extern "C" int gdb_se_gate_add_cat(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
+                                   int64_t S, int C, int chunks, float* partial, float* out, float* out2, int out2_channels, void* stream) {
   GDB_REQUIRE(x && y && w1 && w2 && partial && out && N > 0 && S > 0 && chunks > 0 && R > 0 && R <= 256, GDB_E_BADARG, "gdb_se_gate_add: bad argument");
+  GDB_REQUIRE(!out2 || (aligned16(out2) && out2_channels % 4 == 0 && out2_channels >= C), GDB_E_BADARG,
+              "gdb_se_gate_add_cat: out2 must be 16-byte aligned with a row of out2_channels >= C floats (multiple of 4)");
   GDB_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, GDB_E_BADARG, "gdb_se_gate_add: C must be a multiple of 4 in [4, 1024]");
   GDB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(out) && aligned16(partial) && (!extra || aligned16(extra)), GDB_E_ALIGN,
               "gdb_se_gate_add: pointers must be 16-byte aligned");
   dim3 grid1(chunks, (unsigned)N);
   channel_sum_kernel<<<grid1, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(y), C / 4, S, chunks, reinterpret_cast<float4*>(partial));
   const int64_t per4 = S * (C / 4);
+  GDB_REQUIRE(per4 < ((int64_t)1 << 32), GDB_E_UNSUPPORTED, "gdb_se_gate_add: more than 2^32 float4 per image");
   int bx = (int)std::min<int64_t>((per4 + 255) / 256, std::max<int64_t>(1, (int64_t)sm_count() * 16 / N));
   dim3 grid2(bx, (unsigned)N);
   const int smem = (2 * C + ((R + 3) & ~3)) * (int)sizeof(float);
   // hid is padded to a multiple of 4 floats so that gate stays float4-aligned
   se_gate_add_kernel<<<grid2, 256, smem, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), partial,
                                                                chunks, 1.f / (float)S, w1, w2, R, reinterpret_cast<const float4*>(extra), C,
-                                                               per4, reinterpret_cast<float4*>(out));
+                                                               per4, reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out2),
+                                                               out2_channels / 4);
   return cuda_check("gdb_se_gate_add");
 }
 

@@ -257,7 +257,8 @@ def gate_add(x: Tensor, y: Tensor, gate: Tensor, extra: Optional[Tensor] = None)
     return out
 
 
-def se_gate_add(x: Tensor, y: Tensor, w1: Tensor, w2: Tensor, extra: Optional[Tensor] = None, chunks: int = 64) -> Tensor:
+def se_gate_add(x: Tensor, y: Tensor, w1: Tensor, w2: Tensor, extra: Optional[Tensor] = None, chunks: int = 64,
+                cat_out: Optional[Tensor] = None) -> Tensor:
     """out = x + y * sigmoid(w2 @ relu(w1 @ mean_hw(y))) (+ extra): the squeeze-excite gate of a dense block and its residual
     (decoder_rdn.py:31-41) as two launches - channel sums of y, then one kernel that finishes the gate in its prologue."""
     _dev(x, y, w1, w2, extra)
@@ -271,9 +272,28 @@ def se_gate_add(x: Tensor, y: Tensor, w1: Tensor, w2: Tensor, extra: Optional[Te
     partial = torch.empty((N, chunks, Cc), device=x.device, dtype=torch.float32)
     out = torch.empty_like(x)
     lib = _lib.load()
-    _lib.check(lib.gdb_se_gate_add(x.data_ptr(), y.data_ptr(), _f32(w1).data_ptr(), _f32(w2).data_ptr(), R, _p(extra), N, S, Cc, chunks,
-                                   partial.data_ptr(), out.data_ptr(), _stream()), "gdb_se_gate_add")
+    cat_c = 0
+    if cat_out is not None:      # (N, Ccat, *spatial) channels-last: the result is also written into its first C channels
+        _dev(cat_out)
+        if not (_is_cl(cat_out) and cat_out.shape[0] == N and cat_out.shape[2:] == x.shape[2:] and cat_out.shape[1] >= Cc and cat_out.shape[1] % 4 == 0):
+            raise _lib.GdbError("se_gate_add: cat_out must be a dense channels-last fp32 buffer of x's batch / spatial size with >= C channels")
+        cat_c = cat_out.shape[1]
+    _lib.check(lib.gdb_se_gate_add_cat(x.data_ptr(), y.data_ptr(), _f32(w1).data_ptr(), _f32(w2).data_ptr(), R, _p(extra), N, S, Cc, chunks,
+                                       partial.data_ptr(), out.data_ptr(), _p(cat_out), cat_c, _stream()), "gdb_se_gate_add")
     return out
+
+
+def concat_into(buf: Tensor, offset: int, a: Tensor, b: Tensor) -> Tensor:
+    """buf[:, offset : offset + Ca + Cb] = cat((a, b), 1) for dense channels-last fp32 maps (buf's leading channels were written
+    by the producer of that tensor, see se_gate_add(cat_out=...)).  Returns buf."""
+    _dev(buf, a, b)
+    if not all(_is_cl(t) and t.shape[1] % 4 == 0 and t.shape[0] == buf.shape[0] and t.shape[2:] == buf.shape[2:] for t in (buf, a, b)) \
+            or offset % 4 or offset + a.shape[1] + b.shape[1] > buf.shape[1]:
+        raise _lib.GdbError("concat_into needs dense channels-last fp32 maps of one size with C % 4 == 0 that fit the buffer")
+    npix = buf.numel() // buf.shape[1]
+    _lib.check(_lib.load().gdb_concat2_into(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], npix, buf.data_ptr(), buf.shape[1], offset,
+                                            _stream()), "gdb_concat2_into")
+    return buf
 
 
 def concat_channels(a: Tensor, b: Tensor, c: Optional[Tensor] = None) -> Tensor:

@@ -279,6 +279,13 @@ int gdb_gate_add(const float* x, const float* y, const float* gate, const float*
  * row-major (the nn.Linear weights, no bias); partial (N,chunks,C) is scratch for the fixed-order channel sums of y.    */
 int gdb_se_gate_add(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
                     int64_t S, int C, int chunks, float* partial, float* out, void* stream);
+/* gdb_se_gate_add that also writes its result into the leading C channels of out2, a channels-last buffer with rows of
+ * out2_channels floats (the next dense block's concatenation buffer: its h slice is then never copied); out2 may be null.
+ * gdb_concat2_into fills the slices behind it: out[pix, out_offset : out_offset + Ca + Cb] = [a | b].                  */
+int gdb_se_gate_add_cat(const float* x, const float* y, const float* w1, const float* w2, int R, const float* extra, int64_t N,
+                        int64_t S, int C, int chunks, float* partial, float* out, float* out2, int out2_channels, void* stream);
+int gdb_concat2_into(const float* a, int Ca, const float* b, int Cb, int64_t npix, float* out, int out_channels, int out_offset,
+                     void* stream);
 /* Channel concatenation of channels-last maps over npix pixels: out (npix, Ca+Cb+Cc) = [a | b | c] (c may be null with
  * Cc = 0): the inputs of the dense block's second and third convolutions (decoder_rdn.py:36-41).                          */
 int gdb_concat3(const float* a, int Ca, const float* b, int Cb, const float* c, int Cc, int64_t npix, float* out, void* stream);

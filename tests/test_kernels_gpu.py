@@ -387,6 +387,14 @@ def test_glue_epilogues_match_torch():
     gd = torch.sigmoid(torch.relu(big.double().mean((2, 3)) @ w1.double().t()) @ w2.double().t())
     assert _md(ops.se_gate_add(hx, big, w1, w2), hx.double() + big.double() * gd[:, :, None, None]) <= 2e-6
     assert _md(ops.se_gate_add(hx, big, w1, w2, extra=big, chunks=5), hx.double() + big.double() * gd[:, :, None, None] + big.double()) <= 2e-6
+    # ... and written a second time into the leading channels of the next block's concatenation buffer, whose other slices
+    # concat_into fills
+    buf = torch.full((2, 50, 70, 64 + 8 + 32), float("nan"), device=DEV).permute(0, 3, 1, 2)
+    out_c = ops.se_gate_add(hx, big, w1, w2, cat_out=buf)
+    assert torch.equal(out_c, ops.se_gate_add(hx, big, w1, w2)) and torch.equal(buf[:, :64], out_c)
+    a8b = torch.randn(2, 8, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    b32 = torch.randn(2, 32, 50, 70, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    assert ops.concat_into(buf, 64, a8b, b32) is buf and torch.equal(buf, torch.cat((out_c, a8b, b32), 1))
     w1b, w2b = (torch.randn(2, 32, generator=g) * 0.5).to(DEV), (torch.randn(32, 2, generator=g) * 0.5).to(DEV)      # R = 2: padded hid
     gd = torch.sigmoid(torch.relu(y.double().mean((2, 3)) @ w1b.double().t()) @ w2b.double().t())
     assert _md(ops.se_gate_add(lat, y, w1b, w2b), lat.double() + y.double() * gd[:, :, None, None]) <= 2e-6
