@@ -73,8 +73,25 @@ SIGNATURES = {
     "gdb_assemble_output": (c_i, [c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
 }
 
+ABI_VERSION = 2   # include/gdb_nerf_b200.h GDB_ABI_VERSION: bumped whenever an exported signature changes
+
 _lock = threading.Lock()
 _lib = None
+
+
+def _check_fresh() -> None:
+    """The library must have been built from the sources next to it: the build stamp (digest of csrc/ + the header, written
+    by gdb_nerf_b200.build, git-ignored like the library) is compared with the digest of the sources on disk.  A stale
+    binary whose argument lists no longer match the ctypes signatures would otherwise corrupt pointers silently."""
+    if os.environ.get("GDB_SKIP_DIGEST_CHECK") == "1":
+        return
+    from . import build as _build
+    if not os.path.isdir(_build.CSRC):          # binary-only deployment: nothing to compare with
+        return
+    stamp = open(_build.STAMP).read().strip() if os.path.exists(_build.STAMP) else None
+    if stamp != _build._digest():
+        raise GdbError(f"{LIB_PATH} is stale (built from different sources than gdb_nerf_b200/csrc): "
+                       "rebuild with `python -m gdb_nerf_b200.build`")
 
 
 class GdbError(RuntimeError):
@@ -93,14 +110,15 @@ def load() -> C.CDLL:
             raise GdbError(
                 f"{LIB_PATH} is missing: build it with `python -m gdb_nerf_b200.build` "
                 "(there is no CPU or PyTorch fallback for the rendering path)")
+        _check_fresh()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
         got = lib.gdb_abi_version()
-        if got != 1:
-            raise GdbError(f"ABI version mismatch: library {got}, binding 1")
+        if got != ABI_VERSION:
+            raise GdbError(f"ABI version mismatch: library {got}, binding {ABI_VERSION}; rebuild with `python -m gdb_nerf_b200.build`")
         _lib = lib
     return _lib
 

@@ -539,11 +539,10 @@ static int launch_coarse(const CoarseParams& p, cudaStream_t st, const char* wha
   using ML = MlpLayout<FEAT_DIM>;
   auto kern = coarse_kernel<FEAT_DIM, V, BWD>;
   const size_t smem = (size_t)2 * ((ML::TOTAL + 31) & ~31) * sizeof(float);
-  static bool ready = false;
-  if (!ready) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt_in_smem(opt, kern, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B): %s", what, smem, cudaGetErrorString(e));
-    ready = true;
   }
   const int nwarps = 4;
   const int G = 32 / p.S;

@@ -34,15 +34,34 @@ inline int cuda_check(const char* what) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Per-device caches: one process may drive several GPUs (nn.DataParallel, render_sweep(device=...)), and both the SM count and
+// the dynamic shared-memory opt-in of a kernel belong to ONE device.
+constexpr int GDB_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (GDB_MAX_DEVICES - 1);
+}
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[GDB_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize, remembered per (kernel = owner of the SmemOptIn, device)
+struct SmemOptIn {
+  int bytes[GDB_MAX_DEVICES] = {0};
+};
+template <class K>
+inline cudaError_t opt_in_smem(SmemOptIn& s, K kern, int bytes) {
+  const int dev = current_device();
+  if (bytes <= s.bytes[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) s.bytes[dev] = bytes;
+  return e;
 }
 
 // ------------------------------------------------------------ camera block --

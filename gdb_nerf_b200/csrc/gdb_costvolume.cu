@@ -727,7 +727,6 @@ __global__ void __launch_bounds__(PH_THREADS) prob_head_split_kernel(const float
   if (tid == 0) {
     const int prev = atomicAdd(counters + tile, 1);
     s_last = prev == NCH - 1;
-    if (s_last) counters[tile] = 0;                                    // every chunk has arrived: ready for the next launch
   }
   __syncthreads();
   if (!s_last) return;
@@ -903,6 +902,12 @@ extern "C" int gdb_prob_head_depth_range_split_fwd(const float* y_cl, const floa
   GDB_REQUIRE((nchunks - 1) * per < D, GDB_E_BADARG, "gdb_prob_head_depth_range_split_fwd: %d chunks of %d planes leave one empty (D = %d)",
               nchunks, per, D);
   dim3 grid((w + PH_TX - 1) / PH_TX, (h + PH_TY - 1) / PH_TY, B * nchunks);
+  // the arrival counters are zeroed by every call (a memset node, legal inside stream capture): an aborted launch or a
+  // recycled buffer can never leave a stale count behind
+  {
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)grid.x * grid.y * B, as_stream(stream));
+    if (e != cudaSuccess) return fail((int)e, "gdb_prob_head_depth_range_split_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
   prob_head_split_kernel<<<grid, PH_THREADS, 0, as_stream(stream)>>>(y_cl, weight, depth_range, rh, rw, B, D, h, w, nchunks, ci_scale, inv_depth,
                                                                      reinterpret_cast<float4*>(scratch), counters, depth, ci, vol_range);
   return cuda_check("gdb_prob_head_depth_range_split_fwd");
@@ -919,11 +924,10 @@ extern "C" int gdb_prob_head_depth_range_fwd(const float* y_cl, const float* wei
   GDB_REQUIRE(aligned16(y_cl) && aligned16(weight), GDB_E_ALIGN, "gdb_prob_head_depth_range_fwd: y / weight must be 16-byte aligned");
   const int smem = (3 * PH_PLANE + 54) * 16 + D * PH_THREADS * 4;
   GDB_REQUIRE(smem <= 227 * 1024, GDB_E_UNSUPPORTED, "gdb_prob_head_depth_range_fwd: D=%d needs %d B of shared memory", D, smem);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(prob_head_depth_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt_in_smem(opt, prob_head_depth_range_kernel, smem);
     if (e != cudaSuccess) return fail((int)e, "gdb_prob_head_depth_range_fwd: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e));
-    configured = smem;
   }
   dim3 grid((w + PH_TX - 1) / PH_TX, (h + PH_TY - 1) / PH_TY, B);
   prob_head_depth_range_kernel<<<grid, PH_THREADS, smem, as_stream(stream)>>>(y_cl, weight, depth_range, rh, rw, B, D, h, w, ci_scale, inv_depth,

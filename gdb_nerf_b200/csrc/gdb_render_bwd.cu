@@ -694,11 +694,10 @@ static int launch_render_bwd(const RenderBwdParams& q, cudaStream_t st) {
   using ML = MlpLayout<FEAT_DIM>;
   auto kern = render_bwd_kernel<BS, FEAT_DIM, V>;
   const size_t smem = (size_t)2 * ((ML::TOTAL + 31) & ~31) * sizeof(float);
-  static bool ready = false;
-  if (!ready) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt_in_smem(opt, kern, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "gdb_render_fused_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-    ready = true;
   }
   const int nwarps = 4;
   const int G = 32 / q.f.max_samples;

@@ -767,11 +767,10 @@ template <int BS, int FEAT_DIM, int V, bool SPLIT>
 static int launch_render_tc(const RenderParams& p, cudaStream_t st) {
   using C = TcCfg<BS, FEAT_DIM, V, SPLIT>;
   auto kern = render_tc_kernel<BS, FEAT_DIM, V, SPLIT>;
-  static bool ready = false;
-  if (!ready) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt_in_smem(opt, kern, C::SMEM);
     if (e != cudaSuccess) return fail((int)e, "gdb_render_fused_fwd(tc): cudaFuncSetAttribute(%d B): %s", C::SMEM, cudaGetErrorString(e));
-    ready = true;
   }
   const int G = 32 / p.max_samples;
   const long NB = (long)p.B * p.Hb * p.Wb;

@@ -811,11 +811,10 @@ static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   static_assert(C::SMEM <= 227 * 1024, "shared memory plan");
   auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG, TAPS>;
-  static bool ready = false;
-  if (!ready) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt_in_smem(opt, kern, C::SMEM);
     if (e != cudaSuccess) return fail((int)e, "gdb_render_fused_fwd(tc2): cudaFuncSetAttribute(%d B): %s", C::SMEM, cudaGetErrorString(e));
-    ready = true;
   }
   if ((long)p.Wb * C::QL >= (1 << 14))
     return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): bundle map width %d too large for the packed tap stride", p.Wb);

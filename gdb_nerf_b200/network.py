@@ -61,7 +61,7 @@ class DepthNet(nn.Module):
             CoarseNeRF(config.nerf.nerf_hidden_dims, voxel_dim, self.feat_dims[i], config.nerf.viewdir_agg)
             for i in range(self.num_stages - 1)])
 
-    def forward_train(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far):
+    def forward_train(self, src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far, coarse: bool = True):
         """Training-mode cascade (depth_net.py:118-198 with self.training): the CNNs run as plain modules (batch-norm
         in batch-statistics mode, autograd), K1 / K2 through their forward+backward kernel pairs, and every stage but
         the last also renders the coarse supervision image (row a14)."""
@@ -81,13 +81,14 @@ class DepthNet(nn.Module):
             vol_list.append(vol_range)
             volume_list.append(volume)
             depth_range = ci
-            if s < self.num_stages - 1:
+            if s < self.num_stages - 1 and coarse:
                 src_ints_s = src_ints.clone()
                 src_ints_s[..., :2, :] *= self.feat_scales[s]
                 tar_ints_s = tar_ints.clone()
                 tar_ints_s[:, :2, :] *= self.vol_scales[s]
                 blend_rgbs.append(AG.coarse_render_train(self.nerfs[s], volume, feats, src_images, src_exts, src_ints_s, tar_exts,
                                                          tar_ints_s, near_far, ci, vol_range, self.num_samples[s], self.inv_depth[s]))
+            if s < self.num_stages - 1:
                 up = self.vol_scales[s + 1] / self.vol_scales[s]
                 depth_range = F.interpolate(ci, scale_factor=up, mode="bilinear", align_corners=False)
         return mvs_depths, range_list, vol_list, volume_list, blend_rgbs
@@ -168,12 +169,26 @@ class Network(nn.Module):
         # "modules": the plain nn.Module graph in the reference's NCHW layout.  Same arithmetic either way.
         self.cnn_mode = "fused"
         self._cl_ready = False
-        # MLP arithmetic inside the fused render kernel:
-        #   2 (default): tcgen05 tensor cores, every operand split into two fp16 planes (hi + lo = 22 bits), three MMAs per
-        #                K step, fp32 accumulation in TMEM - the north star's fp32 class (1e-4), agrees with 0 to ~1e-5
-        #   0: fp32 SIMT (the validation variant of the same class)
-        #   1: tcgen05 with single fp16 operands (the north star's reduced-precision class, 2e-3; measured ~1e-4)
+        # MLP arithmetic inside the fused render kernel (DESIGN.md section 4):
+        #   1 (default): tcgen05 tensor cores, single fp16 operands, fp32 accumulation in TMEM - the north star's
+        #                reduced-precision class (2e-3; measured: fine rgb ~1e-5, decoder features ~3e-4)
+        #   2: tcgen05, every operand split into two fp16 planes (hi + lo = 22 bits), three MMAs per K step - the north
+        #      star's fp32 class (1e-4), agrees with 0 to ~1e-5
+        #   0: fp32 SIMT (the validation variant of the fp32 class)
         self.mlp_precision = 1
+        # derived eval-time parameters (folded batch-norm, width/depth-folded kernels, the packed MLP block) are cached on
+        # the modules keyed on the parameters' version counters; in-place `.data` writes do not bump those, so a
+        # checkpoint load drops every cache explicitly
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_caches())
+
+    def invalidate_caches(self) -> None:
+        """Drop every derived-parameter cache (call after writing parameters through `.data` / `copy_` under no_grad)."""
+        for m in self.modules():
+            for name in [k for k in vars(m) if k.startswith("_gdb_")]:
+                object.__delattr__(m, name)
+            if isinstance(m, NeRF):
+                m._packed, m._packed_key = None, None
+        ops._PH_WEIGHTS.clear()
 
     def _channels_last_params(self) -> None:
         if not self._cl_ready:
@@ -193,10 +208,9 @@ class Network(nn.Module):
         B, V, _, H, W = src_images.shape
         feats = self.feature_net(src_images.flatten(0, 1), levels=self._fpn_levels)
         ms_feats = [f.unflatten(0, (B, V)) for f in feats]
+        # the coarse supervision render only exists in training mode (depth_net.py:181)
         mvs_depths, range_list, vol_list, volume_list, blend_rgbs = self.depth_net.forward_train(
-            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far)
-        if not self.training:
-            blend_rgbs = []
+            src_images, ms_feats, src_exts, src_ints, tar_exts, tar_ints, near_far, coarse=self.training)
         depth_range, vol_range, feat_volume, mvs_depth = range_list[-1], vol_list[-1], volume_list[-1], mvs_depths[-1]
         b = self.b_size
         Hb, Wb = H // b, W // b
@@ -247,6 +261,9 @@ class Network(nn.Module):
             src_ints[..., :2, :] *= self.render_scale
             tar_ints[:, :2, :] *= self.render_scale
 
+        # differentiable route: training mode, or an eval-mode caller that asked for gradients (grad mode on and parameters
+        # that require them) - same kernels' forward+backward pairs, fp32 SIMT MLP; eval under torch.no_grad() (run.py:56)
+        # takes the fast path below
         if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.nerf.parameters()):
             return self._forward_train(src_images, src_exts, src_ints, tar_exts, tar_ints, near_far)
 

@@ -24,11 +24,19 @@ def _stream() -> int:
 
 
 def _dev(*tensors: Tensor) -> None:
+    """Every tensor handed to the library must live on the CURRENT CUDA device: the kernels launch on that device's current
+    stream (one process per GPU is the deployment; a caller driving several GPUs wraps calls in ``torch.cuda.device``)."""
+    cur = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise _lib.GdbError("gdb_nerf_b200 operators need CUDA tensors (no CPU fallback exists)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.GdbError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                                "wrap the call in `with torch.cuda.device(tensor.device):`")
 
 
 def _f32(t: Tensor) -> Tensor:
@@ -156,7 +164,6 @@ def depth_range_from_logits(depth_range: Tensor, logits: Tensor, ci_scale: float
     return depth, ci, vol, prob
 
 
-_PH_COUNTERS: Dict = {}
 _PH_WEIGHTS: Dict = {}
 
 
@@ -197,11 +204,8 @@ def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_sca
     if nch > 1 and B * nch <= 65535:
         # depth axis split over nch CTAs per tile (on-line soft-max partials merged by the tile's last CTA)
         scratch = torch.empty(int(lib.gdb_prob_head_split_scratch_floats(B, h, w, nch)), device=dev, dtype=torch.float32)
-        # one counter set per stream: launches on one stream are serialised, two streams must not share arrival counts
-        key = (dev, int(lib.gdb_prob_head_split_counters(B, h, w)), _stream())
-        counters = _PH_COUNTERS.get(key)
-        if counters is None:      # zero once; the kernel leaves the counters zero
-            counters = _PH_COUNTERS[key] = torch.zeros(key[1], device=dev, dtype=torch.int32)
+        # arrival counters: owned by this call, zeroed by the library (cudaMemsetAsync) in front of the kernel
+        counters = torch.empty(int(lib.gdb_prob_head_split_counters(B, h, w)), device=dev, dtype=torch.int32)
         _lib.check(lib.gdb_prob_head_depth_range_split_fwd(y.data_ptr(), wk.data_ptr(), depth_range.data_ptr(), rh, rw, B, Cc, D, h, w,
                                                            nch, float(ci_scale), int(inv_depth), scratch.data_ptr(), counters.data_ptr(),
                                                            depth.data_ptr(), ci.data_ptr(), vol.data_ptr(), _stream()),

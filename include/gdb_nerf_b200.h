@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GDB_ABI_VERSION 1
+#define GDB_ABI_VERSION 2
 
 #define GDB_E_BADARG  (-1)   /* null pointer / non-positive size            */
 #define GDB_E_UNSUPPORTED (-2) /* parameter combination not instantiated     */

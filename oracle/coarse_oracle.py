@@ -2,7 +2,7 @@
 reference: networks/gdb_nerf/depth_net.py:49-116 `_render_rays`, :301-341 `build_rays`,
 :344-396 `get_img_feat_vectorized`).
 
-Status: TEST REFERENCE.  The product path runs this row on hand-written kernels
+Status: TEST INFRASTRUCTURE (lives under oracle/; only tests import it).  The product path runs this row on hand-written kernels
 (csrc/gdb_coarse.cu through autograd.CoarseRender / coarse_render_train); this PyTorch-operator
 restatement is what tests/test_backward_gpu.py evaluates in float64 on the CPU to check the
 kernels' outputs and gradients.  The arithmetic follows the reference step by step.

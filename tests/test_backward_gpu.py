@@ -220,7 +220,7 @@ def test_training_step_updates_every_trainable_parameter():
 def test_coarse_render_forward_and_backward(inv_depth, V):
     """gdb_coarse_render_fwd/bwd against coarse.coarse_render (depth_net.py:49-116 restated with PyTorch operators,
     itself pinned end-to-end by the reference's blend_rgbs) evaluated in float64 on the CPU."""
-    from gdb_nerf_b200.coarse import coarse_render
+    from oracle.coarse_oracle import coarse_render
     from gdb_nerf_b200.nerf import CoarseNeRF
     from gdb_nerf_b200.synthetic import camera_rig, smooth_images
     B, H, W, Cf, D, S = 2, 32, 40, 32, 16, 8

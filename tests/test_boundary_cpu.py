@@ -52,7 +52,7 @@ def test_header_symbols_are_exported_and_typed():
     for name in declared:
         assert hasattr(lib, name), name
     typed = _lib.load()
-    assert typed.gdb_abi_version() == 1
+    assert typed.gdb_abi_version() == _lib.ABI_VERSION
     assert typed.gdb_last_error_string() is not None
 
 

@@ -44,7 +44,9 @@ def main():
     src = open(srcfile).read().split("\n")
     marks = [(i + 1, l.strip()[:72]) for i, l in enumerate(src) if "=====" in l or "// ---- " in l]
     marks = [(1, "(prologue)")] + marks + [(len(src) + 1, "end")]
-    agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0.0])
+    STALLS = ["stall_long_sb", "stall_barrier", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_mio", "stall_lg",
+              "stall_math", "stall_no_inst", "stall_not_selected", "stall_selected"]
+    agg = collections.defaultdict(lambda: [0.0] * (4 + len(STALLS)))
 
     def num(r, k):
         try:
@@ -60,12 +62,20 @@ def main():
         a[1] += num(r, "# Samples")
         a[2] += num(r, "L1 Tag Requests Global")
         a[3] += num(r, "L1 Wavefronts Shared")
+        for j, k in enumerate(STALLS):
+            a[4 + j] += num(r, k)
     ti, ts = sum(a[0] for a in agg.values()) or 1, sum(a[1] for a in agg.values()) or 1
     print(f"{'phase':72s} {'inst%':>6s} {'smp%':>6s} {'L1 tags':>10s} {'smem wf':>10s}")
     for ph in sorted(agg):
         a = agg[ph]
         print(f"{marks[ph][1]:72s} {100 * a[0] / ti:6.1f} {100 * a[1] / ts:6.1f} {a[2] / 1e6:9.1f}M {a[3] / 1e6:9.1f}M")
     print(f"total warp instructions {ti / 1e6:.1f}M, samples {ts:.0f}")
+    print("stall samples per phase (% of all samples): " + " ".join(k.replace("stall_", "") for k in STALLS))
+    for ph in sorted(agg):
+        a = agg[ph]
+        print(f"{marks[ph][1][:40]:40s} " + " ".join(f"{100 * x / ts:6.1f}" for x in a[4:]))
+    tot = [sum(agg[ph][4 + j] for ph in agg) for j in range(len(STALLS))]
+    print(f"{'total':40s} " + " ".join(f"{100 * x / ts:6.1f}" for x in tot))
 
 
 if __name__ == "__main__":
