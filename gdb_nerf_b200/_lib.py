@@ -47,7 +47,7 @@ SIGNATURES = {
     "gdb_texture_floats": (c_i64, [c_i, c_i, c_i, c_i, c_i]),
     "gdb_prepare_sources": (c_i, [c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f]),
     "gdb_render_fused_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
-                                   c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, C.POINTER(RenderTaps), c_f]),
+                                   c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_i, C.POINTER(RenderTaps), c_f]),
     "gdb_depth_range_from_logits_fwd": (c_i, [c_f, c_i, c_i, c_f, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f,
                                               c_f, c_f]),
     "gdb_prob_head_depth_range_split_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),

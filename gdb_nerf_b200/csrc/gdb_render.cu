@@ -481,7 +481,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
                                     int V, int H, int W, int bundle_size, int feat_dim, int D, int vol_stride, int vol_layout, int max_samples,
                                     int max_mip_level, int inv_depth, int adaptive, int precision, int out_channels_last,
                                     int dec_stride, float* out_feat, float* out_dec, float* out_depth, float* out_opacity,
-                                    const gdb_render_taps* taps, void* stream) {
+                                    int row_lo, int row_hi, const gdb_render_taps* taps, void* stream) {
   GDB_REQUIRE(rgba && tex && vol_cl && depth_range && vol_range && cam && mlp && out_feat && out_depth && out_opacity,
               GDB_E_BADARG, "gdb_render_fused_fwd: null pointer");
   GDB_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, GDB_E_BADARG, "gdb_render_fused_fwd: bad size");
@@ -489,9 +489,15 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               "gdb_render_fused_fwd: image %dx%d not divisible by bundle size %d", H, W, bundle_size);
   GDB_REQUIRE(max_samples >= 1 && max_samples <= 32, GDB_E_BADARG, "gdb_render_fused_fwd: max_samples must be 1..32");
   GDB_REQUIRE(max_mip_level >= 0 && max_mip_level <= 3, GDB_E_UNSUPPORTED, "gdb_render_fused_fwd: max_mip_level must be 0..3");
-  GDB_REQUIRE(precision >= 0 && precision <= 3, GDB_E_UNSUPPORTED,
+  GDB_REQUIRE(precision >= 0 && precision <= 4, GDB_E_UNSUPPORTED,
               "gdb_render_fused_fwd: precision %d not built (0 = fp32 SIMT, 1 = fp16-operand tcgen05 MLP, 2 = split-fp16 tcgen05 MLP, "
-              "3 = first-generation fp16-operand tcgen05 kernel)", precision);
+              "3 = first-generation fp16-operand tcgen05 kernel, 4 = round-1 kernel of 1)", precision);
+  GDB_REQUIRE(row_lo >= 0 && row_hi <= H / bundle_size && row_lo < row_hi, GDB_E_BADARG,
+              "gdb_render_fused_fwd: row range [%d, %d) outside the %d bundle rows", row_lo, row_hi, H / bundle_size);
+  GDB_REQUIRE((row_lo == 0 && row_hi == H / bundle_size) || precision == 1 || precision == 4, GDB_E_UNSUPPORTED,
+              "gdb_render_fused_fwd: a partial row range needs precision 1 or 4 (got %d)", precision);
+  GDB_REQUIRE(!(precision == 1 && out_channels_last) || (aligned16(out_feat) && aligned16(out_dec)), GDB_E_ALIGN,
+              "gdb_render_fused_fwd: channels-last outputs must be 16-byte aligned");
   GDB_REQUIRE(aligned16(rgba) && aligned16(tex) && aligned16(vol_cl) && aligned16(mlp), GDB_E_ALIGN,
               "gdb_render_fused_fwd: rgba/tex/vol/mlp must be 16-byte aligned");
   GDB_REQUIRE(cam_stride == CAM_HEAD + CAM_VIEW * V, GDB_E_BADARG, "gdb_render_fused_fwd: cam_stride %d != %d", cam_stride,
@@ -520,6 +526,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   GDB_REQUIRE(vol_layout == 0 || vol_layout == 1, GDB_E_BADARG, "gdb_render_fused_fwd: vol_layout must be 0 (B,D,Hb,Wb,.) or 1 (B,Hb,Wb,D,.)");
   p.B = B; p.H = H; p.W = W; p.Hb = H / bundle_size; p.Wb = W / bundle_size; p.D = D; p.max_samples = max_samples;
   p.L = max_mip_level; p.inv_depth = inv_depth; p.adaptive = adaptive;
+  p.pix_lo = row_lo * p.Wb; p.pix_hi = row_hi * p.Wb;
   if (vol_layout == 0) {
     p.vol_sx = vol_stride; p.vol_sy = (int64_t)vol_stride * p.Wb; p.vol_sz = p.vol_sy * p.Hb; p.vol_sb = p.vol_sz * D;
   } else {
@@ -531,7 +538,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   p.tex_level[0] = 0;
   for (int k = 1; k <= 3; ++k) p.tex_level[k] = p.tex_level[k - 1] + (int64_t)B * V * (p.Hb >> (k - 1)) * (p.Wb >> (k - 1)) * FPad;
   cudaStream_t st = as_stream(stream);
-  if (precision == 1) return render_tc2_dispatch(p, bundle_size, feat_dim, V, st);
+  if (precision == 1 || precision == 4) return render_tc2_dispatch(p, bundle_size, feat_dim, V, precision == 1 ? 3 : 2, st);
   if (precision >= 2) return render_tc_dispatch(p, bundle_size, feat_dim, V, precision == 2, st);
 #define GDB_R(BSZ, FD, VV) \
   if (bundle_size == BSZ && feat_dim == FD && V == VV) return launch_render<BSZ, FD, VV>(p, st);

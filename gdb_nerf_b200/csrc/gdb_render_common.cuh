@@ -31,6 +31,7 @@ struct RenderParams {
   int vol_stride;      // floats between consecutive voxels of vol (>= 8, multiple of 4)
   int64_t vol_sb, vol_sz, vol_sy, vol_sx;   // float strides of vol over (batch, depth, row, column): layout 0 (B,D,Hb,Wb,.) or 1 (B,Hb,Wb,D,.)
   int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
+  int pix_lo, pix_hi;  // range of bundle indices (row-major over the Hb x Wb bundle map) rendered in every view: the image-tile split
 };
 
 template <int N>
@@ -120,6 +121,6 @@ __device__ __forceinline__ float4 bilerp4(float4 a00, float4 a10, float4 a01, fl
 // tensor-core (tcgen05) variant, gdb_render_tc.cu
 int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int split, cudaStream_t st);
 // second-generation tensor-core variant (fp16 operands), gdb_render_tc2.cu
-int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st);
+int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st);
 
 }  // namespace gdb

@@ -25,120 +25,24 @@
 //    gather iterations / rays / views of the epilogues are rolled: 7.3 k SASS instructions instead of 13.3 k in the first
 //    tcgen05 variant, whose top stall reason was instruction fetch.  The production instantiation (TAPS = false)
 //    carries none of the per-sample parity outputs.
-#include <cuda_fp16.h>
-
-#include "gdb_render_common.cuh"
-
-#include "gdb_tcgen05.cuh"
+#include "gdb_render_tc2.cuh"
 
 namespace gdb {
 
-__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
-__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
-
-template <int BS, int FEAT_DIM, int V, int NG>
-struct Tc2Cfg {
-  using ML = MlpLayout<FEAT_DIM>;
-  static constexpr int BB = BS * BS;
-  static constexpr int F = ML::F;
-  static constexpr int FP = ML::FP;
-  static constexpr int R = 3 * BB;
-  static constexpr int CT = R + F + 8;
-  static constexpr int RFD = R + F + 4;
-  static constexpr int QL = FP / 4;                    // 16-byte quads per texel = lanes per row in the feature fetch
-  static constexpr int IPW = 32 / QL;                  // rows per warp iteration of the feature fetch
-  static constexpr int NIT = (32 + IPW - 1) / IPW;
-  static_assert(F == FP - 1, "the texel has exactly one pad channel (F = feat_dim + 3, feat_dim a multiple of 4)");
-  static_assert(QL % 2 == 1, "the last quad starts a chunk");
-  // operand chunks (a chunk = 8 K values x 128 rows x fp16 = 2 KB)
-  static constexpr int XCH = (F + 1 + 7) / 8;          // [x_v (F) | 1]
-  static constexpr int FDCH = (F + 4 + 7) / 8;         // [featrgb_v (F) | dir_v (4)]
-  static constexpr int SCH = (2 * FP + 7) / 8;         // [var (FP) | mean (FP)]
-  static constexpr int KS_X = (XCH + 1) / 2, KS_FD = (FDCH + 1) / 2, KS_S = (SCH + 1) / 2;   // K steps of 16
-  static constexpr int CH_X = cmax(V * XCH, 9);        // later [h (8) | vox]
-  static constexpr int CH_FD = V * FDCH;
-  static constexpr int CH_S = cmax(SCH, 4);            // later the aggregated vector (4), then img (2)
-  // fp16 weight matrices (bytes), UMMA B layout [K/8][N][8]
-  static constexpr int W_GS = 0;
-  static constexpr int W_GX = W_GS + 32 * KS_S * 32;
-  static constexpr int W_FC = W_GX + 32 * KS_X * 32;
-  static constexpr int W_LR0 = W_FC + 16 * 32 * 2;
-  static constexpr int W_SH = W_LR0 + 64 * 32 * 2;
-  static constexpr int W_0S = W_SH + 16 * 64 * 2;
-  static constexpr int W_0V = W_0S + 64 * 96 * 2;
-  static constexpr int W_END = W_0V + 64 * KS_FD * 32;
-  // fp32 vectors (floats)
-  static constexpr int X_VIEW_W = 0;                   // [4][FP]
-  static constexpr int X_VIEW_B = X_VIEW_W + 4 * FP;   // [FP]
-  static constexpr int X_AGG_W = X_VIEW_B + FP;        // 32
-  static constexpr int X_FC_B = X_AGG_W + 32;          // 16
-  static constexpr int X_W2_W = X_FC_B + 16;           // 64
-  static constexpr int X_FH_B = X_W2_W + 64;           // 8
-  static constexpr int X_SCAL = X_FH_B + 8;            // agg_b, sig_b, w2_b, pad
-  static constexpr int X_END = X_SCAL + 4;
-  static constexpr int VEC_OFF = ((W_END + 127) / 128) * 128;
-  static constexpr int GROUP_OFF = ((VEC_OFF + X_END * 4 + 127) / 128) * 128;
-  // per-group regions (bytes from the group base); S lies after X so that chunk pairs (X[8], S[0]) have a positive stride
-  static constexpr int A_X = 0;
-  static constexpr int A_FD = A_X + CH_X * 2048;
-  static constexpr int A_S = A_FD + CH_FD * 2048;
-  static constexpr int A_END = A_S + CH_S * 2048;
-  static constexpr int CAM_OFF = A_END + 128;          // mbarrier at A_END
-  static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
-  static constexpr int ZERO_OFF = GROUP_OFF + NG * GROUP_BYTES;   // constant chunks after every group
-  static constexpr int ONE_OFF = ZERO_OFF + 2048;
-  static constexpr int SMEM = ONE_OFF + 2048;
-  // per-(row, ray) weighted colours: a warp uses its own rows' 512 B of the first BB chunks of X + FD
-  static_assert(BB <= CH_X + CH_FD, "colour stash must fit in X + FD");
-  static constexpr int NC = F + 10;                    // composited channels: featrgb (F), geometry head (8), depth, opacity
-  static constexpr int NCP = NC <= 32 ? 32 : 64;       // padded row of the transposition stash (swizzled by float4)
-  static_assert(32 * NCP * 4 <= 512 * (CH_X + CH_FD), "compositing stash must fit in the warp's rows of X + FD");
-  // TMEM columns per group
-  static constexpr int TC = cmin((512 / NG) & ~31, 256);
-  static constexpr int TALLOC = NG * TC <= 256 ? 256 : 512;      // tcgen05.alloc takes a power of two
-  static constexpr int NB = TC / 64;                   // 64-column buffers for weight.0
-  static_assert(V * 32 <= TC && NB >= 2, "TMEM column plan");
-  static constexpr int ROUNDS = 1 + (cmax(V - (NB - 1), 0) + NB - 1) / NB;
-  __host__ __device__ static constexpr int round_start(int r) { return r == 0 ? 0 : (NB - 1) + (r - 1) * NB; }
-  __host__ __device__ static constexpr int round_n(int r) { return cmax(0, cmin(r == 0 ? NB - 1 : NB, V - round_start(r))); }
-};
-
-// weights: fp32 packed block (global) -> fp16 UMMA B operand [Kpad/8][N][8]; value(k, n) supplied by the caller
-template <class Fn>
-__device__ __forceinline__ void stage_b2(unsigned char* dst, int N, int Kpad, int tid, int nthreads, Fn value) {
-  for (int i = tid; i < (Kpad / 8) * N; i += nthreads) {
-    const int c = i / N, n = i - c * N;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = value(c * 8 + j, n);
-    *reinterpret_cast<uint4*>(dst + (size_t)i * 16) =
-        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-  }
-}
-
-// one K step (16) of D (+)= A B: the two A chunks may live anywhere (a1 > a0), B K steps are contiguous
-__device__ __forceinline__ void mma_step(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b_addr, int N, uint32_t accumulate) {
-  umma_f16(d_tmem, umma_desc(a0, a1 - a0, 128), umma_desc(b_addr, N * 16, 128), umma_idesc_f16(N), accumulate);
-}
-// `nch` consecutive chunks starting at `a` (odd counts pair the last chunk with the zero chunk)
-__device__ __forceinline__ void mma_chunks(uint32_t d_tmem, uint32_t a, int nch, uint32_t zero_chunk, uint32_t b_addr, int N,
-                                           uint32_t accumulate) {
-  for (int ks = 0; 2 * ks < nch; ++ks) {
-    const uint32_t a0 = a + ks * 4096;
-    const uint32_t a1 = (2 * ks + 1 < nch) ? a0 + 2048 : zero_chunk;
-    mma_step(d_tmem, a0, a1, b_addr + ks * 2 * (N * 16), N, (ks > 0 || accumulate) ? 1u : 0u);
-  }
-}
-
-// F.normalize(eps = 1e-12) with a reciprocal square root (2 ulp): the result feeds fp16 operands
-__device__ __forceinline__ void unit3_fast(float& x, float& y, float& z) {
-  const float inv = rsqrtf(fmaxf(x * x + y * y + z * z, 1e-24f));
-  x *= inv; y *= inv; z *= inv;
-}
-__device__ __forceinline__ float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
-
 // TAPS: the per-sample parity outputs (tests); the production instantiation carries none of that code or state
-template <int BS, int FEAT_DIM, int V, int NG, bool TAPS>
+//
+// GEN = 2: the round-1 kernel as measured in profiles/r01_* (kept for A/B, `precision = 4`).
+// GEN = 3: the same arithmetic (bit-identical results) restructured against the long-scoreboard stalls that ncu showed to be
+//   the top stall reason (37 % of all warp samples, profiles/r02_k3_phase_profile_gen2.txt):
+//    * per-(row, view) fetch descriptors travel through the row's own 48 bytes of the X_v operand region (three LDS.128 of
+//      a fetch lane instead of thirteen warp shuffles; 36 registers freed for loads in flight),
+//    * the gathers are issued in batches as predicated loads (no branches between them): level-0 taps of ALL views, then
+//      level-1 taps of all views (FB = 1), or all 8 V taps at once (FB = 2); twelve colour taps per (row, ray) at once;
+//      the voxel taps at once; the depth ranges of the NEXT tile are prefetched under the current tile,
+//    * compositing and the output stores run on float4 quads (lane = (bundle, channel quad), STG.128 into the channels-last
+//      decoder input), the fine colours are stashed component-wise so that a lane sums and stores one float4 of a bundle,
+//    * the colour pass reads its per-row parameters from shared memory (two LDS.128) instead of 5 + V shuffles.
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   using ML = typename C::ML;
@@ -156,43 +60,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
 
   // ---- one-time setup: weights -> smem (fp16 B operands + fp32 vectors), constant chunks, mbarriers, TMEM
   {
-    const float* m = p.mlp;
-    const int nt = blockDim.x;
-    // [var | mean] rows of global_fc: k < F -> var_k, FP <= k < FP + F -> mean_(k - FP)
-    stage_b2(smem + C::W_GS, 32, C::KS_S * 16, tid, nt, [&](int k, int n) {
-      return k < F ? __ldg(m + ML::GLOB_W + (size_t)(F + k) * 32 + n)
-                   : (k >= FP && k < FP + F ? __ldg(m + ML::GLOB_W + (size_t)(2 * F + k - FP) * 32 + n) : 0.f);
-    });
-    // [x_v | 1]: the constant-one slot carries global_fc's bias
-    stage_b2(smem + C::W_GX, 32, C::KS_X * 16, tid, nt, [&](int k, int n) {
-      return k < F ? __ldg(m + ML::GLOB_W + (size_t)k * 32 + n) : (k == F ? __ldg(m + ML::GLOB_B + n) : 0.f);
-    });
-    stage_b2(smem + C::W_FC, 16, 32, tid, nt, [&](int k, int n) { return __ldg(m + ML::FC_W + k * 16 + n); });
-    // [vox (8) | img (16) | 1 | 0]
-    stage_b2(smem + C::W_LR0, 64, 32, tid, nt, [&](int k, int n) {
-      return k < 24 ? __ldg(m + ML::LR0_W + k * 64 + n) : (k == 24 ? __ldg(m + ML::LR0_B + n) : 0.f);
-    });
-    // [sigma | feat_head] as one N = 16 operand: n = 0 sigma, n = 1..8 geometry head
-    stage_b2(smem + C::W_SH, 16, 64, tid, nt, [&](int k, int n) {
-      return n == 0 ? __ldg(m + ML::SIG_W + k) : (n <= 8 ? __ldg(m + ML::FH_W + k * 8 + (n - 1)) : 0.f);
-    });
-    // [h (64) | vox (8) | img (16) | 1 | 0]
-    stage_b2(smem + C::W_0S, 64, 96, tid, nt, [&](int k, int n) {
-      return k < 88 ? __ldg(m + ML::W0_W + (size_t)k * 64 + n) : (k == 88 ? __ldg(m + ML::W0_B + n) : 0.f);
-    });
-    // [featrgb_v (F) | dir_v (4) | 0]
-    stage_b2(smem + C::W_0V, 64, C::KS_FD * 16, tid, nt,
-             [&](int k, int n) { return k < F + 4 ? __ldg(m + ML::W0_W + (size_t)(88 + k) * 64 + n) : 0.f; });
-    for (int i = tid; i < 5 * FP; i += nt) vec[C::X_VIEW_W + i] = m[ML::VIEW_W + i];   // W [4][FP] + b [FP]
-    for (int i = tid; i < 32; i += nt) vec[C::X_AGG_W + i] = m[ML::AGG_W + i];
-    for (int i = tid; i < 16; i += nt) vec[C::X_FC_B + i] = m[ML::FC_B + i];
-    for (int i = tid; i < 64; i += nt) vec[C::X_W2_W + i] = m[ML::W2_W + i];
-    for (int i = tid; i < 8; i += nt) vec[C::X_FH_B + i] = m[ML::FH_B + i];
-    if (tid == 0) { vec[C::X_SCAL + 0] = m[ML::AGG_B]; vec[C::X_SCAL + 1] = m[ML::SIG_B]; vec[C::X_SCAL + 2] = m[ML::W2_B]; }
-    for (int i = tid; i < 128; i += nt) {
-      *reinterpret_cast<uint4*>(smem + C::ZERO_OFF + i * 16) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(smem + C::ONE_OFF + i * 16) = make_uint4(0x3C00u, 0, 0, 0);    // fp16 1.0 in K slot 0
-    }
+    tc2_stage_weights<C>(smem, vec, p.mlp, tid, blockDim.x);
     if (row == 0) mbar_init(mbar, 1);
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -219,7 +87,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   const int HW = p.Hb * p.Wb;
   const int ns = p.max_samples;
   const int G = 32 / ns;                                   // bundles per warp
-  const int tiles_pv = (HW + 4 * G - 1) / (4 * G);         // tiles per target view (a tile = 4 warps x G bundles, one view)
+  const int pix_lo = p.pix_lo, pix_hi = p.pix_hi;          // bundle range of every view this launch renders (image-tile split)
+  const int tiles_pv = (pix_hi - pix_lo + 4 * G - 1) / (4 * G);   // tiles per target view (a tile = 4 warps x G bundles, one view)
   const int tiles = p.B * tiles_pv;
   const int bl = lane / ns, slot = lane - bl * ns;
   const int seg_base = bl * ns;
@@ -234,6 +103,18 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   const float4* tex4 = reinterpret_cast<const float4*>(p.tex);
   const float inv_Wb = 1.f / (float)p.Wb, inv_Hb = 1.f / (float)p.Hb, two_W = 2.f / (float)p.W, two_H = 2.f / (float)p.H;
 
+  // (near, far, vol_near, vol_far) of my row's bundle in tile `t`
+  auto load_ranges = [&](int t) -> float4 {
+    const int tb = t / tiles_pv;
+    const int praw = pix_lo + ((t - tb * tiles_pv) * 4 + wq) * G + bl;
+    const int px = (bl < G && praw < pix_hi) ? praw : pix_lo;
+    const float* dr = p.depth_range + (size_t)(tb * 2) * HW + px;
+    const float* vr = p.vol_range + (size_t)(tb * 2) * HW + px;
+    return make_float4(__ldg(dr), __ldg(dr + HW), __ldg(vr), __ldg(vr + HW));
+  };
+  float4 rng_next = make_float4(1.f, 2.f, 1.f, 2.f);
+  if (GEN == 3 && (int)(blockIdx.x * NG + g) < tiles) rng_next = load_ranges(blockIdx.x * NG + g);
+
 #pragma unroll 1
   for (int tile = blockIdx.x * NG + g; tile < tiles; tile += gridDim.x * NG) {
     const int b = tile / tiles_pv;                         // uniform over the group
@@ -243,16 +124,16 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       group_sync(g);
       cur_b = b;
     }
-    const int pix_warp0 = ((tile - b * tiles_pv) * 4 + wq) * G;       // first bundle of my warp
+    const int pix_warp0 = pix_lo + ((tile - b * tiles_pv) * 4 + wq) * G;       // first bundle of my warp
     const int pix_raw = pix_warp0 + bl;
-    const bool has_bundle = bl < G && pix_raw < HW;
-    const int pix = has_bundle ? pix_raw : 0;
+    const bool has_bundle = bl < G && pix_raw < pix_hi;
+    const int pix = has_bundle ? pix_raw : pix_lo;
     const int bidx = b * HW + pix;
     const int yb = pix / p.Wb, xb = pix - yb * p.Wb;
 
     // =========================== P0: sample placement (thread = row) ===========================
-    float nr = p.depth_range[(size_t)(b * 2 + 0) * HW + pix], fr_ = p.depth_range[(size_t)(b * 2 + 1) * HW + pix];
-    float vn = p.vol_range[(size_t)(b * 2 + 0) * HW + pix], vf = p.vol_range[(size_t)(b * 2 + 1) * HW + pix];
+    const float4 rng = GEN == 3 ? rng_next : load_ranges(tile);
+    float nr = rng.x, fr_ = rng.y, vn = rng.z, vf = rng.w;
     const int n = bundle_sample_count(nr, fr_, head[CAM_MINIV], ns, p.inv_depth, p.adaptive);
     if (p.inv_depth) { nr = fdiv(1.f, nr); fr_ = fdiv(1.f, fr_); vn = fdiv(1.f, vn); vf = fdiv(1.f, vf); }
     const bool active = has_bundle && slot < n;
@@ -289,6 +170,25 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       int x1 = min(x0 + 1, p.Wb - 1), y1 = min(y0 + 1, p.Hb - 1), z1 = min(z0 + 1, p.D - 1);
       const float* vb_ = p.vol + (size_t)b * p.vol_sb;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+      if constexpr (GEN == 3) {
+        // all (non-zero-weight) taps in flight at once; same accumulation order as below
+        float4 tl[8], th[8];
+        float tw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
+          tw[k] = ((k & 1) ? tx : 1.f - tx) * ((k & 2) ? ty : 1.f - ty) * ((k & 4) ? tz : 1.f - tz);
+          const float4* tp = reinterpret_cast<const float4*>(vb_ + zz * p.vol_sz + yy * p.vol_sy + xx * p.vol_sx);
+          tl[k] = ldg4_if(tp, tw[k] != 0.f);
+          th[k] = ldg4_if(tp + 1, tw[k] != 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (tw[k] != 0.f) {
+            lo = f4_scale_add(lo, tl[k], tw[k]);
+            hi = f4_scale_add(hi, th[k], tw[k]);
+          }
+      } else
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         int xx = (k & 1) ? x1 : x0, yy = (k & 2) ? y1 : y0, zz = (k & 4) ? z1 : z0;
@@ -362,10 +262,166 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           tp[0] = ddx; tp[1] = ddy; tp[2] = ddz; tp[3] = d_dir[v][3];
         }
       }
+      if constexpr (GEN == 3) {
+        // the descriptor of (row, view) travels through the row's own 3 x 16 bytes of the X_v operand region: the fetch
+        // lanes of the row read it there and overwrite it with the operand afterwards
+        static_assert(C::XCH >= 3, "three 16-byte slots per (row, view)");
+        unsigned char* dp = sX + (v * C::XCH) * 2048 + row * 16;
+        *reinterpret_cast<uint4*>(dp) = make_uint4((uint32_t)d_a0[v], (uint32_t)d_a1[v], d_pk[v], __float_as_uint(d_fr[v]));
+        *reinterpret_cast<float4*>(dp + 2048) = make_float4(d_fu0[v], d_fv0[v], d_fu1[v], d_fv1[v]);
+        *reinterpret_cast<float4*>(dp + 4096) = make_float4(d_dir[v][0], d_dir[v][1], d_dir[v][2], d_dir[v][3]);
+      }
+    }
+    if constexpr (GEN == 3) {
+      // the depth ranges of my next tile, in flight underneath this tile
+      const int tn = tile + gridDim.x * NG;
+      if (tn < tiles) rng_next = load_ranges(tn);
     }
 
     // ================= P2: mip-mapped feature fetch, lane = (row, quad) =================
     // writes FD_v = [featrgb_v | dir_v], X_v = [x_v | 1] (nerf.py:69-71) and S = [var | mean] over views (nerf.py:73)
+    if constexpr (GEN == 3) {
+      __syncwarp();                       // the descriptors of my warp's 32 rows are in shared memory
+#pragma unroll 1
+      for (int it = 0; it < C::NIT; ++it) {
+        const int src_raw = it * IPW + gr;
+        const bool ok = glane && src_raw < 32;
+        const int src = min(src_raw, 31);
+        const int orow16 = (wq * 32 + src) * 16;
+        const int64_t srow_g = TAPS ? __shfl_sync(full, srow, src) : 0;
+        const unsigned char* dsc = sX + orow16;
+        const float4* tq = tex4 + (glane ? gq : 0);
+        // four taps of one mip level of one view as predicated loads
+        auto taps4 = [&](const uint4 q0, int level, float4(&t)[4]) {
+          const uint32_t pk = q0.z;
+          const int a = level ? (int)q0.y : (int)q0.x;
+          const int dy = level ? (int)((pk >> 14) & 0x3FFF) : (int)(pk & 0x3FFF);
+          const int dx = (int)((pk >> (28 + level)) & 1) * QL;
+          const bool pr = ok && (pk >> 31) && (level == 0 || ((pk >> 30) & 1));
+          const float4* b0 = tq + a;
+          t[0] = ldg4_if(b0, pr);
+          t[1] = ldg4_if(b0 + dx, pr);
+          t[2] = ldg4_if(b0 + dy, pr);
+          t[3] = ldg4_if(b0 + (dy + dx), pr);
+        };
+        auto mix = [&](float4& f, const float4(&t)[4], const uint4 q0, const float4 q1) {      // level-1 blend (tri-linear part)
+          if ((q0.z >> 30) & 1) {
+            const float4 bq = bilerp4(t[0], t[1], t[2], t[3], q1.z, q1.w);
+            const float frac = __uint_as_float(q0.w);
+            f.x = lerpf(f.x, bq.x, frac); f.y = lerpf(f.y, bq.y, frac); f.z = lerpf(f.z, bq.z, frac); f.w = lerpf(f.w, bq.w, frac);
+          }
+        };
+        float4 f[V];
+        if constexpr (FB == 2) {            // all 8 V taps of the iteration in flight
+          float4 t0[V][4], t1[V][4];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
+            taps4(q0, 0, t0[v]);
+            taps4(q0, 1, t1[v]);
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            f[v] = bilerp4(t0[v][0], t0[v][1], t0[v][2], t0[v][3], q1.x, q1.y);
+            mix(f[v], t1[v], q0, q1);
+          }
+        } else if constexpr (FB == 1) {     // level 0 of all views, then level 1 of all views
+          float4 t[V][4];
+#pragma unroll
+          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048), 0, t[v]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            f[v] = bilerp4(t[v][0], t[v][1], t[v][2], t[v][3], q1.x, q1.y);
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048), 1, t[v]);
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            mix(f[v], t[v], *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048),
+                *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048));
+        } else {                             // both levels of one view at a time
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            float4 t0[4], t1[4];
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
+            taps4(q0, 0, t0);
+            taps4(q0, 1, t1);
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            f[v] = bilerp4(t0[0], t0[1], t0[2], t0[3], q1.x, q1.y);
+            mix(f[v], t1, q0, q1);
+          }
+        }
+        // view_fc weights of my quad's four channels
+        float4 vw0, vw1, vw2, vw3, vbq;
+        {
+          const float* vq = vec + (glane ? gq : 0) * 4;
+          vw0 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 0 * FP);
+          vw1 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 1 * FP);
+          vw2 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 2 * FP);
+          vw3 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 3 * FP);
+          vbq = *reinterpret_cast<const float4*>(vq + C::X_VIEW_B);
+        }
+        const float vw[4][4] = {{vw0.x, vw0.y, vw0.z, vw0.w}, {vw1.x, vw1.y, vw1.z, vw1.w}, {vw2.x, vw2.y, vw2.z, vw2.w}, {vw3.x, vw3.y, vw3.z, vw3.w}};
+        const float vb[4] = {vbq.x, vbq.y, vbq.z, vbq.w};
+        float xq[V][4];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const uint32_t pk = *reinterpret_cast<const uint32_t*>(dsc + (v * C::XCH) * 2048 + 8);
+          const float4 q2 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 2) * 2048);
+          const float dir[4] = {q2.x, q2.y, q2.z, q2.w};
+          const bool act = ok && (pk >> 31);
+          if (TAPS && p.tap_rfd && act) {
+            float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
+            tp[0] = f[v].x; tp[1] = f[v].y; tp[2] = f[v].z;
+            if (!last_quad) tp[3] = f[v].w;
+          }
+          const float fe[4] = {f[v].x, f[v].y, f[v].z, f[v].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = vb[e];
+            t = fmaf(vw[0][e], dir[0], t);
+            t = fmaf(vw[1][e], dir[1], t);
+            t = fmaf(vw[2][e], dir[2], t);
+            t = fmaf(vw[3][e], dir[3], t);
+            xq[v][e] = act ? fe[e] + fmaxf(t, 0.f) : 0.f;
+          }
+          __syncwarp();                     // every lane of the row has read the descriptor that the operand now replaces
+          if (ok) {
+            unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * 2048 + orow16;
+            unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * 2048 + orow16;
+            if (last_quad) {
+              *reinterpret_cast<uint4*>(fdp) = make_uint4(pack_h2(fe[0], fe[1]), pack_h2(fe[2], dir[0]), pack_h2(dir[1], dir[2]), pack_h2(dir[3], 0.f));
+              *reinterpret_cast<uint4*>(xp) = make_uint4(pack_h2(xq[v][0], xq[v][1]), pack_h2(xq[v][2], act ? 1.f : 0.f), 0u, 0u);
+              xq[v][3] = 0.f;
+            } else {
+              *reinterpret_cast<uint2*>(fdp + (gq & 1) * 8) = make_uint2(pack_h2(fe[0], fe[1]), pack_h2(fe[2], fe[3]));
+              *reinterpret_cast<uint2*>(xp + (gq & 1) * 8) = make_uint2(pack_h2(xq[v][0], xq[v][1]), pack_h2(xq[v][2], xq[v][3]));
+            }
+          }
+        }
+        if (ok) {
+          float var[4], mean[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float mu = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) mu += xq[v][e];
+            mu *= (1.f / V);
+            float s2 = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) { float t = xq[v][e] - mu; s2 = fmaf(t, t, s2); }
+            var[e] = s2 * (1.f / (V - 1));
+            mean[e] = mu;
+          }
+          const int kv = gq, km = QL + gq;      // quad positions of var / mean inside S
+          *reinterpret_cast<uint2*>(sS + (kv >> 1) * 2048 + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
+          *reinterpret_cast<uint2*>(sS + (km >> 1) * 2048 + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
+        }
+      }
+    } else
 #pragma unroll 1
     for (int it = 0; it < C::NIT; ++it) {
       const int src_raw = it * IPW + gr;
@@ -692,13 +748,46 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         *stash_f(lane * C::NCP + ((q4 ^ (lane & 7)) << 2)) =
             make_float4(wgt * vals[q4 * 4 + 0], wgt * vals[q4 * 4 + 1], wgt * vals[q4 * 4 + 2], wgt * vals[q4 * 4 + 3]);
       __syncwarp();
+      if (GEN == 3 && p.out_cl && p.dec_stride == F + 9) {
+        // lane = (bundle, channel quad): float4 sums over the bundle's samples, 16-byte stores into the channels-last decoder
+        // input.  F + 8 = 3 (mod 4): the depth is the last lane of the last decoder quad (whose slot in memory is the pad
+        // channel), the opacity the first lane of the quad after it.
+        constexpr int NQ = (F + 9) / 4 + 1;
+        static_assert((F + 8) % 4 == 3 && NQ * 4 <= C::NCP, "quad plan of the compositing stash");
+#pragma unroll 1
+        for (int base = 0; base < G * NQ; base += 32) {
+          const int item = base + lane;
+          const int bb = min(item / NQ, G - 1), q = item - (item / NQ) * NQ;
+          const int nb = __shfl_sync(full, n, bb * ns);
+          const int pixb = pix_warp0 + bb;
+          if (item < G * NQ && pixb < pix_hi) {
+            const int r0 = bb * ns;
+            float4 a = *stash_f(r0 * C::NCP + ((q ^ (r0 & 7)) << 2));
+            for (int k = 1; k < nb; ++k) {
+              const int rl = r0 + k;
+              const float4 o = *stash_f(rl * C::NCP + ((q ^ (rl & 7)) << 2));
+              a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            }
+            const size_t ob = (size_t)b * HW + pixb;
+            if (q < NQ - 1) {
+              if (q == NQ - 2) {
+                p.out_depth[ob] = p.inv_depth ? fdiv(1.f, a.w) : a.w;
+                a.w = p.dec_pad0;
+              }
+              *reinterpret_cast<float4*>(p.out_dec + ob * (F + 9) + q * 4) = a;
+            } else {
+              p.out_opacity[ob] = a.x;
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int base = 0; base < G * C::NC; base += 32) {
         const int item = base + lane;
         const int bb = min(item / C::NC, G - 1), c = item - (item / C::NC) * C::NC;
         const int nb = __shfl_sync(full, n, bb * ns);               // every lane of a bundle holds its count
         const int pixb = pix_warp0 + bb;
-        if (item < G * C::NC && pixb < HW) {
+        if (item < G * C::NC && pixb < pix_hi) {
           float a = 0.f;
           for (int k = 0; k < nb; ++k) {
             const int rl = bb * ns + k;
@@ -722,6 +811,106 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     // ============== P6: fine colours, lane = (row, ray) (bundle_sampler.py:327-337) ==============
     // every lane of the warp is done with its FD rows (the stash aliases X + FD, rows of this warp only)
     __syncwarp();
+    if constexpr (GEN == 3) {
+      // per-row parameters through the row's 16-byte slots of S[0..2] (free since GEMM 4): (z, x0, y0, w), the view weights,
+      // (active, packed-sample row)
+      static_assert(C::CH_S >= 3 && V <= 4, "row-parameter slots of the colour pass");
+      *reinterpret_cast<float4*>(sS + row * 16) = make_float4(z, geo.x0, geo.y0, wgt);
+      {
+        float w4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < V; ++v) w4[v] = wv[v];
+        *reinterpret_cast<float4*>(sS + 2048 + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      *reinterpret_cast<uint4*>(sS + 4096 + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
+      __syncwarp();
+      // component-wise stash of the weighted colours: float index row * R + c * BB + j, in the warp's rows of X + FD
+      static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows of X + FD");
+      auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+#pragma unroll 1
+      for (int it = 0; it < BB; ++it) {
+        const int item = it * 32 + lane;
+        const int r = item / BB, j = item - r * BB;
+        const float4 ra = *reinterpret_cast<const float4*>(sS + (wq * 32 + r) * 16);
+        const float4 rb = *reinterpret_cast<const float4*>(sS + 2048 + (wq * 32 + r) * 16);
+        const uint4 rc = *reinterpret_cast<const uint4*>(sS + 4096 + (wq * 32 + r) * 16);
+        const float zr = ra.x, wr = ra.w;
+        const bool actr = rc.x != 0;
+        const int64_t srow_r = TAPS ? (int64_t)(((uint64_t)rc.z << 32) | rc.y) : 0;
+        const float wvr[4] = {rb.x, rb.y, rb.z, rb.w};
+        const float x = ra.y + (float)(j % BS), y = ra.z + (float)(j / BS);
+        const float* M = head + CAM_M;
+        const float dx = fmaf(x, M[0], fmaf(y, M[1], M[2]));
+        const float dy = fmaf(x, M[3], fmaf(y, M[4], M[5]));
+        const float dz = fmaf(x, M[6], fmaf(y, M[7], M[8]));
+        const float wx = fmaf(dx, zr, ox), wy = fmaf(dy, zr, oy), wz = fmaf(dz, zr, oz);
+        // all 4 V taps of the (row, ray) in flight at once
+        float4 t[V][4];
+        float tw[V][4];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float* cv = head + CAM_HEAD + CAM_VIEW * v;
+          float cx = fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
+          float cy = fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
+          float cz = fmaf(wx, cv[CV_E + 8], fmaf(wy, cv[CV_E + 9], fmaf(wz, cv[CV_E + 10], cv[CV_E + 11])));
+          float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
+          float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
+          float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+          const float rz = fdiv(1.f, iz);
+          float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
+          const Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
+          const float4* ib = reinterpret_cast<const float4*>(p.rgba) + (size_t)(b * V + v) * p.H * p.W;
+          t[v][0] = ldg4_if(ib + bl4.o00, actr);
+          t[v][1] = ldg4_if(ib + bl4.o10, actr);
+          t[v][2] = ldg4_if(ib + bl4.o01, actr);
+          t[v][3] = ldg4_if(ib + bl4.o11, actr);
+          tw[v][0] = bl4.w00; tw[v][1] = bl4.w10; tw[v][2] = bl4.w01; tw[v][3] = bl4.w11;
+        }
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) c4 = f4_scale_add(c4, t[v][k], tw[v][k]);
+          if (TAPS && p.tap_rfd && actr) {
+            float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_r) * C::RFD;
+            tp[0 * BB + j] = c4.x; tp[1 * BB + j] = c4.y; tp[2 * BB + j] = c4.z;
+          }
+          cr = fmaf(c4.x, wvr[v], cr); cg = fmaf(c4.y, wvr[v], cg); cb = fmaf(c4.z, wvr[v], cb);
+        }
+        if (TAPS && p.tap_feat && actr) {
+          float* tfr = p.tap_feat + srow_r * CT;
+          tfr[0 * BB + j] = cr; tfr[1 * BB + j] = cg; tfr[2 * BB + j] = cb;
+        }
+        *cst(r * R + 0 * BB + j) = wr * cr;
+        *cst(r * R + 1 * BB + j) = wr * cg;
+        *cst(r * R + 2 * BB + j) = wr * cb;
+      }
+      __syncwarp();
+      // sum over the samples of a bundle in slot order, lane = (bundle, quad of the 3 b^2 fine-colour channels)
+      constexpr int R4 = R / 4;
+#pragma unroll 1
+      for (int base = 0; base < G * R4; base += 32) {
+        const int item = base + lane;
+        const int bb = min(item / R4, G - 1), q = item - (item / R4) * R4;
+        const int nb = __shfl_sync(full, n, bb * ns);
+        const int pixb = pix_warp0 + bb;
+        if (item < G * R4 && pixb < pix_hi) {
+          float4 a = *reinterpret_cast<const float4*>(cst((bb * ns) * R + q * 4));
+          for (int k = 1; k < nb; ++k) {
+            const float4 o = *reinterpret_cast<const float4*>(cst((bb * ns + k) * R + q * 4));
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          }
+          if (p.out_cl) {
+            *reinterpret_cast<float4*>(p.out_feat + ((size_t)b * HW + pixb) * R + q * 4) = a;
+          } else {
+            float* ofb = p.out_feat + ((size_t)b * CT + q * 4) * HW + pixb;
+            ofb[0] = a.x; ofb[(size_t)HW] = a.y; ofb[2 * (size_t)HW] = a.z; ofb[3 * (size_t)HW] = a.w;
+          }
+        }
+      }
+      __syncwarp();           // stash reads complete before the next tile's descriptors overwrite X
+    } else {
     auto stash = [&](int t) { return reinterpret_cast<float4*>(gsm + (t >> 5) * 2048 + wq * 512 + (t & 31) * 16); };
 #pragma unroll 1
     for (int it = 0; it < BB; ++it) {
@@ -782,7 +971,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       const int bb = min(item / BB, G - 1), j = item % BB;
       const int nb = __shfl_sync(full, n, bb * ns);                 // every lane of a bundle holds its count
       const int pixb = pix_warp0 + bb;
-      if (item < G * BB && pixb < HW) {
+      if (item < G * BB && pixb < pix_hi) {
         float4 a = *stash((bb * ns) * BB + j);
         for (int k = 1; k < nb; ++k) {
           const float4 o = *stash((bb * ns + k) * BB + j);
@@ -795,6 +984,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
     }
     __syncwarp();           // stash reads complete before the next tile's gathers overwrite X / FD
+    }
   }
 
   // ---- teardown
@@ -806,11 +996,11 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   }
 }
 
-template <int BS, int FEAT_DIM, int V, int NG, bool TAPS>
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   static_assert(C::SMEM <= 227 * 1024, "shared memory plan");
-  auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG, TAPS>;
+  auto kern = render_tc2_kernel<BS, FEAT_DIM, V, NG, TAPS, GEN, FB>;
   static SmemOptIn opt;
   {
     cudaError_t e = opt_in_smem(opt, kern, C::SMEM);
@@ -819,26 +1009,48 @@ static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   if ((long)p.Wb * C::QL >= (1 << 14))
     return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): bundle map width %d too large for the packed tap stride", p.Wb);
   const int G = 32 / p.max_samples;
-  const long NB = (long)p.B * p.Hb * p.Wb;
-  const long tiles = (NB + 4 * G - 1) / (4 * G);
+  const long NB = (long)p.B * (p.pix_hi - p.pix_lo);
+  const long tiles = (long)p.B * ((p.pix_hi - p.pix_lo + 4 * G - 1) / (4 * G));
+  (void)NB;
   long ctas = (tiles + NG - 1) / NG;
   if (ctas > sm_count()) ctas = sm_count();
   kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(p);
   return cuda_check("gdb_render_fused_fwd(tc2)");
 }
-template <int BS, int FEAT_DIM, int V, int NG>
+template <int BS, int FEAT_DIM, int V, int NG, int GEN, int FB>
 static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
   const bool taps = p.tap_rfd || p.tap_vox || p.tap_sigma || p.tap_feat || p.tap_w;
-  return taps ? launch_render_tc2_t<BS, FEAT_DIM, V, NG, true>(p, st) : launch_render_tc2_t<BS, FEAT_DIM, V, NG, false>(p, st);
+  return taps ? launch_render_tc2_t<BS, FEAT_DIM, V, NG, true, GEN, FB>(p, st) : launch_render_tc2_t<BS, FEAT_DIM, V, NG, false, GEN, FB>(p, st);
 }
 
-int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
-  if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4>(p, st);
-  if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4>(p, st);
-  if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2>(p, st);
-  if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2>(p, st);
-  if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2>(p, st);
-  if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1>(p, st);
+// gen = 2: the round-1 kernel (A/B reference, `precision = 4` of the C ABI); gen = 3: the batched-gather kernel (default).
+// The batching mode of the feature fetch (FB, see the kernel's header comment) defaults to 1; GDB_K3_FB = 0 / 2 select the
+// measured alternatives for the two benchmark shapes (V = 3).
+int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st) {
+  static int fb_env = -1;
+  if (fb_env < 0) {
+    const char* e = getenv("GDB_K3_FB");
+    fb_env = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  if (gen == 2) {
+    if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 2, 0>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 2, 0>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2, 2, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2, 2, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 2, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 2, 0>(p, st);
+  } else {
+    if (V == 3 && fb_env != 1) {
+      if (bundle_size == 2 && feat_dim == 16) return fb_env == 0 ? launch_render_tc2<2, 16, 3, 4, 3, 0>(p, st) : launch_render_tc2<2, 16, 3, 4, 3, 2>(p, st);
+      if (bundle_size == 4 && feat_dim == 32) return fb_env == 0 ? launch_render_tc2<4, 32, 3, 2, 3, 0>(p, st) : launch_render_tc2<4, 32, 3, 2, 3, 2>(p, st);
+    }
+    if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 3, 1>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 3, 1>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2, 3, 1>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2, 3, 1>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 3, 1>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 3, 1>(p, st);
+  }
   return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): (bundle_size=%d, feat_dim=%d, V=%d) not instantiated", bundle_size, feat_dim, V);
 }
 

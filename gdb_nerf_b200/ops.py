@@ -447,13 +447,15 @@ def texture_level(src: Sources, BV: int, Hb: int, Wb: int, level: int) -> Tensor
 def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: Tensor, cam: Tensor, mlp: Tensor,
                  B: int, V: int, H: int, W: int, bundle_size: int, max_samples: int, inv_depth: bool, adaptive: bool,
                  taps: Optional[SampleList] = None, precision: int = 0, out_channels_last: bool = False,
-                 pad_dec: bool = False, dec_one: bool = False) -> Dict[str, Tensor]:
+                 pad_dec: bool = False, dec_one: bool = False, rows: Optional[Tuple[int, int]] = None) -> Dict[str, Tensor]:
     """-> {'feat' (B,CT,Hb,Wb), 'depth' (B,Hb,Wb), 'opacity' (B,Hb,Wb)} and, when
     ``taps`` (a SampleList) is given, the reference's packed intermediates.
     With ``out_channels_last``: {'fine' (B,Hb,Wb,3b^2), 'dec_in' (B,Hb,Wb,F+8), 'depth', 'opacity'}; ``pad_dec`` rounds the
     channels of 'dec_in' up to a multiple of 4 (zero pad channels: a float4-aligned pixel for the decoder's first convolution);
     ``dec_one`` writes 1.0 into the first pad channel (a constant-one channel that can carry that convolution's bias; needs a
-    pad channel, i.e. (F + 8) % 4 != 0)."""
+    pad channel, i.e. (F + 8) % 4 != 0).  ``rows = (lo, hi)`` renders only the bundle-map rows [lo, hi) of every view (the
+    image-tile split of a view over several GPUs): the outputs keep their full shape, rows outside the range stay
+    uninitialised."""
     _dev(src.tex, src.rgba, vol_cl, depth_range, vol_range, cam, mlp)
     depth_range, vol_range = _f32(depth_range), _f32(vol_range)
     Hb, Wb = H // bundle_size, W // bundle_size
@@ -503,7 +505,7 @@ def render_fused(src: Sources, vol_cl: Tensor, depth_range: Tensor, vol_range: T
                                         vol_range.data_ptr(), cam.data_ptr(), cam.shape[1], mlp.data_ptr(), B, V, H, W, bundle_size,
                                         src.feat_dim, D, vs, vol_layout, max_samples, src.max_mip, int(inv_depth), int(adaptive), precision,
                                         (2 if dec_one else 1) if out_channels_last else 0, out_dec.shape[-1] if out_dec is not None else 0, out_feat.data_ptr(), _p(out_dec), out_depth.data_ptr(), out_opac.data_ptr(),
-                                        C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
+                                        rows[0] if rows else 0, rows[1] if rows else Hb, C.byref(tp) if tp is not None else None, _stream()), "gdb_render_fused_fwd")
     return res
 
 

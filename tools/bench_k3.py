@@ -12,6 +12,7 @@ from gdb_nerf_b200.synthetic import WORKLOADS, camera_rig, smooth_images
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--precision", type=int, default=-1)
+ap.add_argument("--precisions", default="", help="comma-separated list, e.g. 4,1 (4 = round-1 kernel, 1 = batched-gather kernel)")
 ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--workload", default="dtu")
@@ -48,14 +49,15 @@ if args.folded:
     buf[..., :8] = vol_cl.permute(0, 2, 3, 1, 4)
     vol_cl = buf[..., :8].permute(0, 3, 1, 2, 4)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for prec in ([0, 1, 2, 3] if args.precision < 0 else [args.precision]):
+plist = [int(x) for x in args.precisions.split(",")] if args.precisions else ([0, 1, 2, 3, 4] if args.precision < 0 else [args.precision])
+for prec in plist:
     ts = []
     for i in range(args.iters + 2):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        out = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, H, W, b, cfg.nerf.max_num_samples, False, True, precision=prec, out_channels_last=True)
+        out = ops.render_fused(src, vol_cl, dr, vr, cam, mlp, B, V, H, W, b, cfg.nerf.max_num_samples, False, True, precision=prec, out_channels_last=True, pad_dec=True, dec_one=True)
         e.record(); torch.cuda.synchronize()
         if i >= 2: ts.append(s.elapsed_time(e))
     ms = sum(ts) / len(ts)
-    print(f"precision {prec}: {ms:.3f} ms per launch ({B} views) = {ms / B * 1e3:.1f} us/view")
+    print(f"{args.workload} precision {prec} (GDB_K3_FB={os.environ.get('GDB_K3_FB', '-')}): {ms:.4f} ms per launch ({B} views) = {ms / B * 1e3:.1f} us/view, min {min(ts):.4f}", flush=True)
