@@ -10,9 +10,10 @@ timed step bracketed by CUDA events on the launching stream, an L2 flush (256 MB
 memset) between timed steps outside the events, max over ranks, SM clocks and
 throttle reasons sampled with nvidia-smi during the timed region.
 
-``--impl reference`` times the CPU port of the reference's forward
-(oracle/gdb_oracle.py:network_forward - the reference itself is pure Python and
-cannot travel to the GPU box) on the host cores, one target view per step.
+``--impl reference`` times the reference's own ``Network.forward`` (the unmodified tree staged under baseline/_ref,
+see baseline/README.md; pure-PyTorch stand-ins for nvdiffrast / nerfacc) on the host cores, one target view per step;
+when the tree is not staged it falls back to the CPU port (oracle/gdb_oracle.py:network_forward) and says so.
+The GPU arm's line also carries ``reference_cuda``: the same unmodified model on the same GPU in the same process.
 """
 from __future__ import annotations
 
@@ -49,15 +50,37 @@ def _peaks():
 
 def _ncu_traffic(kernel, workload, views):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed ncu --set full capture (per launch),
-    when one exists for this workload and launch size; None otherwise."""
+    when one exists for this workload, launch size AND this build of the kernels (keyed on the source digest: a capture of
+    an older kernel is never reported); None otherwise."""
     path = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
     if kernel != "gdb_render_fused_fwd" or not os.path.exists(path):
         return None
     with open(path) as fh:
         d = json.load(fh)
-    if d.get("workload") != workload or d.get("views_per_launch") != views:
+    if d.get("workload") != workload or d.get("views_per_launch") != views or d.get("kernel_source_sha256") != _kernel_digest():
         return None
     return d["traffic_bytes_per_launch"]
+
+
+def _kernel_digest():
+    """sha256 of the fused render kernel's sources (the file the ncu capture of profiles/k3_dram_traffic.json profiled)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("gdb_render_tc2.cu", "gdb_render_tc2.cuh", "gdb_render_common.cuh", "gdb_tcgen05.cuh", "gdb_sampling.cuh", "gdb_common.cuh"):
+        with open(os.path.join(ROOT, "gdb_nerf_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _parity_note(workload):
+    """End-to-end error of the BENCHED math mode (TF32 cuDNN convolutions, fp16-operand MLP) against the CPU oracle at the
+    benchmark's full image size, measured by tests/test_network_gpu.py::test_benched_math_mode_against_oracle and committed
+    under profiles/ (the test asserts the same bounds on every GPU run)."""
+    path = os.path.join(ROOT, "profiles", "r02_benched_mode_parity.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get(workload)
 
 
 def _tensor_peak():
@@ -116,39 +139,51 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, wl, cfg):
-    """CPU arm: the oracle port of Network.forward on the host cores, one target view per step."""
+def _reference_forward(cfg, device):
+    """(callable batch -> outputs, kind): the unmodified reference model when its tree is staged, else the CPU port."""
+    from oracle import ref_runner
+    if ref_runner.reference_dir() is not None:
+        net = ref_runner.load_reference_network(cfg, device=device, seed=0)
+        return (lambda batch: net(batch)), "reference"
     from gdb_nerf_b200.network import Network
-    from gdb_nerf_b200.synthetic import workload_batch
     from oracle import gdb_oracle as O
+    torch.manual_seed(0)
+    net = Network(cfg).eval()
+    return (lambda batch: O.network_forward(net, batch, cfg)), "port"
+
+
+def run_reference(args, wl, cfg):
+    """CPU arm: the reference's own Network.forward on the host cores, one target view per step (run.py:53-66 loop body)."""
+    from gdb_nerf_b200.synthetic import workload_batch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    net = Network(cfg).eval()
-    batch = workload_batch(args.workload, B=1, V=3, seed=0)
+    fwd, kind = _reference_forward(cfg, "cpu")
+    batch = workload_batch(args.workload, B=1, V=3, seed=0, images="noise8")
     H, W = batch["src_views"]["rgb"].shape[-2:]
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            O.network_forward(net, batch, cfg)
+            fwd(batch)
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 times.append(dt)
     total = sum(times)
     value = args.steps * H * W / total
-    sample = f"{args.steps} steps x 1 target view ({H}x{W}, 3 source views) after {args.warmup} warm-up"
+    what = ("the unmodified reference Network.forward (baseline/_ref/reference, pure-PyTorch stand-ins for nvdiffrast / nerfacc)"
+            if kind == "reference" else "CPU port of Network.forward (oracle/gdb_oracle.py; reference tree not staged)")
+    sample = f"{what}: {args.steps} steps x 1 target view ({H}x{W}, 3 source views) after {args.warmup} warm-up, torch threads = {cores}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload} {H}x{W} eval forward, 3 source views, 1 target view per step, CPU",
                    "recipe": wl["recipe"], "views_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,26 +192,58 @@ def run_reference(args, wl, cfg):
 
 def cpu_baseline_sample(args, cfg, wl):
     """Bounded CPU sample for the `cpu_baseline` object of our own arm (rank 0, N=1)."""
-    from gdb_nerf_b200.network import Network
     from gdb_nerf_b200.synthetic import workload_batch
-    from oracle import gdb_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    net = Network(cfg).eval()
-    batch = workload_batch(args.workload, B=1, V=3, seed=0)
+    fwd, kind = _reference_forward(cfg, "cpu")
+    batch = workload_batch(args.workload, B=1, V=3, seed=0, images="noise8")
     H, W = batch["src_views"]["rgb"].shape[-2:]
     times = []
     with torch.no_grad():
         for i in range(3):
             t0 = time.perf_counter()
-            O.network_forward(net, batch, cfg)
+            fwd(batch)
             times.append(time.perf_counter() - t0)
     best = min(times[1:])
-    return {"value": H * W / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"CPU port of Network.forward (oracle/gdb_oracle.py), 1 target view {H}x{W}, best of 2 after 1 warm-up "
-                      f"({best:.2f} s/view)"}
+    what = "unmodified reference Network.forward (baseline/_ref, stand-ins for nvdiffrast / nerfacc)" if kind == "reference" \
+        else "CPU port of Network.forward (oracle/gdb_oracle.py)"
+    return {"value": H * W / best, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{what}, 1 target view {H}x{W}, best of 2 after 1 warm-up ({best:.2f} s/view)"}
+
+
+def reference_cuda_probe(workload, cfg, dev):
+    """The reference's own PyTorch-CUDA forward on THIS GPU in THIS process (the denominator of the north star's >= 50x):
+    the unmodified model from baseline/_ref with pure-PyTorch stand-ins for nvdiffrast / nerfacc, timed as run.py:59-73
+    does (synchronize, wall clock, network(batch), synchronize; first iteration dropped), 1 and 8 target views per call."""
+    from gdb_nerf_b200.synthetic import batch_to, workload_batch
+    from oracle import ref_runner
+    if ref_runner.reference_dir() is None:
+        return {"unavailable": "reference tree not staged under baseline/_ref (baseline/README.md)"}
+    try:
+        net = ref_runner.load_reference_network(cfg, device=dev, seed=0)
+        out = {"what": "unmodified reference Network.forward on this GPU (stand-ins: pure-PyTorch nvdiffrast.texture / nerfacc.volrend), "
+                       "run.py:59-73 timing, mean of 5 calls after 3 dropped, PyTorch default math (TF32 conv), cudnn.benchmark as our arm"}
+        for B in (1, 8):
+            batch = batch_to(workload_batch(workload, B=B, V=3, seed=0, images="noise8"), dev)
+            H, W = batch["src_views"]["rgb"].shape[-2:]
+            times = []
+            with torch.no_grad():
+                for _ in range(8):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    net(batch)
+                    torch.cuda.synchronize()
+                    times.append(time.perf_counter() - t0)
+            ms = 1e3 * sum(times[3:]) / len(times[3:])
+            out[f"views_per_call_{B}"] = {"ms_per_call": ms, "ms_per_view": ms / B, "rays_per_s": B * H * W / (ms * 1e-3)}
+            del batch
+        del net
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:                         # the probe must never take the benchmark down
+        torch.cuda.empty_cache()
+        return {"unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
 
 def run_ours(args, wl, cfg):
@@ -184,7 +251,7 @@ def run_ours(args, wl, cfg):
 
     from gdb_nerf_b200 import ops
     from gdb_nerf_b200.network import Network
-    from gdb_nerf_b200.synthetic import batch_to, workload_batch
+    from gdb_nerf_b200.synthetic import batch_to, with_uint8_images, workload_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,13 +267,17 @@ def run_ours(args, wl, cfg):
     torch.manual_seed(0)
     net = Network(cfg).to(dev).eval()
     # every rank renders its own target views (round-robin shard of the sweep): no data-path collective
-    host_batch = workload_batch(args.workload, B=B, V=3, seed=rank, view_offset=rank * B)
+    # source images are 8-bit samples / 255 (what the reference's loaders produce from image files, dtu.py:135)
+    host_batch = workload_batch(args.workload, B=B, V=3, seed=rank, view_offset=rank * B, images="noise8")
     H, W = host_batch["src_views"]["rgb"].shape[-2:]
 
     def pin(x):
         return {k: pin(v) for k, v in x.items()} if isinstance(x, dict) else x.pin_memory()
 
-    pinned = pin(host_batch)
+    # end to end the images cross PCIe as the 8-bit samples they are; Network.forward converts them on the device
+    # (gdb_u8_to_unit_f32: the loaders' `astype(float32) / 255.`, bit-identical), so both timings render the same pixels
+    host_e2e = with_uint8_images(host_batch)
+    pinned = pin(host_e2e)
     dev_batch = batch_to(host_batch, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -215,7 +286,7 @@ def run_ours(args, wl, cfg):
     counts = {"n": 0}
     spans = {"gdb_render_fused_fwd": [], "gdb_warp_variance_fwd": []}
     recording = {"on": False}
-    launches_per_call = {"to_channels_last": 1, "homography_mats": 1, "depth_values": 1, "warp_variance": 1, "depth_range_from_prob": 1,
+    launches_per_call = {"u8_to_unit": 1, "to_channels_last": 1, "homography_mats": 1, "depth_values": 1, "warp_variance": 1, "depth_range_from_prob": 1,
                          "depth_range_from_logits": 1, "bias_act_add": 1, "gate_add": 1, "se_gate_add": 2, "concat_into": 1,
                          "camera_block": 1, "prepare_sources": 1, "render_fused": 1, "assemble_output": 1,
                          "prob_head_depth_range": 1, "concat_channels": 1, "channel_mean": 2, "pixel_shuffle2_bias": 1}
@@ -244,16 +315,34 @@ def run_ours(args, wl, cfg):
             ret, _, _ = net(dev_batch)
         return ret
 
-    out_host = [torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    b_sz = cfg.nerf.bundle_size
+    out_shapes = {"rgb": (B, 3, H, W), "nerf_depth": (B, H, W), "mvs_depth": (B, H // b_sz, W // b_sz)}
+    out_host = [{k: torch.empty(shp, dtype=torch.float32).pin_memory() for k, shp in out_shapes.items()} for _ in range(2)]
     side = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
     def step_e2e(i):
-        """One end-to-end step on stream i%2: pinned H2D of the batch, forward, D2H of the image into pinned memory.
-        Two steps are in flight, so the copies of one overlap the kernels of the other; every step still pays its own copies."""
+        """One end-to-end step on stream i%2: pinned H2D of the batch, forward, D2H of what the reference's evaluator
+        consumes (image + both depth maps, evaluators/gdb_nerf.py:37-39,98-100) into pinned memory.  Two steps are in flight,
+        so the copies of one overlap the kernels of the other; every step still pays its own copies."""
         st = side[i % 2]
         with torch.cuda.stream(st), torch.no_grad():
             ret, _, _ = net(batch_to(pinned, dev, non_blocking=True))
-            out_host[i % 2].copy_(ret["rgb"], non_blocking=True)
+            for k, buf in out_host[i % 2].items():
+                buf.copy_(ret[k], non_blocking=True)
+
+    def time_e2e():
+        for i in range(4):
+            step_e2e(i)
+        barrier()
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_e2e(i)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        return ms
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,7 +382,7 @@ def run_ours(args, wl, cfg):
     spans_main = {k: list(v) for k, v in spans.items()}
     alt_steps = max(3, args.steps // 2)
     alt = {}
-    for prec in (0, 2):
+    for prec in (() if args.lean else (0, 2)):
         for v in spans.values():
             v.clear()
         net.mlp_precision = prec
@@ -306,18 +395,14 @@ def run_ours(args, wl, cfg):
     net.mlp_precision = 1
     barrier()
 
-    # end to end through the public API with host buffers (pinned H2D inside, D2H of the image inside)
-    for i in range(4):
-        step_e2e(i)
-    barrier()
-    flush.zero_()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
-    torch.cuda.synchronize()
-    ms_e2e = 1e3 * (time.perf_counter() - t0)
-    barrier()
+    # end to end through the public API with host buffers (pinned H2D inside, D2H of the outputs inside):
+    # the headline arithmetic, then the fp32-class MLP (precision 2)
+    ms_e2e = time_e2e()
+    ms_e2e_p2 = 0.0
+    if not args.lean:
+        net.mlp_precision = 2
+        ms_e2e_p2 = time_e2e()
+        net.mlp_precision = 1
     # the sampler ran through every timed region above (device-timed headline, the MLP variants, end to end): the GPU was
     # under the same load throughout; a default run is too short for nvidia-smi to report during the headline loop alone
     clocks = sampler.stop() if rank == 0 else None
@@ -327,7 +412,7 @@ def run_ours(args, wl, cfg):
     # latency of ONE target view per call (the "ms/target-view" half of the metric for an interactive caller): eager launches
     # vs the whole forward replayed as one CUDA graph (gdb_nerf_b200/graphed.py); rank 0 only, not the headline
     latency = None
-    if rank == 0:
+    if rank == 0 and not args.lean:
         from gdb_nerf_b200.graphed import GraphedForward
         one = batch_to(workload_batch(args.workload, B=1, V=3, seed=0), dev)
         with torch.no_grad():
@@ -353,10 +438,18 @@ def run_ours(args, wl, cfg):
         del runner
     barrier()
 
-    t = torch.tensor([ms_dev, ms_e2e, alt[0][0], alt[2][0]], dtype=torch.float64, device=dev)
+    # the reference's own CUDA forward on this GPU, same process (rank 0 of a single-GPU run only: it needs ~7 GB)
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.lean and not args.no_reference_cuda:
+        del dev_batch
+        torch.cuda.empty_cache()
+        ref_cuda = reference_cuda_probe(args.workload, cfg, dev)
+    barrier()
+
+    t = torch.tensor([ms_dev, ms_e2e, alt[0][0] if alt else 0.0, alt[2][0] if alt else 0.0, ms_e2e_p2], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_p0, ms_p2 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_dev, ms_e2e, ms_p0, ms_p2, ms_e2e_p2 = (float(x) for x in t)
 
     if rank == 0:
         rays_per_step = world * B * H * W
@@ -390,29 +483,35 @@ def run_ours(args, wl, cfg):
             return {"kernel": key, "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
                     "flop_per_launch": flop_per_view * B, "avg_launch_ms": ms, "peak_source": thow}
 
-        h2d = sum(v.numel() * v.element_size() for d in (host_batch["src_views"], host_batch["tar_views"]) for v in d.values())
-        h2d += host_batch["near_far"].numel() * 4
-        d2h = B * 3 * H * W * 4
+        h2d = sum(v.numel() * v.element_size() for d in (host_e2e["src_views"], host_e2e["tar_views"]) for v in d.values())
+        h2d += host_e2e["near_far"].numel() * 4
+        d2h = sum(buf.numel() * 4 for buf in out_host[0].values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "ms_per_target_view": ms_dev / args.steps / B,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (TF32 cuDNN convolutions as in PyTorch's default; per-point MLP GEMM operands f16, f32 accumulate)",
+            "data": "synthetic",
             "config": {"mlp_arithmetic": "MLP GEMMs on tcgen05 with fp16 operands and fp32 accumulation in TMEM (the operand precision of the TF32 "
                                          "convolutions PyTorch runs next to it); gathers, geometry, compositing and everything else fp32",
                        "workload": f"{args.workload} {H}x{W} eval forward, 3 source views, batch of {B} target views per GPU per step "
                                    f"(BASELINE.json configs[1])", "recipe": wl["recipe"], "views_per_step_per_gpu": B,
                        "parallelism": f"target views sharded over {world} GPU(s), no data-path collective",
-                       "l2": "256 MB memset between timed steps (outside the CUDA events)", "cnn_math": "cuDNN, PyTorch default (TF32 conv), cudnn.benchmark"},
+                       "l2": "256 MB memset between timed steps (outside the CUDA events)", "cnn_math": "cuDNN, PyTorch default (TF32 conv), cudnn.benchmark",
+                       "images": "8-bit white noise / 255 (as the loaders decode image files); resident run: float32 on the device, e2e: the 8-bit samples cross PCIe",
+                       "parity_of_this_math_mode": _parity_note(args.workload)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "what": "pinned host batch -> H2D -> Network.forward -> D2H of ret['rgb'] into pinned memory, every step; two steps in "
-                            "flight on two streams (copies overlap kernels); wall clock over all steps"},
+                    "ms_per_step": ms_e2e / args.steps, "what": "pinned host batch (8-bit source images, cameras) -> H2D -> Network.forward -> D2H of ret['rgb'], "
+                            "ret['nerf_depth'], ret['mvs_depth'] into pinned memory, every step; two steps in flight on two streams (copies overlap kernels); "
+                            "wall clock over all steps"},
             "gpu_launches": launches,
             "single_view_latency": latency,
             "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload]),
             "roofline_warp_variance": roof("gdb_warp_variance_fwd", K1_BYTES_PER_VIEW[args.workload]),
             "roofline_mlp_tensor": roof_tensor("gdb_render_fused_fwd", K3_MLP_FLOP_PER_VIEW[args.workload]),
-            "mlp_variants": {
+            "reference_cuda": ref_cuda,
+            "mlp_variants": None if args.lean else {
                 "headline": "gdb_render_fused_fwd precision=1: MLP GEMMs on tcgen05, fp16 operands, fp32 accumulators in TMEM. Measured against "
                             "the oracle at full size (tools/k3_errors.py): fine rgb <= 1.3e-5, depth <= 1.3e-6 of the range, decoder "
                             "features <= 3.4e-4 - inside the north star's 2e-3 class for a reduced-precision MLP, rgb/depth inside its 1e-4 class",
@@ -422,10 +521,15 @@ def run_ours(args, wl, cfg):
                 "tcgen05_split_fp16": {"what": "precision=2, operands split into two fp16 planes (hi+lo, 22 bits), three MMAs per K step (fp32 class: "
                                                "1e-4 vs the reference, 2e-5 vs the SIMT kernel)",
                                        "value": rays_per_step * alt_steps / (ms_p2 * 1e-3), "unit": UNIT, "ms_per_step": ms_p2 / alt_steps, "steps": alt_steps,
+                                       "e2e": {"value": rays_per_step * args.steps / (ms_e2e_p2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_p2 / args.steps,
+                                               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                                        "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload], alt[2][1], alt_steps)},
             },
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if ref_cuda and "views_per_call_8" in ref_cuda:
+            line["reference_cuda"]["speedup_device_timed"] = value / ref_cuda["views_per_call_8"]["rays_per_s"]
+            line["reference_cuda"]["speedup_fp32_class"] = (rays_per_step * alt_steps / (ms_p2 * 1e-3)) / ref_cuda["views_per_call_8"]["rays_per_s"]
+        if world == 1 and not args.no_cpu_baseline and not args.lean:
             line["cpu_baseline"] = cpu_baseline_sample(args, cfg, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -551,6 +655,8 @@ def main():
     ap.add_argument("--workload", choices=["dtu", "llff", "nerf"], default="dtu")
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference's own CUDA forward (reference_cuda object)")
+    ap.add_argument("--lean", action="store_true", help="headline + e2e only (no MLP variants, latency, CPU / reference-CUDA legs): multi-GPU matrix runs")
     ap.add_argument("--no-graph", action="store_true", help="train mode: time eager launches only")
     ap.add_argument("--mode", choices=["eval", "train"], default="eval", help="train: BASELINE.json configs[4] (not the headline)")
     args = ap.parse_args()

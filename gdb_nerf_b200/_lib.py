@@ -36,6 +36,7 @@ SIGNATURES = {
     "gdb_last_error_string": (C.c_char_p, []),
     "gdb_mlp_param_floats": (c_i, [c_i]),
     "gdb_planar_to_channels_last": (c_i, [c_f, c_f, c_i, c_i, c_i64, c_i, c_f]),
+    "gdb_u8_to_unit_f32": (c_i, [c_f, c_f, c_i64, c_f]),
     "gdb_homography_mats": (c_i, [c_f, c_f, c_f, c_f, c_fl, c_fl, c_i, c_i, c_f, c_f]),
     "gdb_depth_values": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),
     "gdb_warp_variance_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f]),

@@ -204,6 +204,37 @@ extern "C" int gdb_prepare_sources(const float* feat, int feat_channels_last, co
   return cuda_check("gdb_prepare_sources");
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// 8-bit images -> float32 in [0, 1]: the reference's loaders do `img.astype(np.float32) / 255.` on the host
+// (datasets/dataloader/dtu.py:84,135, llff.py:134, nerf.py:132) and ship 4 bytes per sample over PCIe; here the
+// 8-bit samples cross the bus and the same IEEE division runs on the device (a 256-entry table of
+// __fdiv_rn((float)u, 255.f): bit-identical to numpy's float32 division).
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint4* __restrict__ in, float4* __restrict__ out, int64_t n16,
+                                                         const unsigned char* __restrict__ in_tail, float* __restrict__ out_tail, int tail) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = fdiv((float)threadIdx.x, 255.f);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(in + i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      __stcs(out + i * 4 + k, make_float4(lut[w[k] & 255u], lut[(w[k] >> 8) & 255u], lut[(w[k] >> 16) & 255u], lut[w[k] >> 24]));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) out_tail[threadIdx.x] = lut[in_tail[threadIdx.x]];
+}
+
+extern "C" int gdb_u8_to_unit_f32(const unsigned char* src, float* dst, int64_t n, void* stream) {
+  GDB_REQUIRE(src && dst && n > 0, GDB_E_BADARG, "gdb_u8_to_unit_f32: bad argument");
+  GDB_REQUIRE(aligned16(src) && aligned16(dst), GDB_E_ALIGN, "gdb_u8_to_unit_f32: src / dst must be 16-byte aligned");
+  const int64_t n16 = n / 16;
+  const int tail = (int)(n - n16 * 16);
+  int blocks = (int)std::min<int64_t>((n16 + 255) / 256 + 1, (int64_t)sm_count() * 8);
+  u8_to_unit_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), n16,
+                                                          src + n16 * 16, dst + n16 * 16, tail);
+  return cuda_check("gdb_u8_to_unit_f32");
+}
+
 extern "C" int gdb_assemble_output(const float* feat, int Ctot, const float* dec, const float* bdepth, const float* bopacity,
                                    int B, int Hb, int Wb, int bundle_size, int reweighting, int layout, const float* dec_bias,
                                    float* rgb, float* depth, float* opacity, void* stream) {

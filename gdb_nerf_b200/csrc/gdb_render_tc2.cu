@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   const int pix_lo = p.pix_lo, pix_hi = p.pix_hi;          // bundle range of every view this launch renders (image-tile split)
   const int tiles_pv = (pix_hi - pix_lo + 4 * G - 1) / (4 * G);   // tiles per target view (a tile = 4 warps x G bundles, one view)
   const int tiles = p.B * tiles_pv;
-  const int bl = lane / ns, slot = lane - bl * ns;
-  const int seg_base = bl * ns;
+  // row (= lane) of sample `k` of the warp's bundle `bb`.  GEN 2: bundle-major (the packed sample order).  GEN 3: slot-major,
+  // consecutive lanes hold the SAME slot of ADJACENT bundles, so the rows a gather instruction covers read neighbouring
+  // texels (one run of contiguous bytes per image row instead of one 128-byte line per lane)
+  auto rowof = [&](int bb, int k) { return GEN == 3 ? k * G + bb : bb * ns + k; };
+  const int slot = GEN == 3 ? lane / G : lane % ns;
+  const int bl = GEN == 3 ? lane - slot * G : lane / ns;
+  const bool lane_ok = GEN == 3 ? slot < ns : bl < G;
   float* scam = reinterpret_cast<float*>(gsm + C::CAM_OFF);
   const float* head = scam;
   int cur_b = -1;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   auto load_ranges = [&](int t) -> float4 {
     const int tb = t / tiles_pv;
     const int praw = pix_lo + ((t - tb * tiles_pv) * 4 + wq) * G + bl;
-    const int px = (bl < G && praw < pix_hi) ? praw : pix_lo;
+    const int px = (lane_ok && praw < pix_hi) ? praw : pix_lo;
     const float* dr = p.depth_range + (size_t)(tb * 2) * HW + px;
     const float* vr = p.vol_range + (size_t)(tb * 2) * HW + px;
     return make_float4(__ldg(dr), __ldg(dr + HW), __ldg(vr), __ldg(vr + HW));
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     }
     const int pix_warp0 = pix_lo + ((tile - b * tiles_pv) * 4 + wq) * G;       // first bundle of my warp
     const int pix_raw = pix_warp0 + bl;
-    const bool has_bundle = bl < G && pix_raw < pix_hi;
+    const bool has_bundle = lane_ok && pix_raw < pix_hi;
     const int pix = has_bundle ? pix_raw : pix_lo;
     const int bidx = b * HW + pix;
     const int yb = pix / p.Wb, xb = pix - yb * p.Wb;
@@ -282,6 +287,18 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     // writes FD_v = [featrgb_v | dir_v], X_v = [x_v | 1] (nerf.py:69-71) and S = [var | mean] over views (nerf.py:73)
     if constexpr (GEN == 3) {
       __syncwarp();                       // the descriptors of my warp's 32 rows are in shared memory
+      // view_fc weights of my quad's four channels, loaded once per tile (the descriptors no longer occupy registers)
+      float4 vw0, vw1, vw2, vw3, vbq;
+      {
+        const float* vq = vec + (glane ? gq : 0) * 4;
+        vw0 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 0 * FP);
+        vw1 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 1 * FP);
+        vw2 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 2 * FP);
+        vw3 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 3 * FP);
+        vbq = *reinterpret_cast<const float4*>(vq + C::X_VIEW_B);
+      }
+      const float vw[4][4] = {{vw0.x, vw0.y, vw0.z, vw0.w}, {vw1.x, vw1.y, vw1.z, vw1.w}, {vw2.x, vw2.y, vw2.z, vw2.w}, {vw3.x, vw3.y, vw3.z, vw3.w}};
+      const float vb[4] = {vbq.x, vbq.y, vbq.z, vbq.w};
 #pragma unroll 1
       for (int it = 0; it < C::NIT; ++it) {
         const int src_raw = it * IPW + gr;
@@ -354,18 +371,6 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             mix(f[v], t1, q0, q1);
           }
         }
-        // view_fc weights of my quad's four channels
-        float4 vw0, vw1, vw2, vw3, vbq;
-        {
-          const float* vq = vec + (glane ? gq : 0) * 4;
-          vw0 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 0 * FP);
-          vw1 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 1 * FP);
-          vw2 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 2 * FP);
-          vw3 = *reinterpret_cast<const float4*>(vq + C::X_VIEW_W + 3 * FP);
-          vbq = *reinterpret_cast<const float4*>(vq + C::X_VIEW_B);
-        }
-        const float vw[4][4] = {{vw0.x, vw0.y, vw0.z, vw0.w}, {vw1.x, vw1.y, vw1.z, vw1.w}, {vw2.x, vw2.y, vw2.z, vw2.w}, {vw3.x, vw3.y, vw3.z, vw3.w}};
-        const float vb[4] = {vbq.x, vbq.y, vbq.z, vbq.w};
         float xq[V][4];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -692,13 +697,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     float one_minus = 1.f - alpha;
     float T = 1.f;
     for (int k = 0; k + 1 < ns; ++k) {
-      float o = __shfl_sync(full, one_minus, min(seg_base + k, 31));
+      float o = __shfl_sync(full, one_minus, min(rowof(bl, k), 31));
       if (k < slot) T *= o;
     }
     float wgt = alpha * T;
     float wtot = 0.f;
     for (int k = 0; k < ns; ++k) {
-      float o = __shfl_sync(full, wgt, min(seg_base + k, 31));
+      float o = __shfl_sync(full, wgt, min(rowof(bl, k), 31));
       if (k < n) wtot += o;
     }
     wgt = active ? wgt / fmaxf(wtot, 1e-6f) : 0.f;
@@ -758,13 +763,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         for (int base = 0; base < G * NQ; base += 32) {
           const int item = base + lane;
           const int bb = min(item / NQ, G - 1), q = item - (item / NQ) * NQ;
-          const int nb = __shfl_sync(full, n, bb * ns);
+          const int nb = __shfl_sync(full, n, rowof(bb, 0));
           const int pixb = pix_warp0 + bb;
           if (item < G * NQ && pixb < pix_hi) {
-            const int r0 = bb * ns;
+            const int r0 = rowof(bb, 0);
             float4 a = *stash_f(r0 * C::NCP + ((q ^ (r0 & 7)) << 2));
             for (int k = 1; k < nb; ++k) {
-              const int rl = r0 + k;
+              const int rl = rowof(bb, k);
               const float4 o = *stash_f(rl * C::NCP + ((q ^ (rl & 7)) << 2));
               a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
             }
@@ -785,12 +790,12 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       for (int base = 0; base < G * C::NC; base += 32) {
         const int item = base + lane;
         const int bb = min(item / C::NC, G - 1), c = item - (item / C::NC) * C::NC;
-        const int nb = __shfl_sync(full, n, bb * ns);               // every lane of a bundle holds its count
+        const int nb = __shfl_sync(full, n, rowof(bb, 0));          // every lane of a bundle holds its count
         const int pixb = pix_warp0 + bb;
         if (item < G * C::NC && pixb < pix_hi) {
           float a = 0.f;
           for (int k = 0; k < nb; ++k) {
-            const int rl = bb * ns + k;
+            const int rl = rowof(bb, k);
             const float o = *reinterpret_cast<const float*>(stash_f(rl * C::NCP + (((c >> 2) ^ (rl & 7)) << 2) + (c & 3)));
             a = k == 0 ? o : a + o;
           }
@@ -822,7 +827,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         for (int v = 0; v < V; ++v) w4[v] = wv[v];
         *reinterpret_cast<float4*>(sS + 2048 + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
       }
-      *reinterpret_cast<uint4*>(sS + 4096 + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
+      if (TAPS)
+        *reinterpret_cast<uint4*>(sS + 4096 + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
       __syncwarp();
       // component-wise stash of the weighted colours: float index row * R + c * BB + j, in the warp's rows of X + FD
       static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows of X + FD");
@@ -833,9 +839,11 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         const int r = item / BB, j = item - r * BB;
         const float4 ra = *reinterpret_cast<const float4*>(sS + (wq * 32 + r) * 16);
         const float4 rb = *reinterpret_cast<const float4*>(sS + 2048 + (wq * 32 + r) * 16);
-        const uint4 rc = *reinterpret_cast<const uint4*>(sS + 4096 + (wq * 32 + r) * 16);
+        uint4 rc = make_uint4(0u, 0u, 0u, 0u);
+        if (TAPS) rc = *reinterpret_cast<const uint4*>(sS + 4096 + (wq * 32 + r) * 16);
         const float zr = ra.x, wr = ra.w;
-        const bool actr = rc.x != 0;
+        // production build: a row without compositing weight contributes w * colour = 0 whatever it gathers - not fetched
+        const bool actr = TAPS ? rc.x != 0 : wr != 0.f;
         const int64_t srow_r = TAPS ? (int64_t)(((uint64_t)rc.z << 32) | rc.y) : 0;
         const float wvr[4] = {rb.x, rb.y, rb.z, rb.w};
         const float x = ra.y + (float)(j % BS), y = ra.z + (float)(j / BS);
@@ -893,12 +901,12 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       for (int base = 0; base < G * R4; base += 32) {
         const int item = base + lane;
         const int bb = min(item / R4, G - 1), q = item - (item / R4) * R4;
-        const int nb = __shfl_sync(full, n, bb * ns);
+        const int nb = __shfl_sync(full, n, rowof(bb, 0));
         const int pixb = pix_warp0 + bb;
         if (item < G * R4 && pixb < pix_hi) {
-          float4 a = *reinterpret_cast<const float4*>(cst((bb * ns) * R + q * 4));
+          float4 a = *reinterpret_cast<const float4*>(cst(rowof(bb, 0) * R + q * 4));
           for (int k = 1; k < nb; ++k) {
-            const float4 o = *reinterpret_cast<const float4*>(cst((bb * ns + k) * R + q * 4));
+            const float4 o = *reinterpret_cast<const float4*>(cst(rowof(bb, k) * R + q * 4));
             a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
           }
           if (p.out_cl) {
@@ -1024,13 +1032,13 @@ static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
 }
 
 // gen = 2: the round-1 kernel (A/B reference, `precision = 4` of the C ABI); gen = 3: the batched-gather kernel (default).
-// The batching mode of the feature fetch (FB, see the kernel's header comment) defaults to 1; GDB_K3_FB = 0 / 2 select the
+// The batching mode of the feature fetch (FB, see the kernel's header comment) defaults to 0; GDB_K3_FB = 1 / 2 select the
 // measured alternatives for the two benchmark shapes (V = 3).
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st) {
   static int fb_env = -1;
   if (fb_env < 0) {
     const char* e = getenv("GDB_K3_FB");
-    fb_env = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    fb_env = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
   }
   if (gen == 2) {
     if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 2, 0>(p, st);
@@ -1040,16 +1048,16 @@ int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, in
     if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 2, 0>(p, st);
     if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 2, 0>(p, st);
   } else {
-    if (V == 3 && fb_env != 1) {
-      if (bundle_size == 2 && feat_dim == 16) return fb_env == 0 ? launch_render_tc2<2, 16, 3, 4, 3, 0>(p, st) : launch_render_tc2<2, 16, 3, 4, 3, 2>(p, st);
-      if (bundle_size == 4 && feat_dim == 32) return fb_env == 0 ? launch_render_tc2<4, 32, 3, 2, 3, 0>(p, st) : launch_render_tc2<4, 32, 3, 2, 3, 2>(p, st);
+    if (V == 3 && fb_env != 0) {
+      if (bundle_size == 2 && feat_dim == 16) return fb_env == 1 ? launch_render_tc2<2, 16, 3, 4, 3, 1>(p, st) : launch_render_tc2<2, 16, 3, 4, 3, 2>(p, st);
+      if (bundle_size == 4 && feat_dim == 32) return fb_env == 1 ? launch_render_tc2<4, 32, 3, 2, 3, 1>(p, st) : launch_render_tc2<4, 32, 3, 2, 3, 2>(p, st);
     }
-    if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 3, 1>(p, st);
-    if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 3, 1>(p, st);
-    if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2, 3, 1>(p, st);
-    if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2, 3, 1>(p, st);
-    if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 3, 1>(p, st);
-    if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 3, 1>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 3, 0>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 3, 0>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2, 3, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2, 3, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 3, 0>(p, st);
+    if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 3, 0>(p, st);
   }
   return fail(GDB_E_UNSUPPORTED, "gdb_render_fused_fwd(tc2): (bundle_size=%d, feat_dim=%d, V=%d) not instantiated", bundle_size, feat_dim, V);
 }

@@ -245,6 +245,10 @@ class Network(nn.Module):
         src_images = src_views['rgb']
         if not src_images.is_cuda:
             raise ops._lib.GdbError("gdb_nerf_b200.Network.forward needs CUDA tensors (no CPU fallback exists)")
+        if src_images.dtype == torch.uint8:
+            # 8-bit source images (what the loaders read from disk, dtu.py:135) converted on the device: x / 255 in IEEE
+            # float32, bit-identical to the loaders' host-side conversion, a quarter of the PCIe bytes
+            src_images = ops.u8_to_unit(src_images)
         B, V, _, H, W = src_images.shape
         src_exts = src_views['extrinsics']
         src_ints = src_views['intrinsics'].clone()

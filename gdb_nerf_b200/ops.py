@@ -74,6 +74,19 @@ def to_channels_last(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
     return out
 
 
+def u8_to_unit(x: Tensor) -> Tensor:
+    """uint8 image samples -> float32 in [0, 1] (x / 255 in IEEE float32, as the reference's loaders compute on the host)."""
+    _dev(x)
+    if x.dtype != torch.uint8:
+        raise _lib.GdbError(f"u8_to_unit needs a uint8 tensor, got {x.dtype}")
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    if x.numel():
+        lib = _lib.load()
+        _lib.check(lib.gdb_u8_to_unit_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "gdb_u8_to_unit_f32")
+    return out
+
+
 # ------------------------------------------------------------- cost volume --
 def homography_mats(src_exts: Tensor, src_ints: Tensor, tar_exts: Tensor, tar_ints: Tensor, src_scale: float, tar_scale: float) -> Tensor:
     _dev(src_exts, src_ints, tar_exts, tar_ints)

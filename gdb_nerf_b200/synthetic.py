@@ -74,6 +74,9 @@ def make_batch(
     """Batch dict in the reference's layout (networks/gdb_nerf/network.py:96-103)."""
     if images == "noise":
         rgb = torch.rand(B, V, 3, H, W, generator=torch.Generator().manual_seed(seed))
+    elif images == "noise8":
+        # 8-bit white noise converted as the reference's loaders convert image files (dtu.py:135: astype(float32) / 255.)
+        rgb = torch.randint(0, 256, (B, V, 3, H, W), generator=torch.Generator().manual_seed(seed), dtype=torch.uint8).float() / 255.0
     elif images == "smooth":
         rgb = smooth_images(B, V, H, W, seed)
     else:
@@ -89,6 +92,18 @@ def make_batch(
 def workload_batch(name: str, B: int = 1, V: int = 3, seed: int = 0, images: str = "noise", view_offset: int = 0) -> Dict:
     w = WORKLOADS[name]
     return make_batch(B, V, w["H"], w["W"], w["near"], w["far"], w["focal"], seed, images, view_offset)
+
+
+def with_uint8_images(batch: Mapping) -> Dict:
+    """The same batch with the source images as 8-bit samples (exact for images that came from 8-bit files or from
+    ``images="noise8"``: x -> round(255 x)); ``Network.forward`` converts them back on the device, bit-identically."""
+    out = {k: (dict(v) if isinstance(v, Mapping) else v) for k, v in batch.items()}
+    rgb = batch["src_views"]["rgb"]
+    u8 = torch.round(rgb * 255.0).clamp_(0, 255).to(torch.uint8)
+    if not torch.equal(u8.float() / 255.0, rgb):
+        raise ValueError("source images are not 8-bit samples / 255: an 8-bit copy would change the result")
+    out["src_views"]["rgb"] = u8
+    return out
 
 
 def batch_to(batch: Mapping, device, non_blocking: bool = False) -> Dict:

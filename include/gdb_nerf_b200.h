@@ -46,6 +46,11 @@ int gdb_mlp_param_floats(int feat_dim);
  * (C=8).  C <= Cpad, Cpad % 4 == 0.                                          */
 int gdb_planar_to_channels_last(const float* src, float* dst, int N, int C, int64_t S, int Cpad, void* stream);
 
+/* 8-bit image samples -> float32 in [0, 1] on the device: dst[i] = (float)src[i] / 255.f in IEEE arithmetic, bit-identical
+ * to the host-side `img.astype(np.float32) / 255.` of the reference's loaders (datasets/dataloader/dtu.py:84,135,
+ * llff.py:134, nerf.py:132).  Lets a caller ship 8-bit source images over PCIe (4x fewer bytes).                        */
+int gdb_u8_to_unit_f32(const unsigned char* src, float* dst, int64_t n, void* stream);
+
 /* --------------------------------------------------------- cost volume ---- */
 /* Homography matrices, replaces depth_net.py:453-457.
  * src_exts (B,V,4,4) src_ints (B,V,3,3) tar_exts (B,4,4) tar_ints (B,3,3);
