@@ -539,12 +539,16 @@ def run_ours(args, wl, cfg):
 def run_train(args):
     """BASELINE.json configs[4]: DTU pre-training step (fwd + bwd of the fused render path and the rest of the network,
     gradient all-reduce, clip, Adam) on a 64x64 crop = 1024 bundles per GPU.  One JSON line: training steps are not the
-    headline metric; rays/s here counts the rays of the crops all ranks trained on."""
+    headline metric; rays/s here counts the rays of the crops all ranks trained on.  The step tail runs on ONE flat buffer
+    (gdb_nerf_b200/optim.py: a single NCCL all-reduce issued on the flat gradient, then the fused average + clip + Adam
+    kernel); the whole step, collective included, is also captured as a CUDA graph."""
+    import copy
+
     import torch.distributed as dist
 
     from gdb_nerf_b200.config import make_cfg
     from gdb_nerf_b200.network import Network
-    from gdb_nerf_b200.sharding import allreduce_gradients
+    from gdb_nerf_b200.optim import FlatAdam
     from gdb_nerf_b200.synthetic import batch_to, make_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -562,85 +566,83 @@ def run_train(args):
     if world > 1:
         net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)            # as trainer.py:16
     net.train()
-    import copy
-    # single GPU: the step is also captured as a CUDA graph (never run eagerly).  With more ranks the capture would have to
-    # include the NCCL all-reduce and SyncBN's collectives on every rank in lock-step; a 2-GPU attempt hung, so multi-GPU
-    # training steps are timed with eager launches
-    net_g = None if (args.no_graph or world > 1) else copy.deepcopy(net)
-    params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=5e-4, capturable=True)
+    # the captured model never runs eagerly on the default stream (its AccumulateGrad nodes must live on the capture stream)
+    net_g = None if args.no_graph else copy.deepcopy(net)
+    opt = FlatAdam(net.parameters(), lr=5e-4)
     crop, B, V = 64, 1, 3
     batch = batch_to(make_batch(B, V, crop, crop, 425.0, 905.0, 1446.0 * crop / 512.0, seed=100 + rank, images="smooth", tilt=0.03), dev)
     stream = torch.cuda.current_stream()
 
+    def loss_fn(out):
+        return out[0]["rgb"].square().mean() + sum(b.square().mean() for b in out[2])
+
     def step():
-        opt.zero_grad(set_to_none=True)
-        ret, _, blend = net(batch)
-        loss = ret["rgb"].square().mean() + sum(b.square().mean() for b in blend)
+        opt.zero_grad()
+        loss = loss_fn(net(batch))
         loss.backward()
-        nbytes = allreduce_gradients(params)
-        torch.nn.utils.clip_grad_value_(params, 40)                        # trainer.py:64
-        opt.step()
-        return loss, nbytes
+        opt.step()                                                         # all-reduce + clip(40) + Adam: trainer.py:63-65
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e.record(stream)
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / steps, out
 
     for _ in range(max(args.warmup, 3)):
-        loss, nbytes = step()
-    torch.cuda.synchronize()
-    # eager launches (reported next to the headline) on a copy of the model: the AccumulateGrad nodes of the captured model
-    # must be created on the capture stream, so the model that is captured never runs eagerly on the default stream
+        loss = step()
+    ms_eager, loss = timed(step, args.steps)
+    # the exchange step alone: one all-reduce of the flat gradient (what DDP spreads over its buckets)
+    ms_ar = None
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(stream)
-    for _ in range(args.steps):
-        loss, nbytes = step()
-    e0.record(stream)
-    torch.cuda.synchronize()
-    ms_eager = s0.elapsed_time(e0) / args.steps
-    graphed = None
+        ms_ar, _ = timed(lambda: dist.all_reduce(opt.grad_flat), 50)
+    ms_tail, _ = timed(lambda: opt.step(), 50)                             # all-reduce + fused clip/Adam kernel (+ counter)
+    graphed, graph_note = None, "not attempted (--no-graph)"
     if net_g is not None:
         try:
             from gdb_nerf_b200.graphed import GraphedTrainStep
-            params_g = [p for p in net_g.parameters() if p.requires_grad]
-            opt_g = torch.optim.Adam(params_g, lr=5e-4, capturable=True)
-            graphed = GraphedTrainStep(net_g, opt_g, batch, lambda out: out[0]["rgb"].square().mean() + sum(b.square().mean() for b in out[2]),
-                                       params_g, clip_value=40.0, allreduce=allreduce_gradients)
-
-            def step():                                                    # noqa: F811
-                return graphed(batch), nbytes
+            opt_g = FlatAdam(net_g.parameters(), lr=5e-4)
+            graphed = GraphedTrainStep(net_g, opt_g, batch, loss_fn, opt_g.params)
             for _ in range(3):
-                step()
+                graphed(batch)
             torch.cuda.synchronize()
+            graph_note = "whole step (forward, loss, backward, all-reduce of the flat gradient, fused clip + Adam) replayed as one CUDA graph"
         except Exception:                                                  # capture is an optimisation, never a requirement
             import traceback
             sys.stderr.write("[bench] CUDA-graph capture of the training step failed, timing eager launches:\n" + traceback.format_exc()[-1500:] + "\n")
-            graphed = None
+            graphed, graph_note = None, "capture failed (see stderr): eager launches"
+    ok = torch.tensor([1.0 if graphed is not None else 0.0], device=dev)
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                          # replay only if every rank captured
     torch.cuda.nvtx.range_push("gdb_timed")
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(stream)
-    for _ in range(args.steps):
-        loss, nbytes = step()
-    e.record(stream)
-    torch.cuda.synchronize()
+    if float(ok[0]) > 0:
+        ms_head, loss = timed(lambda: graphed(batch), args.steps)
+    else:
+        ms_head, loss = ms_eager, loss
+        if net_g is not None and graphed is not None:
+            graph_note = "another rank failed to capture: eager launches"
     torch.cuda.nvtx.range_pop()
-    ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_head, ms_eager, ms_ar or 0.0, ms_tail], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        ms_step = float(ms[0]) / args.steps
+        ms_step = float(t[0])
         print(json.dumps({
             "metric": "training step (fwd+bwd+allreduce+Adam), DTU pretrain, 64x64 crop = 1024 bundles per GPU", "value": world * B * crop * crop / (ms_step * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "loss": float(loss.detach()),
-            "step_execution": "whole step (forward, loss, backward, all-reduce, clip, Adam) replayed as one CUDA graph" if graphed is not None
-                              else "eager launches", "eager_ms_per_step": ms_eager,
+            "step_execution": graph_note if float(ok[0]) > 0 else f"eager launches ({graph_note})", "eager_ms_per_step": float(t[1]),
+            "allreduce_ms": float(t[2]) if world > 1 else None, "allreduce_plus_clip_adam_ms": float(t[3]),
             "config": {"workload": "dtu_pretrain training step, 3 source views, fixed 6 samples/bundle, 1 crop of 64x64 px per GPU "
-                                   "(BASELINE.json configs[4])", "allreduce_bytes": nbytes,
-                       "parallelism": f"data parallel over {world} GPU(s): one flat-bucket NCCL all-reduce of the gradients per step, SyncBN"},
+                                   "(BASELINE.json configs[4])", "allreduce_bytes": opt.allreduce_bytes,
+                       "optimizer": "FlatAdam: one flat fp32 buffer, gdb_adam_clip_step (average + clip 40 + Adam) in one kernel",
+                       "parallelism": f"data parallel over {world} GPU(s): one NCCL all-reduce issued on the flat gradient per step, SyncBN"},
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()

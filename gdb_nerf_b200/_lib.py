@@ -71,6 +71,8 @@ SIGNATURES = {
     "gdb_pixel_shuffle2": (c_i, [c_f, c_f, c_i64, c_i, c_i, c_i, c_f, c_f]),
     "gdb_concat3": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_i64, c_f, c_f]),
     "gdb_channel_mean": (c_i, [c_f, c_i64, c_i64, c_i, c_i, c_f, c_f, c_f]),
+    "gdb_adam_clip_step": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i64, c_fl, c_fl, c_fl, c_fl, c_fl, c_fl, c_fl, c_f]),
+    "gdb_adam_advance": (c_i, [c_f, c_f]),
     "gdb_assemble_output": (c_i, [c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
 }
 

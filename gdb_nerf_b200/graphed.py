@@ -96,36 +96,47 @@ class GraphedTrainStep:
         loss = stepper(batch)          # device scalar, overwritten by the next call
     """
 
-    def __init__(self, net: torch.nn.Module, opt: torch.optim.Optimizer, example_batch: Mapping, loss_fn, params,
-                 clip_value: float = 40.0, allreduce=None, warmup: int = 3) -> None:
+    def __init__(self, net: torch.nn.Module, opt, example_batch: Mapping, loss_fn, params,
+                 clip_value: float = 40.0, allreduce=None, warmup: int = 3, group=None) -> None:
         if not net.training:
             raise ValueError("GraphedTrainStep captures the training step; call net.train() first")
+        from .optim import FlatAdam
         flat = {k: v for k, v in _flatten(example_batch).items() if torch.is_tensor(v) and v.is_cuda}
         self._static_in = {k: v.clone() for k, v in flat.items()}
         self._batch = _rebuild(example_batch, {**_flatten(example_batch), **self._static_in})
         self.params = list(params)
+        fused = isinstance(opt, FlatAdam)
 
         def one_step():
+            if fused:
+                opt.zero_grad()                       # a memset node of the graph: the flat gradient is static memory
             out = net(self._batch)
             loss = loss_fn(out)
             loss.backward()
-            if allreduce is not None:
-                allreduce(self.params)
-            torch.nn.utils.clip_grad_value_(self.params, clip_value)          # trainer.py:64
-            opt.step()
+            if fused:
+                opt.step(group=group)                 # all-reduce on the flat gradient + fused average / clip / Adam
+            else:
+                if allreduce is not None:
+                    allreduce(self.params)
+                torch.nn.utils.clip_grad_value_(self.params, clip_value)          # trainer.py:64
+                opt.step()
             return loss
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
-                opt.zero_grad(set_to_none=True)
+                if not fused:
+                    opt.zero_grad(set_to_none=True)
                 one_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        if not fused:
+            opt.zero_grad(set_to_none=True)
+        # thread_local: the NCCL watchdog thread of a multi-GPU run polls CUDA events while this thread captures; under the
+        # default "global" mode those calls invalidate the capture (round 1: a 2-GPU capture never completed)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._loss = one_step()
 
     def __call__(self, batch: Mapping) -> torch.Tensor:

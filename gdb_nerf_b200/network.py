@@ -176,10 +176,18 @@ class Network(nn.Module):
         #      star's fp32 class (1e-4), agrees with 0 to ~1e-5
         #   0: fp32 SIMT (the validation variant of the fp32 class)
         self.mlp_precision = 1
+        # image-tile split of a single target view over several GPUs (set_tile_split): FPN / DepthNet replicated, the fused
+        # render kernel on this rank's bundle rows, one all-gather of the row tiles, decoder replicated
+        self._tile = None
         # derived eval-time parameters (folded batch-norm, width/depth-folded kernels, the packed MLP block) are cached on
         # the modules keyed on the parameters' version counters; in-place `.data` writes do not bump those, so a
         # checkpoint load drops every cache explicitly
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_caches())
+
+    def set_tile_split(self, rank: int = 0, world: int = 1, group=None) -> None:
+        """Render bundle rows ``sharding.shard_rows(Hb, rank, world)`` of every view on this rank and all-gather the tiles
+        (eval path, one target view per call); ``world = 1`` switches the split off."""
+        self._tile = None if world <= 1 else (int(rank), int(world), group)
 
     def invalidate_caches(self) -> None:
         """Drop every derived-parameter cache (call after writing parameters through `.data` / `copy_` under no_grad)."""
@@ -301,9 +309,18 @@ class Network(nn.Module):
         sources = ops.prepare_sources(img_feat, src_images, b, self.sampler.max_mipmap_level)
         vol_cl = feat_volume if fused else ops.to_channels_last(feat_volume, 8)    # fused: already a (B,D,Hb,Wb,8) view
         dec_c = self.nerf.feat_dim + 3 + self.voxel_dim                              # channels of the decoder's input
+        rows = None
+        if self._tile is not None:
+            from .sharding import gather_row_tiles, shard_rows
+            if B != 1 or not fused:
+                raise ValueError("the image-tile split renders one target view per call on the fused eval path")
+            tile = shard_rows(Hb, self._tile[0], self._tile[1])
+            rows = (tile.start, tile.stop)
         out = ops.render_fused(sources, vol_cl, depth_range, vol_range, cam, self.nerf.packed(), B, V, H, W, b,
                                self.max_num_samples, self.inv_depth, self.is_adaptive, out_channels_last=fused,
-                               precision=self.mlp_precision, pad_dec=fused, dec_one=fused and dec_c % 4 != 0)
+                               precision=self.mlp_precision, pad_dec=fused, dec_one=fused and dec_c % 4 != 0, rows=rows)
+        if rows is not None:
+            gather_row_tiles([out['fine'], out['dec_in'], out['depth'], out['opacity']], Hb, self._tile[1], self._tile[2])
         if fused:
             # NCHW shape over channels-last memory; the first pad channel (constant 1) carries the first convolution's bias
             dec12, dec_b = decoder_fused(self.upsampler, out['dec_in'].permute(0, 3, 1, 2), one_channel=dec_c if dec_c % 4 != 0 else -1)

@@ -36,6 +36,28 @@ def shard_rows(n_rows: int, rank: int, world: int, align: int = 8) -> range:
     return range(lo, hi)
 
 
+def gather_row_tiles(tensors: Sequence[torch.Tensor], n_rows: int, world: int, group=None, align: int = 8) -> None:
+    """Image-tile split of ONE target view (north star: "partitioned by target views and image tiles"): every rank has
+    written the bundle rows ``shard_rows(n_rows, rank, world)`` of each ``(1, n_rows, ...)`` tensor; afterwards every rank
+    holds all rows.  Equal tiles travel as one in-place ``all_gather_into_tensor`` per tensor (each rank's tile is already
+    in its slot of the output), ragged tiles as one broadcast per rank."""
+    if world == 1:
+        return
+    tiles = [shard_rows(n_rows, r, world, align) for r in range(world)]
+    equal = len({len(t) for t in tiles}) == 1 and len(tiles[0]) * world == n_rows
+    rank = dist.get_rank(group)
+    for t in tensors:
+        if t.shape[0] != 1 or t.shape[1] != n_rows or not t.is_contiguous():
+            raise ValueError("gather_row_tiles needs contiguous (1, n_rows, ...) tensors (single-view latency mode)")
+        if equal:
+            mine = t[0, tiles[rank].start: tiles[rank].stop]
+            dist.all_gather_into_tensor(t[0], mine, group=group)
+        else:
+            for r, rows in enumerate(tiles):
+                if len(rows):
+                    dist.broadcast(t[0, rows.start: rows.stop], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
 def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
     """Timing reduction used by bench.py: every rank contributes its elapsed time, all get the max."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

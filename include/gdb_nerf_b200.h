@@ -306,6 +306,17 @@ int gdb_pixel_shuffle2(const float* in, const float* bias, int64_t N, int H, int
  * (modules.py, AdaptiveAvgPool2d(1)).  partial (N, chunks, C) is scratch; the summation order is fixed.                    */
 int gdb_channel_mean(const float* x, int64_t N, int64_t S, int C, int chunks, float* partial, float* out, void* stream);
 
+/* --------------------------------------------------------- optimiser ------ */
+/* Tail of the training step on ONE flat fp32 buffer: replaces `torch.nn.utils.clip_grad_value_(parameters, 40)` +
+ * `optimizer.step()` (train/trainers/trainer.py:63-65; torch.optim.Adam built by train/optimizer.py:13-29) and the division of
+ * DistributedDataParallel's gradient average (trainer.py:16-22: the caller all-reduces `grad` with SUM, grad_scale = 1/world).
+ * param, grad, exp_avg, exp_avg_sq: n floats each (n % 4 == 0, 16-byte aligned).  state[0] = completed steps (device-resident
+ * so that the step can be captured into a CUDA graph); gdb_adam_advance adds one after the update.                          */
+int gdb_adam_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* state, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, float clip_value, float grad_scale,
+                       void* stream);
+int gdb_adam_advance(float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,10 @@ DD = torch.float64
 RTOL = 2e-3
 
 
+def _md(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
 def _rel(got, want, floor=1e-30):
     """max |got - want| relative to the largest reference entry (``floor``: smallest scale that counts, for
     gradients that vanish analytically, e.g. the bias in front of a soft-max over views)."""
@@ -309,3 +313,67 @@ def test_training_step_as_cuda_graph_matches_eager():
     for s in (1, 2):
         la, lb = eager(mk(s)), float(stepper(mk(s)))
         assert abs(la - lb) <= 2e-3 * abs(la), (s, la, lb)
+
+
+# ------------------------------------------------------------------ flat-buffer clip + Adam (trainer.py:63-65, optimizer.py:13-29)
+def test_flat_adam_matches_torch_adam_with_value_clipping():
+    """gdb_adam_clip_step on one flat buffer against clip_grad_value_(40) + torch.optim.Adam on the same parameters and
+    gradients over several steps, including clipped gradients, weight decay and a parameter that never receives a gradient."""
+    from gdb_nerf_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 24), (64,), (8, 16, 3, 3), (1,), (7, 5)]
+    for wd in (0.0, 0.01):
+        ref = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+        mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+        opt_ref = torch.optim.Adam([{"params": [p], "lr": 5e-4, "weight_decay": wd, "eps": 1e-8} for p in ref], 5e-4, weight_decay=wd, eps=1e-8)
+        opt = FlatAdam(mine, lr=5e-4, eps=1e-8, weight_decay=wd, clip_value=40.0)
+        for p, q in zip(ref, mine):
+            assert torch.equal(p.data, q.data)
+        for step in range(6):
+            opt_ref.zero_grad()
+            opt.zero_grad()
+            for i, (p, q) in enumerate(zip(ref, mine)):
+                if i == len(shapes) - 1:
+                    continue                                              # never gets a gradient
+                grad = torch.randn(p.shape, generator=g).to(DEV) * (100.0 if step % 2 == 0 else 1e-3)   # clipped / tiny
+                p.grad = grad.clone()
+                q.grad.add_(grad)                                         # autograd accumulates into the flat view
+            torch.nn.utils.clip_grad_value_(ref, 40)
+            opt_ref.step()
+            opt.step()
+        torch.cuda.synchronize()
+        assert float(opt.state[0]) == 6.0
+        for p, q in zip(ref, mine):
+            assert _md(p, q) <= 2e-6 * (1.0 + float(p.abs().max())), (wd, tuple(p.shape), _md(p, q))
+        assert torch.equal(mine[-1].data, ref[-1].data)                   # untouched
+        assert all(q.data.data_ptr() >= opt.param_flat.data_ptr() for q in mine)
+
+
+def test_flat_adam_training_step_is_graph_capturable():
+    """The whole training step (forward, loss, backward into the flat gradient, fused clip + Adam) replays as one CUDA graph
+    and produces the same parameters as the same steps launched eagerly."""
+    import copy
+    from gdb_nerf_b200.graphed import GraphedTrainStep
+    from gdb_nerf_b200.optim import FlatAdam
+    net_a, batch, _ = _train_net()
+    net_b = copy.deepcopy(net_a)
+
+    def loss_fn(out):
+        return out[0]["rgb"].square().mean() + sum(b.square().mean() for b in out[2])
+
+    opt_b = FlatAdam(net_b.parameters(), lr=5e-4)
+    stepper = GraphedTrainStep(net_b, opt_b, batch, loss_fn, opt_b.params, warmup=2)      # 2 warm-up steps + capture (no update)
+    for _ in range(3):
+        loss_b = stepper(batch)
+    torch.cuda.synchronize()
+    opt_a = FlatAdam(net_a.parameters(), lr=5e-4)
+    for _ in range(5):
+        opt_a.zero_grad()
+        loss_a = loss_fn(net_a(batch))
+        loss_a.backward()
+        opt_a.step()
+    torch.cuda.synchronize()
+    assert float(opt_a.state[0]) == float(opt_b.state[0]) == 5.0
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-3 * abs(float(loss_a))
+    rel = float((opt_a.param_flat - opt_b.param_flat).abs().max()) / float(opt_a.param_flat.abs().max())
+    assert rel <= 2e-3, rel                                                # atomics in the backward kernels: not bit-stable

@@ -383,3 +383,111 @@ def test_width_folded_cost_regularisation_matches_modules(small, dhw):
         vol, logits = cost_reg_fused(net, x, want_volume=True)
     assert _md(vol.permute(0, 4, 1, 2, 3), feat) <= 2e-5 * max(1.0, float(feat.abs().max()))
     assert _md(torch.softmax(logits, 1), prob) <= 2e-5
+
+
+# ------------------------------------------------------------------ the BENCHED math mode against the oracle, full size
+def _psnr(a, b):
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 99.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+@pytest.mark.parametrize("workload", ["dtu"])
+def test_benched_math_mode_against_oracle(workload):
+    """bench.py's configuration - TF32 cuDNN convolutions (PyTorch's default, also what the reference's own CUDA forward
+    runs), cudnn.benchmark, fp16-operand MLP (precision 1), 8-bit source images converted on the device - at the benchmark's
+    full image size against the CPU oracle's fp32 forward on the same batch and weights.  The measured errors are written
+    to gpurun_out/ (committed as profiles/r02_benched_mode_parity.json, quoted in the bench line's config); the same run
+    in the fp32 class (TF32 off, precision 2) is reported next to it."""
+    import json
+    import os
+    from gdb_nerf_b200.synthetic import with_uint8_images, workload_batch
+    w = WORKLOADS[workload]
+    cfg = make_cfg(w["recipe"])
+    torch.manual_seed(0)
+    net = Network(cfg).eval()
+    batch = workload_batch(workload, B=1, V=3, seed=0, images="noise8")
+    with torch.no_grad():
+        truth, _ = O.network_forward(net, batch, cfg)
+    net = net.to(DEV)
+    scale = w["far"] - w["near"]
+    report = {}
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
+    try:
+        for mode, tf32, prec in (("benched (TF32 conv, fp16-operand MLP)", True, 1), ("fp32 class (fp32 conv, split-fp16 MLP)", False, 2)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = tf32
+            net.mlp_precision = prec
+            with torch.no_grad():
+                ret, _, _ = net(batch_to(with_uint8_images(batch), DEV))
+            torch.cuda.synchronize()
+            rgb, dep = ret["rgb"].cpu(), ret["nerf_depth"].cpu()
+            report[mode] = {
+                "rgb_max_abs": _md(rgb, truth["rgb"]), "rgb_mean_abs": float((rgb - truth["rgb"]).abs().mean()),
+                "rgb_psnr_vs_oracle_db": _psnr(rgb, truth["rgb"]),
+                "nerf_depth_max_abs_normalised": _md(dep, truth["nerf_depth"]) / scale,
+                "nerf_depth_mean_abs_normalised": float((dep - truth["nerf_depth"]).abs().mean()) / scale,
+                "mvs_depth_max_abs_normalised": _md(ret["mvs_depth"], truth["mvs_depth"]) / scale,
+            }
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+        net.mlp_precision = 1
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"benched_mode_parity_{workload}.json"), "w") as fh:
+        json.dump({workload: report, "what": f"{workload} {w['H']}x{w['W']}, 1 target view, 3 source views, 8-bit white-noise images, "
+                                             "random-init weights (seed 0): Network.forward on the GPU vs oracle.network_forward (CPU fp32)"}, fh, indent=1)
+    print(json.dumps(report))
+    fp32 = report["fp32 class (fp32 conv, split-fp16 MLP)"]
+    bench = report["benched (TF32 conv, fp16-operand MLP)"]
+    # fp32 class: cuDNN vs MKL-DNN summation order through ~40 convolution layers on white-noise images
+    assert fp32["rgb_max_abs"] <= 2e-3 and fp32["nerf_depth_max_abs_normalised"] <= 2e-3, fp32
+    # benched mode: TF32 convolutions (10-bit operand mantissa) dominate; the image must stay visually identical
+    assert bench["rgb_psnr_vs_oracle_db"] >= 45.0 and bench["nerf_depth_mean_abs_normalised"] <= 5e-3, bench
+
+
+def test_network_tile_split_plumbing(monkeypatch):
+    """Image-tile split through Network.forward: each emulated rank renders its bundle rows (the fused kernel launch is
+    restricted to them) and receives the other rows from the gather - here fed from a one-piece run, whose row tiles are
+    bit-identical to what the other ranks' launches write (tests/test_kernels_gpu.py::test_render_fused_row_range_...).
+    The final image equals the one-piece image bit for bit."""
+    import gdb_nerf_b200.sharding as sharding
+    cfg = make_cfg("dtu_eval")
+    torch.manual_seed(0)
+    net = Network(cfg).to(DEV).eval()
+    batch = batch_to(make_batch(1, 3, 128, 160, 425.0, 905.0, 360.0, seed=2, images="smooth"), DEV)
+    captured = {}
+    real = ops.render_fused
+
+    def spy(*a, **k):
+        out = real(*a, **k)
+        captured["out"] = {n: t.clone() for n, t in out.items()}
+        captured["rows"] = k.get("rows")
+        return out
+
+    monkeypatch.setattr(ops, "render_fused", spy)
+    with torch.no_grad():
+        full, _, _ = net(batch)
+    whole = captured["out"]
+    assert captured["rows"] is None
+    world = 4
+    seen = []
+
+    def fake_gather(tensors, n_rows, w, group=None, align=8):
+        tile = sharding.shard_rows(n_rows, net._tile[0], w, align)
+        seen.append((tile.start, tile.stop))
+        for t, name in zip(tensors, ("fine", "dec_in", "depth", "opacity")):
+            mine = t[:, tile.start: tile.stop].clone()
+            assert torch.equal(mine, whole[name][:, tile.start: tile.stop]), name
+            t.copy_(whole[name])
+            t[:, tile.start: tile.stop] = mine
+
+    monkeypatch.setattr(sharding, "gather_row_tiles", fake_gather)
+    for r in range(world):
+        net.set_tile_split(r, world)
+        with torch.no_grad():
+            ret, _, _ = net(batch)
+        assert captured["rows"] == seen[-1]
+        for k in full:
+            assert torch.equal(ret[k], full[k]), (r, k)
+    net.set_tile_split(0, 1)
+    assert seen == [(0, 16), (16, 32), (32, 48), (48, 64)]

@@ -122,3 +122,39 @@ def test_reference_loader_mechanism(tmp_path, monkeypatch):
     finally:
         if saved is not None:
             sys.modules[name] = saved
+
+
+def _tile_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gdb_nerf_b200.sharding import gather_row_tiles
+        out = []
+        for n_rows in (16, 24):                      # equal tiles (one all-gather) and ragged tiles (8 | 16: broadcasts)
+            full = torch.arange(n_rows * 5 * 3, dtype=torch.float32).view(1, n_rows, 5, 3)
+            plane = torch.arange(n_rows * 5, dtype=torch.float32).view(1, n_rows, 5) * 2.0
+            rows = shard_rows(n_rows, rank, world)
+            a, b = torch.full_like(full, -1.0), torch.full_like(plane, -1.0)
+            a[:, rows.start: rows.stop] = full[:, rows.start: rows.stop]      # what this rank's kernel launch wrote
+            b[:, rows.start: rows.stop] = plane[:, rows.start: rows.stop]
+            gather_row_tiles([a, b], n_rows, world)
+            out.append(bool(torch.equal(a, full) and torch.equal(b, plane)))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_row_tile_gather_gloo():
+    """Image-tile split: after gather_row_tiles every rank holds every bundle row of the view."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, [True, True]), (1, [True, True])]

@@ -18,6 +18,8 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--workload", default="dtu")
 ap.add_argument("--lib", default="", help="alternative build of the library (A/B measurements)")
 ap.add_argument("--folded", action="store_true", help="volume in the depth-folded (B,Hb,Wb,D,12) layout of the 2-D cost-regularisation head")
+ap.add_argument("--noisy-depth", action="store_true", help="per-bundle white-noise depth (adversarial: no coherence between neighbouring bundles) "
+                "instead of the smooth depth field a cost-volume network produces")
 ap.add_argument("--narrow", action="store_true", help="narrow depth ranges (adaptive counts 1..max) instead of saturated")
 args = ap.parse_args()
 if args.lib:
@@ -36,7 +38,11 @@ rgb = smooth_images(B, V, H, W).to(dev)
 feat = (torch.randn(B, V, fd, Hb, Wb, generator=g) * 0.5).to(dev)
 vol = (torch.randn(B, 8, 8, Hb, Wb, generator=g) * 0.5).to(dev)
 min_iv = (w["far"] - w["near"]) / cfg.nerf.global_num_depth
-mid = w["near"] + (w["far"] - w["near"]) * (0.3 + 0.4 * torch.rand(B, 1, Hb, Wb, generator=g))
+if args.noisy_depth:
+    mid = w["near"] + (w["far"] - w["near"]) * (0.3 + 0.4 * torch.rand(B, 1, Hb, Wb, generator=g))
+else:       # smooth field: bicubic up-sampling of a coarse random grid
+    coarse = torch.rand(B, 1, max(Hb // 32, 2), max(Wb // 32, 2), generator=g)
+    mid = w["near"] + (w["far"] - w["near"]) * (0.3 + 0.4 * torch.nn.functional.interpolate(coarse, size=(Hb, Wb), mode="bicubic", align_corners=True).clamp(0, 1))
 half = torch.rand(B, 1, Hb, Wb, generator=g) * (0.55 * cfg.nerf.max_num_samples * min_iv) if args.narrow else torch.full((B, 1, Hb, Wb), 4 * min_iv)
 dr = torch.cat((mid - half, mid + half), 1).to(dev); vr = torch.cat((mid - 2.5 * min_iv, mid + 2.5 * min_iv), 1).to(dev)
 torch.manual_seed(0)
