@@ -13,7 +13,8 @@ ONE contiguous fp32 buffer each:
 
 Semantics: ``torch.optim.Adam`` (betas, eps, weight_decay as given; no amsgrad).  One deliberate difference: a parameter that
 receives no gradient in a step is treated as having a zero gradient (its moments decay) instead of being skipped; for
-parameters that NEVER receive one (feature_net.inner2 / out2 in this model) both leave the parameter untouched.
+parameters that NEVER receive one (feature_net.inner2 / out2 in this model) both leave the parameter untouched when
+weight_decay = 0 (the reference's setting, configs/dtu_pretrain.yaml:59); with weight decay the flat update decays them too.
 """
 from __future__ import annotations
 
