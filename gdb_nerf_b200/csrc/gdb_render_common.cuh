@@ -122,5 +122,7 @@ __device__ __forceinline__ float4 bilerp4(float4 a00, float4 a10, float4 a01, fl
 int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int split, cudaStream_t st);
 // second-generation tensor-core variant (fp16 operands), gdb_render_tc2.cu
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st);
+// fourth-generation tensor-core kernel (fp16 operands, the default of precision 1), gdb_render_tc3.cu
+int render_tc3_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st);
 
 }  // namespace gdb

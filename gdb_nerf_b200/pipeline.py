@@ -93,7 +93,18 @@ class PinnedUploader:
         buf.copy_(t)
         return buf
 
+    def _stage_cat(self, slot: int, key: str, ts: Sequence[torch.Tensor]) -> torch.Tensor:
+        shape = (sum(int(t.shape[0]) for t in ts),) + tuple(ts[0].shape[1:])
+        buf = self._host[slot].get(key)
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != ts[0].dtype:
+            buf = torch.empty(shape, dtype=ts[0].dtype).pin_memory()
+            self._host[slot][key] = buf
+        torch.cat([t.cpu() for t in ts], 0, out=buf)
+        return buf
+
     def _walk(self, slot: int, batch: Any, prefix: str) -> Any:
+        if isinstance(batch, _CatList):
+            return self._stage_cat(slot, prefix, batch).to(self.device, non_blocking=True)
         if isinstance(batch, Mapping):
             return {k: (v if k == "meta" else self._walk(slot, v, f"{prefix}{k}.")) for k, v in batch.items()}
         if isinstance(batch, (tuple, list)):
@@ -117,41 +128,84 @@ class PinnedUploader:
         return dev, done
 
 
+class _CatList(list):
+    """Marker for `PinnedUploader`: host tensors to be concatenated along dim 0 straight into the pinned staging buffer."""
+
+
+def _merge_batches(items: Sequence[Any]) -> Any:
+    """Batch dicts of several target views -> one structure whose tensor leaves are `_CatList`s (``meta`` -> list of metas)."""
+    first = items[0]
+    if isinstance(first, Mapping):
+        return {k: ([it[k] for it in items] if k == "meta" else _merge_batches([it[k] for it in items])) for k in first}
+    if isinstance(first, (tuple, list)):
+        return [_merge_batches([it[j] for it in items]) for j in range(len(first))]
+    if torch.is_tensor(first):
+        return _CatList(items)
+    return first
+
+
 def render_sweep(net: torch.nn.Module, batches: Sequence[Mapping] | Callable[[int], Mapping], n_views: Optional[int] = None,
                  rank: int = 0, world: int = 1, device: torch.device | str = "cuda:0",
-                 keys: Sequence[str] = ("rgb",)) -> Iterator[Tuple[int, Dict[str, torch.Tensor]]]:
+                 keys: Sequence[str] = ("rgb",), views_per_call: int = 1, copy: bool = True) -> Iterator[Tuple[int, Dict[str, torch.Tensor]]]:
     """The evaluation loop of run.py:53-66 for this rank's share of a sweep: yields ``(view_index, {key: host tensor})`` in
-    order.  ``batches`` is a sequence of (host) batch dicts or a function ``index -> batch``; view ``i`` goes to rank
-    ``i % world``.  The upload of the next batch overlaps the kernels of the current one; results come back through pinned
-    buffers.  There is no collective: ranks are independent."""
+    order.  ``batches`` is a sequence of (host) batch dicts of ONE target view each or a function ``index -> batch``; view
+    ``i`` goes to rank ``i % world``.  There is no collective: ranks are independent.
+
+    The loop is pipelined so that the GPU never waits for the host: ``views_per_call`` consecutive views of this rank are
+    concatenated into one forward (target views are independent, so this is the reference's loop with its iterations
+    batched; 1 = the reference's one view per call), the upload of call c+1 and the kernels of call c+1 are enqueued before
+    the results of call c are handed out, and results travel through a ring of three pinned buffers per key.  With
+    ``copy=False`` the yielded tensors are views of that ring, valid until two further calls have been consumed (an
+    evaluator that reduces each view to its metrics or writes it to disk, as evaluators/gdb_nerf.py does, needs no copy)."""
     n = len(batches) if n_views is None else n_views       # type: ignore[arg-type]
     get = batches if callable(batches) else (lambda i: batches[i])      # type: ignore[index]
     mine = shard_views(n, rank, world)
     if not mine:
         return
+    vpc = max(1, int(views_per_call))
+    calls = [mine[i: i + vpc] for i in range(0, len(mine), vpc)]
     up = PinnedUploader(device)
     compute = torch.cuda.current_stream(torch.device(device))
-    nxt = up.upload(get(mine[0]))
-    out_host: Dict[str, List[torch.Tensor]] = {}
-    for j, idx in enumerate(mine):
-        dev_batch, arrived = nxt
-        if j + 1 < len(mine):
-            nxt = up.upload(get(mine[j + 1]))
+    ring = 3
+    out_host: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * ring for k in keys}
+
+    def stage(call):
+        items = [get(i) for i in call]
+        return up.upload(items[0] if len(items) == 1 else _merge_batches(items))
+
+    def launch(c, staged):
+        dev_batch, arrived = staged
         compute.wait_event(arrived)
         _record_stream(dev_batch, compute)      # allocated on the upload stream, consumed on the compute stream
         with torch.no_grad():
             ret, _, _ = net(dev_batch)
+        slot = c % ring
         res = {}
         for k in keys:
-            bufs = out_host.setdefault(k, [])
-            slot = j % 2
-            if len(bufs) <= slot or bufs[slot].shape != ret[k].shape:
+            buf = out_host[k][slot]
+            if buf is None or buf.shape != ret[k].shape or buf.dtype != ret[k].dtype:
                 buf = torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory()
-                if len(bufs) <= slot:
-                    bufs.append(buf)
-                else:
-                    bufs[slot] = buf
-            bufs[slot].copy_(ret[k], non_blocking=True)
-            res[k] = bufs[slot]
-        compute.synchronize()
-        yield idx, {k: v.clone() for k, v in res.items()}
+                out_host[k][slot] = buf
+            buf.copy_(ret[k], non_blocking=True)
+            res[k] = buf
+        done = torch.cuda.Event()
+        done.record(compute)
+        return res, done
+
+    staged = stage(calls[0])
+    pending = None
+    for c, call in enumerate(calls):
+        cur = launch(c, staged)
+        if c + 1 < len(calls):
+            staged = stage(calls[c + 1])
+        if pending is not None:
+            yield from _hand_out(*pending, copy)
+        pending = (call, cur)
+    yield from _hand_out(*pending, copy)
+
+
+def _hand_out(call, cur, copy):
+    res, done = cur
+    done.synchronize()
+    for j, idx in enumerate(call):
+        yield idx, {k: (v[j: j + 1].clone() if copy else v[j: j + 1]) for k, v in res.items()}

@@ -315,6 +315,14 @@ def test_render_sweep_matches_direct_forward():
         assert _md(got[i]["rgb"], want[i]) <= 1e-5
     part = dict(render_sweep(net, batches, rank=1, world=2, device=DEV))
     assert sorted(part) == [1, 3] and _md(part[3]["rgb"], want[3]) <= 1e-5
+    # several views per forward (the reference's loop with its independent iterations batched), zero-copy results: a yielded
+    # tensor is valid until two further calls have been consumed, so it is compared as it arrives
+    seen = []
+    for idx, res in render_sweep(net, batches, device=DEV, views_per_call=2, copy=False, keys=("rgb", "nerf_depth")):
+        assert res["rgb"].shape == want[idx].shape and res["nerf_depth"].shape[0] == 1
+        assert _md(res["rgb"], want[idx]) <= 1e-4, idx          # cuDNN may pick another algorithm for the larger batch
+        seen.append(idx)
+    assert seen == [0, 1, 2, 3, 4]
 
 
 @pytest.mark.parametrize("recipe,hw", [("dtu_eval", (64, 96)), ("nerf_eval_4x4", (128, 160))])

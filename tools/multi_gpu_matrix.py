@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--workloads", default="dtu,llff,nerf")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_matrix.jsonl"))
     ap.add_argument("--no-train-graph", action="store_true")
+    ap.add_argument("--sweep-views-per-call", type=int, default=5)
     args = ap.parse_args()
 
     from gdb_nerf_b200.config import make_cfg
@@ -50,17 +51,25 @@ def main():
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a rank that dies must not leave the others (and an N-GPU box charged N times) waiting ten minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     sizes = [n for n in (1, 2, 4, 8) if n <= world]
     groups = {}
     for n in sizes:                       # every rank takes part in every new_group call
         groups[n] = None if world == 1 else (dist.group.WORLD if n == world else dist.new_group(list(range(n))))
     lines = []
 
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        open(args.out, "w").close()
+
     def emit(d):
         if rank == 0:
             print(json.dumps(d), flush=True)
             lines.append(d)
+            with open(args.out, "a") as fh:          # line by line: a later section that dies does not take these with it
+                fh.write(json.dumps(d) + "\n")
 
     def world_barrier():
         torch.cuda.synchronize()
@@ -150,18 +159,21 @@ def main():
             n_views = 200
             mine = shard_views(n_views, rank, world)
             store = {i: with_uint8_images(workload_batch("nerf", B=1, V=3, seed=i, view_offset=i, images="noise8")) for i in mine}
-            for _ in render_sweep(net, lambda i: store[i], n_views=min(2 * world, n_views), rank=rank, world=world, device=dev, keys=("rgb", "nerf_depth")):
+            vpc = args.sweep_views_per_call
+            for _ in render_sweep(net, lambda i: store[i], n_views=min(2 * vpc * world, n_views), rank=rank, world=world, device=dev, keys=("rgb", "nerf_depth"),
+                                  views_per_call=vpc, copy=False):
                 pass
             world_barrier()
             t0 = time.perf_counter()
             got = 0
-            for idx, res in render_sweep(net, lambda i: store[i], n_views=n_views, rank=rank, world=world, device=dev, keys=("rgb", "nerf_depth")):
+            for idx, res in render_sweep(net, lambda i: store[i], n_views=n_views, rank=rank, world=world, device=dev, keys=("rgb", "nerf_depth"),
+                                         views_per_call=vpc, copy=False):
                 got += 1
             torch.cuda.synchronize()
             sec = group_max([time.perf_counter() - t0], world)[0]
             world_barrier()
-            emit({"section": "sweep", "workload": f"NeRF-synthetic 800x800, 4x4 bundles, {n_views}-view render sweep (pipeline.render_sweep: pinned double-buffered "
-                  "uploads of 8-bit images, image + depth copied back per view)", "n_gpus": world, "views_per_gpu": len(mine),
+            emit({"section": "sweep", "workload": f"NeRF-synthetic 800x800, 4x4 bundles, {n_views}-view render sweep (pipeline.render_sweep: {vpc} views per forward, pinned double-buffered "
+                  "uploads of 8-bit images, image + depth of every view copied back into pinned memory, consumed in place)", "n_gpus": world, "views_per_call": vpc, "views_per_gpu": len(mine),
                   "value": n_views * H * W / sec, "unit": "rays/s", "seconds": sec, "ms_per_view_per_gpu": 1e3 * sec / max(len(mine), 1)})
             del store
 
@@ -219,7 +231,14 @@ def main():
                 if n > 1:
                     net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net, process_group=grp)
                 net.train()
-                net_g = None if args.no_train_graph else copy.deepcopy(net)
+                net_g = None
+                if not args.no_train_graph:         # a second instance with the same weights (SyncBatchNorm holds a process group: no deepcopy)
+                    torch.manual_seed(0)
+                    net_g = Network(cfg).to(dev)
+                    if n > 1:
+                        net_g = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net_g, process_group=grp)
+                    net_g.load_state_dict(net.state_dict())
+                    net_g.train()
                 opt = FlatAdam(net.parameters(), lr=5e-4)
 
                 def step():
@@ -278,11 +297,6 @@ def main():
                       "eager_ms_per_step": ms_eager, "graph_ms_per_step": ms_graph if okmin > 0 else None, "allreduce_ms": ms_ar if n > 1 else None,
                       "allreduce_plus_clip_adam_ms": ms_tail, "allreduce_bytes": nbytes})
 
-    if rank == 0:
-        os.makedirs(os.path.dirname(args.out), exist_ok=True)
-        with open(args.out, "w") as fh:
-            for d in lines:
-                fh.write(json.dumps(d) + "\n")
     if world > 1:
         dist.destroy_process_group()
 
