@@ -645,7 +645,10 @@ def run_train(args):
                        "parallelism": f"data parallel over {world} GPU(s): one NCCL all-reduce issued on the flat gradient per step, SyncBN"},
         }), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroying a communicator whose kernels sit in a captured graph never returned at N = 2 (round 2): leave at once
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -489,14 +489,14 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               "gdb_render_fused_fwd: image %dx%d not divisible by bundle size %d", H, W, bundle_size);
   GDB_REQUIRE(max_samples >= 1 && max_samples <= 32, GDB_E_BADARG, "gdb_render_fused_fwd: max_samples must be 1..32");
   GDB_REQUIRE(max_mip_level >= 0 && max_mip_level <= 3, GDB_E_UNSUPPORTED, "gdb_render_fused_fwd: max_mip_level must be 0..3");
-  GDB_REQUIRE(precision >= 0 && precision <= 5, GDB_E_UNSUPPORTED,
+  GDB_REQUIRE(precision >= 0 && precision <= 6, GDB_E_UNSUPPORTED,
               "gdb_render_fused_fwd: precision %d not built (0 = fp32 SIMT, 1 = fp16-operand tcgen05 MLP, 2 = split-fp16 tcgen05 MLP, "
-              "3 / 4 / 5 = first / second (round 1) / third generation of the fp16-operand kernel, kept for A/B)", precision);
+              "3 / 4 / 6 = first / second (round 1) / fourth generation of the fp16-operand kernel, kept for A/B; 5 = 1)", precision);
   GDB_REQUIRE(row_lo >= 0 && row_hi <= H / bundle_size && row_lo < row_hi, GDB_E_BADARG,
               "gdb_render_fused_fwd: row range [%d, %d) outside the %d bundle rows", row_lo, row_hi, H / bundle_size);
-  GDB_REQUIRE((row_lo == 0 && row_hi == H / bundle_size) || precision == 1 || precision == 4 || precision == 5, GDB_E_UNSUPPORTED,
-              "gdb_render_fused_fwd: a partial row range needs precision 1, 4 or 5 (got %d)", precision);
-  GDB_REQUIRE(!(precision == 1 && out_channels_last) || (aligned16(out_feat) && aligned16(out_dec)), GDB_E_ALIGN,
+  GDB_REQUIRE((row_lo == 0 && row_hi == H / bundle_size) || precision == 1 || (precision >= 4 && precision <= 6), GDB_E_UNSUPPORTED,
+              "gdb_render_fused_fwd: a partial row range needs precision 1, 4, 5 or 6 (got %d)", precision);
+  GDB_REQUIRE(!((precision == 1 || precision == 5 || precision == 6) && out_channels_last) || (aligned16(out_feat) && aligned16(out_dec)), GDB_E_ALIGN,
               "gdb_render_fused_fwd: channels-last outputs must be 16-byte aligned");
   GDB_REQUIRE(aligned16(rgba) && aligned16(tex) && aligned16(vol_cl) && aligned16(mlp), GDB_E_ALIGN,
               "gdb_render_fused_fwd: rgba/tex/vol/mlp must be 16-byte aligned");
@@ -538,8 +538,8 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   p.tex_level[0] = 0;
   for (int k = 1; k <= 3; ++k) p.tex_level[k] = p.tex_level[k - 1] + (int64_t)B * V * (p.Hb >> (k - 1)) * (p.Wb >> (k - 1)) * FPad;
   cudaStream_t st = as_stream(stream);
-  if (precision == 1) return render_tc3_dispatch(p, bundle_size, feat_dim, V, st);
-  if (precision == 4 || precision == 5) return render_tc2_dispatch(p, bundle_size, feat_dim, V, precision == 5 ? 3 : 2, st);
+  if (precision == 6) return render_tc3_dispatch(p, bundle_size, feat_dim, V, st);
+  if (precision == 1 || precision == 4 || precision == 5) return render_tc2_dispatch(p, bundle_size, feat_dim, V, precision == 4 ? 2 : 3, st);
   if (precision >= 2) return render_tc_dispatch(p, bundle_size, feat_dim, V, precision == 2, st);
 #define GDB_R(BSZ, FD, VV) \
   if (bundle_size == BSZ && feat_dim == FD && V == VV) return launch_render<BSZ, FD, VV>(p, st);

@@ -1,4 +1,6 @@
-// K3, fourth-generation tensor-core kernel (precision 1: fp16 MLP operands, fp32 accumulation in TMEM): the default.
+// K3, fourth-generation tensor-core kernel (fp16 MLP operands, fp32 accumulation in TMEM): `precision = 6` of the C ABI, a
+// MEASURED VARIANT - the third generation (gdb_render_tc2.cu) stays the default: this kernel issues 7 % fewer instructions and
+// is 2-3 % faster at DTU 512x640 but 4-7 % slower at LLFF 640x960 and NeRF 800x800 4x4 (profiles/r02_k3_gen3_vs_gen4.log).
 //
 // Reference: bundle_sampler.py:193-371, nerf.py:58-115, utils.py:19-43,88-121.
 //
@@ -20,10 +22,16 @@
 //  * inactive rows are not masked to zero anywhere in the MLP operands: rows are independent in every GEMM, an inactive row's
 //    operands are finite by construction and its compositing weight is exactly 0.
 //
-// STAGE = 1 (GDB_K3_STAGE=1, the north star's "TMA / shared-memory staging" as a measured variant): the RGBA rows the colour
-// pass of a tile reads are copied into shared memory by the TMA unit (cp.async.bulk, one bulk copy per image row of a per-view
-// bounding box, issued when the tile's last GEMM has retired into the then dead X region, completed on an mbarrier underneath
-// the GEMM-4 epilogue and the feature compositing), and the colour taps become LDS; taps outside the box fall back to LDG.
+//  * operand chunks are CHB = 2048 + 64 / 80 bytes apart instead of 2048 (the UMMA leading-dimension offset is free): the quad lanes
+//    of a fetch iteration write the same rows of consecutive chunks, which with a 2048-byte stride fall on the same banks
+//    (ncu: 14 M of 75 M shared-memory wavefronts were bank-conflict replays, all of them these stores).
+//
+// Staging (north star: "TMA / shared-memory staging of source-feature tiles") was settled by measurement, not built: the
+// MEMSRC = 1 instantiation serves EVERY gather of the kernel from shared memory (no global latency, no L1 tag stage, no DRAM,
+// no staging cost - a bound no TMA scheme can beat) and runs 0.90 ms against 0.98 ms per 8 DTU views (NeRF 4x4: 1.94 vs 2.43,
+// LLFF 1.67 vs 1.84; profiles/r02_k3_variants.log, profiles/r02_ncu_full_k3_g4_ldsbound_dtu.json): the L1 data pipe stays at
+// 73 % because a shared-memory tap costs the same wavefronts as a global one, and the operand plan leaves 7.8 KB of the SM's
+// 227 KB free where one tile's colour footprint alone is 3 x 17 KB.
 #include <string>
 
 #include "gdb_render_tc2.cuh"
@@ -42,38 +50,39 @@ __device__ __forceinline__ float4 f4_scale(float4 v, float w) {
   return r;
 }
 
-// ---- TMA (bulk async copy) glue for the staged colour variant
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(mbar)
-               : "memory");
-}
-
+// operand plan of generation 4: Tc2Cfg's regions with a padded chunk stride
 template <int BS, int FEAT_DIM, int V, int NG>
 struct Tc3Cfg : Tc2Cfg<BS, FEAT_DIM, V, NG> {
   using Base = Tc2Cfg<BS, FEAT_DIM, V, NG>;
-  // staged colour boxes: region X of the group (dead once GEMM 4 has retired), one box per view
-  static constexpr int BOX_BYTES = (Base::CH_X * 2048 / V) & ~127;
-  static constexpr int BOX_PIX = BOX_BYTES / 16;
-  static constexpr int BOX_MAX_ROWS = 16;
-  // per-group control block of the staged variant, appended to the camera block: mbarrier (8 B) + per view (x0, y0, w, h)
-  static constexpr int STG_OFF = Base::GROUP_BYTES;
-  static constexpr int GROUP_BYTES_S = Base::GROUP_BYTES + 128;
-  static constexpr int ZERO_OFF_S = Base::GROUP_OFF + NG * GROUP_BYTES_S;
-  static constexpr int ONE_OFF_S = ZERO_OFF_S + 2048;
-  static constexpr int SMEM_S = ONE_OFF_S + 2048;
+  static constexpr int CHB = 2048 + (NG >= 4 ? 64 : 80);   // bytes between consecutive operand chunks (what the 227 KB allow)
+  static constexpr int A_X = 0;
+  static constexpr int A_FD = A_X + Base::CH_X * CHB;
+  static constexpr int A_S = A_FD + Base::CH_FD * CHB;
+  static constexpr int A_END = ((A_S + Base::CH_S * CHB + 127) / 128) * 128;
+  static constexpr int CAM_OFF = A_END + 128;          // mbarrier at A_END
+  static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
+  static constexpr int ZERO_OFF = Base::GROUP_OFF + NG * GROUP_BYTES;
+  static constexpr int ONE_OFF = ZERO_OFF + 2048;
+  static constexpr int SMEM = ONE_OFF + 2048;
+  static_assert(32 * Base::NCP * 4 <= 512 * (Base::CH_X + Base::CH_FD), "compositing stash must fit in the warp's rows of X + FD");
 };
 
-template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int STAGE, int PB, int MEMSRC = 0>
+// `nch` consecutive chunks (CHB apart) starting at `a` (odd counts pair the last chunk with the zero chunk)
+template <int CHB>
+__device__ __forceinline__ void mma_chunks_p(uint32_t d_tmem, uint32_t a, int nch, uint32_t zero_chunk, uint32_t b_addr, int N,
+                                             uint32_t accumulate) {
+  for (int ks = 0; 2 * ks < nch; ++ks) {
+    const uint32_t a0 = a + ks * 2 * CHB;
+    const uint32_t a1 = (2 * ks + 1 < nch) ? a0 + CHB : zero_chunk;
+    mma_step(d_tmem, a0, a1, b_addr + ks * 2 * (N * 16), N, (ks > 0 || accumulate) ? 1u : 0u);
+  }
+}
+
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int PB, int MEMSRC = 0>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderParams p) {
   using C = Tc3Cfg<BS, FEAT_DIM, V, NG>;
   constexpr int BB = C::BB, F = C::F, FP = C::FP, R = C::R, CT = C::CT, QL = C::QL, IPW = C::IPW;
-  constexpr int GROUP_BYTES = STAGE ? C::GROUP_BYTES_S : C::GROUP_BYTES;
-  constexpr int ZERO_OFF = STAGE ? C::ZERO_OFF_S : C::ZERO_OFF;
-  constexpr int ONE_OFF = STAGE ? C::ONE_OFF_S : C::ONE_OFF;
+  constexpr int CHB = C::CHB, GROUP_BYTES = C::GROUP_BYTES, ZERO_OFF = C::ZERO_OFF, ONE_OFF = C::ONE_OFF;
   static_assert(C::XCH >= 3 && C::FDCH >= 2, "five 16-byte descriptor slots per (row, view)");
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
@@ -84,8 +93,6 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
   const int wq = warp & 3;
   unsigned char* gsm = smem + C::GROUP_OFF + (size_t)g * GROUP_BYTES;
   const uint32_t mbar = smem_u32(gsm + C::A_END);
-  const uint32_t sbar = smem_u32(gsm + C::STG_OFF);          // staged variant: completion of the tile's bulk copies
-  int* const sbox = reinterpret_cast<int*>(gsm + C::STG_OFF + 16);   // staged variant: (x0, y0, w, h) per view, h = 0: not staged
   const unsigned full = 0xffffffffu;
   // MEMSRC = 1 (GDB_K3_VARIANT=ldsbound, TIMING ONLY - the results are meaningless): every gather is served from the first 16 KB
   // of shared memory instead of global memory.  It bounds from below what ANY staging scheme (TMA boxes or otherwise) that
@@ -97,16 +104,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
 
   // ---- one-time setup: weights -> smem (fp16 B operands + fp32 vectors), constant chunks, mbarriers, TMEM
   {
-    tc2_stage_weights<C>(smem, vec, p.mlp, tid, blockDim.x);
-    if (STAGE)       // tc2_stage_weights wrote the constant chunks of the unstaged plan; this plan has them 128 B per group later
-      for (int i = tid; i < 128; i += blockDim.x) {
-        *reinterpret_cast<uint4*>(smem + ZERO_OFF + i * 16) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(smem + ONE_OFF + i * 16) = make_uint4(0x3C00u, 0, 0, 0);
-      }
-    if (row == 0) {
-      mbar_init(mbar, 1);
-      if (STAGE) mbar_init(sbar, 1);
-    }
+    tc2_stage_weights<C>(smem, vec, p.mlp, tid, blockDim.x);       // (its constant chunks land at this plan's ZERO_OFF / ONE_OFF)
+    if (row == 0) mbar_init(mbar, 1);
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                    "r"(C::TALLOC)
@@ -120,7 +119,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
   }
   const uint32_t tmem_group = tmem_base_s + g * C::TC;                      // column offset of my group
   const uint32_t tmem_row = tmem_group + ((uint32_t)(wq * 32) << 16);       // my warp's lane quarter
-  uint32_t parity = 0, sparity = 0;
+  uint32_t parity = 0;
 
   const uint32_t w_base = smem_u32(smem);
   const uint32_t zero_chunk = w_base + ZERO_OFF, one_chunk = w_base + ONE_OFF;
@@ -308,13 +307,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
       }
       // the descriptor of (row, view) travels through the row's own 16-byte slots of the X_v (3) and FD_v (2) operand regions:
       // the fetch lanes of the row read it there and overwrite it with the operands afterwards
-      unsigned char* dx_ = sX + (v * C::XCH) * 2048 + row * 16;
-      unsigned char* df_ = sFD + (v * C::FDCH) * 2048 + row * 16;
+      unsigned char* dx_ = sX + (v * C::XCH) * CHB + row * 16;
+      unsigned char* df_ = sFD + (v * C::FDCH) * CHB + row * 16;
       *reinterpret_cast<uint4*>(dx_) = o0;
-      *reinterpret_cast<uint4*>(dx_ + 2048) = o1;
-      *reinterpret_cast<float4*>(dx_ + 4096) = w0;
+      *reinterpret_cast<uint4*>(dx_ + CHB) = o1;
+      *reinterpret_cast<float4*>(dx_ + 2 * CHB) = w0;
       *reinterpret_cast<float4*>(df_) = w1;
-      *reinterpret_cast<float4*>(df_ + 2048) = dr;
+      *reinterpret_cast<float4*>(df_ + CHB) = dr;
     }
     {
       // the depth ranges of my next tile, in flight underneath this tile
@@ -356,15 +355,15 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
           float4 t[V][8];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const uint4 o0 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH) * 2048);
-            const uint4 o1 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH + 1) * 2048);
+            const uint4 o0 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH) * CHB);
+            const uint4 o1 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH + 1) * CHB);
             t[v][0] = gather(tq + o0.x); t[v][1] = gather(tq + o0.y); t[v][2] = gather(tq + o0.z); t[v][3] = gather(tq + o0.w);
             t[v][4] = gather(tq + o1.x); t[v][5] = gather(tq + o1.y); t[v][6] = gather(tq + o1.z); t[v][7] = gather(tq + o1.w);
           }
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const float4 w0 = *reinterpret_cast<const float4*>(dsx + (v * C::XCH + 2) * 2048);
-            const float4 w1 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH) * 2048);
+            const float4 w0 = *reinterpret_cast<const float4*>(dsx + (v * C::XCH + 2) * CHB);
+            const float4 w1 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH) * CHB);
             float4 f = f4_scale(t[v][0], w0.x);
             f = f4_scale_add(f, t[v][1], w0.y);
             f = f4_scale_add(f, t[v][2], w0.z);
@@ -381,23 +380,33 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
           if constexpr (PB > 1) {
             f = fb[v];
           } else {
-            const uint4 o0 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH) * 2048);
-            const uint4 o1 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH + 1) * 2048);
-            // eight unconditional taps in flight
+            const uint4 o0 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH) * CHB);
+            const uint4 o1 = *reinterpret_cast<const uint4*>(dsx + (v * C::XCH + 1) * CHB);
+            // unconditional taps in flight.  The second mip level is skipped when NO row of this instruction blends two levels
+            // (a warp-uniform branch; P1 gave such rows o1 = o0 and zero weights, and the level is a smooth function of depth and
+            // position, so neighbouring bundles mostly agree)
+            const bool two_levels = __any_sync(full, o1.x != o0.x);
             const float4 t0 = gather(tq + o0.x), t1 = gather(tq + o0.y), t2 = gather(tq + o0.z), t3 = gather(tq + o0.w);
-            const float4 t4 = gather(tq + o1.x), t5 = gather(tq + o1.y), t6 = gather(tq + o1.z), t7 = gather(tq + o1.w);
-            const float4 w0 = *reinterpret_cast<const float4*>(dsx + (v * C::XCH + 2) * 2048);
-            const float4 w1 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH) * 2048);
-            f = f4_scale(t0, w0.x);
-            f = f4_scale_add(f, t1, w0.y);
-            f = f4_scale_add(f, t2, w0.z);
-            f = f4_scale_add(f, t3, w0.w);
-            f = f4_scale_add(f, t4, w1.x);
-            f = f4_scale_add(f, t5, w1.y);
-            f = f4_scale_add(f, t6, w1.z);
-            f = f4_scale_add(f, t7, w1.w);
+            const float4 w0 = *reinterpret_cast<const float4*>(dsx + (v * C::XCH + 2) * CHB);
+            if (two_levels) {
+              const float4 t4 = gather(tq + o1.x), t5 = gather(tq + o1.y), t6 = gather(tq + o1.z), t7 = gather(tq + o1.w);
+              const float4 w1 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH) * CHB);
+              f = f4_scale(t0, w0.x);
+              f = f4_scale_add(f, t1, w0.y);
+              f = f4_scale_add(f, t2, w0.z);
+              f = f4_scale_add(f, t3, w0.w);
+              f = f4_scale_add(f, t4, w1.x);
+              f = f4_scale_add(f, t5, w1.y);
+              f = f4_scale_add(f, t6, w1.z);
+              f = f4_scale_add(f, t7, w1.w);
+            } else {
+              f = f4_scale(t0, w0.x);
+              f = f4_scale_add(f, t1, w0.y);
+              f = f4_scale_add(f, t2, w0.z);
+              f = f4_scale_add(f, t3, w0.w);
+            }
           }
-          const float4 q2 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH + 1) * 2048);
+          const float4 q2 = *reinterpret_cast<const float4*>(dsf + (v * C::FDCH + 1) * CHB);
           const float dir[4] = {q2.x, q2.y, q2.z, q2.w};
           if (TAPS && p.tap_rfd && ok && act_g) {
             float* tp = p.tap_rfd + ((size_t)v * p.S_total + srow_g) * C::RFD + R + gq * 4;
@@ -416,8 +425,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
           }
           __syncwarp();                     // every lane of the row has read the descriptor that the operands now replace
           if (ok) {
-            unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * 2048 + orow16;
-            unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * 2048 + orow16;
+            unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * CHB + orow16;
+            unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * CHB + orow16;
             if (last_quad) {
               // featrgb's pad channel is K slot F: dir_v follows in FD, the constant one in X
               *reinterpret_cast<uint4*>(fdp) = make_uint4(pack_h2(fe[0], fe[1]), pack_h2(fe[2], dir[0]), pack_h2(dir[1], dir[2]), pack_h2(dir[3], 0.f));
@@ -444,8 +453,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
             mean[e] = mu;
           }
           const int kv = gq, km = QL + gq;      // quad positions of var / mean inside S
-          *reinterpret_cast<uint2*>(sS + (kv >> 1) * 2048 + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
-          *reinterpret_cast<uint2*>(sS + (km >> 1) * 2048 + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
+          *reinterpret_cast<uint2*>(sS + (kv >> 1) * CHB + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
+          *reinterpret_cast<uint2*>(sS + (km >> 1) * CHB + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
         }
       }
     }
@@ -458,8 +467,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
       tc_fence_after();
 #pragma unroll 1
       for (int v = 0; v < V; ++v) {
-        mma_chunks(tmem_group + v * 32, aS, C::SCH, zero_chunk, w_base + C::W_GS, 32, 0);
-        mma_chunks(tmem_group + v * 32, aX + v * C::XCH * 2048, C::XCH, zero_chunk, w_base + C::W_GX, 32, 1);
+        mma_chunks_p<CHB>(tmem_group + v * 32, aS, C::SCH, zero_chunk, w_base + C::W_GS, 32, 0);
+        mma_chunks_p<CHB>(tmem_group + v * 32, aX + v * C::XCH * CHB, C::XCH, zero_chunk, w_base + C::W_GX, 32, 1);
       }
       umma_commit(mbar);
     }
@@ -510,7 +519,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(im[ch * 8 + 0], im[ch * 8 + 1]), pack_h2(im[ch * 8 + 2], im[ch * 8 + 3]),
+        *reinterpret_cast<uint4*>(sS + ch * CHB + row * 16) = make_uint4(pack_h2(im[ch * 8 + 0], im[ch * 8 + 1]), pack_h2(im[ch * 8 + 2], im[ch * 8 + 3]),
                                                                           pack_h2(im[ch * 8 + 4], im[ch * 8 + 5]), pack_h2(im[ch * 8 + 6], im[ch * 8 + 7]));
     }
     // ================= GEMM 2: fc =================
@@ -519,7 +528,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      mma_chunks(tmem_group, aS, 4, zero_chunk, w_base + C::W_FC, 16, 0);
+      mma_chunks_p<CHB>(tmem_group, aS, 4, zero_chunk, w_base + C::W_FC, 16, 0);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -530,10 +539,10 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
 #pragma unroll
       for (int k = 0; k < 16; ++k) img[k] = fmaxf(img[k] + vec[C::X_FC_B + k], 0.f);
       // X[8] <- vox, S[0..1] <- img (their previous contents were consumed by GEMMs 1 and 2)
-      *reinterpret_cast<uint4*>(sX + 8 * 2048 + row * 16) = voxh;
+      *reinterpret_cast<uint4*>(sX + 8 * CHB + row * 16) = voxh;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
-        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(img[ch * 8 + 0], img[ch * 8 + 1]), pack_h2(img[ch * 8 + 2], img[ch * 8 + 3]),
+        *reinterpret_cast<uint4*>(sS + ch * CHB + row * 16) = make_uint4(pack_h2(img[ch * 8 + 0], img[ch * 8 + 1]), pack_h2(img[ch * 8 + 2], img[ch * 8 + 3]),
                                                                           pack_h2(img[ch * 8 + 4], img[ch * 8 + 5]), pack_h2(img[ch * 8 + 6], img[ch * 8 + 7]));
     }
     // ================= GEMM 3: lr0 on [vox | img | 1] =================
@@ -542,8 +551,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      mma_step(tmem_group, aX + 8 * 2048, aS, w_base + C::W_LR0, 64, 0);
-      mma_step(tmem_group, aS + 2048, one_chunk, w_base + C::W_LR0 + 2 * 64 * 16, 64, 1);
+      mma_step(tmem_group, aX + 8 * CHB, aS, w_base + C::W_LR0, 64, 0);
+      mma_step(tmem_group, aS + CHB, one_chunk, w_base + C::W_LR0 + 2 * 64 * 16, 64, 1);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
       tmem_ld32(tmem_row + half * 32, h);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sX + (half * 4 + ch) * 2048 + row * 16) =
+        *reinterpret_cast<uint4*>(sX + (half * 4 + ch) * CHB + row * 16) =
             make_uint4(pack_h2(fmaxf(h[ch * 8 + 0], 0.f), fmaxf(h[ch * 8 + 1], 0.f)), pack_h2(fmaxf(h[ch * 8 + 2], 0.f), fmaxf(h[ch * 8 + 3], 0.f)),
                        pack_h2(fmaxf(h[ch * 8 + 4], 0.f), fmaxf(h[ch * 8 + 5], 0.f)), pack_h2(fmaxf(h[ch * 8 + 6], 0.f), fmaxf(h[ch * 8 + 7], 0.f)));
     }
@@ -568,14 +577,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
       group_sync(g);
       if (row == 0) {
         tc_fence_after();
-        if (r == 0) mma_chunks(tmem_group + (C::NB - 1) * 64, aX, 8, zero_chunk, w_base + C::W_SH, 16, 0);
+        if (r == 0) mma_chunks_p<CHB>(tmem_group + (C::NB - 1) * 64, aX, 8, zero_chunk, w_base + C::W_SH, 16, 0);
 #pragma unroll 1
         for (int i = 0; i < nv; ++i) {
           const uint32_t d = tmem_group + i * 64;
-          mma_chunks(d, aX, 8, zero_chunk, w_base + C::W_0S, 64, 0);                                   // h
-          mma_step(d, aX + 8 * 2048, aS, w_base + C::W_0S + 8 * 64 * 16, 64, 1);                        // vox | img[0:8]
-          mma_step(d, aS + 2048, one_chunk, w_base + C::W_0S + 10 * 64 * 16, 64, 1);                    // img[8:16] | 1
-          mma_chunks(d, aFD + (v0 + i) * C::FDCH * 2048, C::FDCH, zero_chunk, w_base + C::W_0V, 64, 1); // featrgb_v | dir_v
+          mma_chunks_p<CHB>(d, aX, 8, zero_chunk, w_base + C::W_0S, 64, 0);                                   // h
+          mma_step(d, aX + 8 * CHB, aS, w_base + C::W_0S + 8 * 64 * 16, 64, 1);                        // vox | img[0:8]
+          mma_step(d, aS + CHB, one_chunk, w_base + C::W_0S + 10 * 64 * 16, 64, 1);                    // img[8:16] | 1
+          mma_chunks_p<CHB>(d, aFD + (v0 + i) * C::FDCH * CHB, C::FDCH, zero_chunk, w_base + C::W_0V, 64, 1); // featrgb_v | dir_v
         }
         umma_commit(mbar);
       }
@@ -641,11 +650,9 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
     if (TAPS && p.tap_sigma && active) p.tap_sigma[srow] = sigma;
     if (TAPS && p.tap_w && active) p.tap_w[srow] = wgt;
 
-    // compositing / colour stash: the warp's own rows of the dead operand regions (X and FD; FD and S when X holds the staged
-    // colour boxes)
-    constexpr int STASH0 = STAGE ? C::A_FD : C::A_X;
-    auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + STASH0 + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
-    static_assert(32 * C::NCP * 4 <= 512 * (STAGE ? C::CH_FD + C::CH_S : C::CH_X + C::CH_FD), "compositing stash must fit in the warp's rows");
+    // compositing / colour stash: the warp's own rows of the dead operand regions X and FD
+    constexpr int STASH0 = C::A_X;
+    auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + STASH0 + ((t * 4) >> 9) * CHB + wq * 512 + ((t * 4) & 511)); };
     float* tf = (TAPS && p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
     // ---- blended features sum_v w_v featrgb_v (featrgb read back from the FD operand), geometry head, depth, opacity:
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const uint4 q = *reinterpret_cast<const uint4*>(sFD + (v * C::FDCH + ch) * 2048 + row * 16);
+          const uint4 q = *reinterpret_cast<const uint4*>(sFD + (v * C::FDCH + ch) * CHB + row * 16);
           const float2 f0 = h2_to_f2(q.x), f1 = h2_to_f2(q.y), f2 = h2_to_f2(q.z), f3 = h2_to_f2(q.w);
           acc[0] = fmaf(f0.x, wv[v], acc[0]); acc[1] = fmaf(f0.y, wv[v], acc[1]);
           acc[2] = fmaf(f1.x, wv[v], acc[2]); acc[3] = fmaf(f1.y, wv[v], acc[3]);
@@ -759,22 +766,22 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
         float w4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int v = 0; v < V; ++v) w4[v] = wv[v];
-        *reinterpret_cast<float4*>(sS + 2048 + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+        *reinterpret_cast<float4*>(sS + CHB + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
       }
       if (TAPS)
-        *reinterpret_cast<uint4*>(sS + 4096 + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
+        *reinterpret_cast<uint4*>(sS + 2 * CHB + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
       __syncwarp();
       // component-wise stash of the weighted colours: float index row * R + c * BB + j, in the warp's rows of FD (+ X)
-      static_assert(32 * R * 4 <= 512 * (STAGE ? C::CH_FD : C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows");
-      auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + STASH0 + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+      static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows");
+      auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + STASH0 + ((t * 4) >> 9) * CHB + wq * 512 + ((t * 4) & 511)); };
 #pragma unroll 1
       for (int it = 0; it < BB; ++it) {
         const int item = it * 32 + lane;
         const int r = item / BB, j = item - r * BB;
         const float4 ra = *reinterpret_cast<const float4*>(sS + (wq * 32 + r) * 16);
-        const float4 rb = *reinterpret_cast<const float4*>(sS + 2048 + (wq * 32 + r) * 16);
+        const float4 rb = *reinterpret_cast<const float4*>(sS + CHB + (wq * 32 + r) * 16);
         uint4 rc = make_uint4(0u, 0u, 0u, 0u);
-        if (TAPS) rc = *reinterpret_cast<const uint4*>(sS + 4096 + (wq * 32 + r) * 16);
+        if (TAPS) rc = *reinterpret_cast<const uint4*>(sS + 2 * CHB + (wq * 32 + r) * 16);
         const float zr = ra.x, wr = ra.w;
         // production build: a row without compositing weight contributes w * colour = 0 whatever it gathers: it reads pixel 0
         const bool actr = TAPS ? rc.x != 0 : wr != 0.f;
@@ -864,15 +871,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc3_kernel(const RenderPar
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(C::TALLOC) : "memory");
   }
-  (void)sbar; (void)sbox; (void)sparity;
 }
 
-template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int STAGE, int PB, int MEMSRC = 0>
+template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int PB, int MEMSRC = 0>
 static int launch_render_tc3_t(const RenderParams& p, cudaStream_t st) {
   using C = Tc3Cfg<BS, FEAT_DIM, V, NG>;
-  constexpr int SMEM = STAGE ? C::SMEM_S : C::SMEM;
-  static_assert(SMEM <= 227 * 1024, "shared memory plan");
-  auto kern = render_tc3_kernel<BS, FEAT_DIM, V, NG, TAPS, STAGE, PB, MEMSRC>;
+  constexpr int SMEM = C::SMEM;
+  static_assert(SMEM + 1024 <= 227 * 1024, "shared memory plan (dynamic + the kernel's 1 KB static section)");
+  auto kern = render_tc3_kernel<BS, FEAT_DIM, V, NG, TAPS, PB, MEMSRC>;
   static SmemOptIn opt;
   {
     cudaError_t e = opt_in_smem(opt, kern, SMEM);
@@ -888,10 +894,10 @@ static int launch_render_tc3_t(const RenderParams& p, cudaStream_t st) {
 template <int BS, int FEAT_DIM, int V, int NG, int PB = 1>
 static int launch_render_tc3(const RenderParams& p, cudaStream_t st) {
   const bool taps = p.tap_rfd || p.tap_vox || p.tap_sigma || p.tap_feat || p.tap_w;
-  return taps ? launch_render_tc3_t<BS, FEAT_DIM, V, NG, true, 0, PB>(p, st) : launch_render_tc3_t<BS, FEAT_DIM, V, NG, false, 0, PB>(p, st);
+  return taps ? launch_render_tc3_t<BS, FEAT_DIM, V, NG, true, PB>(p, st) : launch_render_tc3_t<BS, FEAT_DIM, V, NG, false, PB>(p, st);
 }
 
-// the fourth-generation kernel (default arithmetic of the C ABI's `precision = 1`).
+// the fourth-generation kernel (`precision = 6` of the C ABI).
 // GDB_K3_VARIANT (development A/B, V = 3 only): "pb" = all 8 V taps of a fetch iteration in flight; "ng3" / "ng1" = one tile slot
 // less per SM (more registers per thread, a larger L1); "ng3pb" / "ng1pb" = both.
 int render_tc3_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st) {
@@ -902,8 +908,8 @@ int render_tc3_dispatch(const RenderParams& p, int bundle_size, int feat_dim, in
     variant = s == "pb" ? 1 : s == "ng3" || s == "ng1" ? 2 : s == "ng3pb" || s == "ng1pb" ? 3 : s == "ldsbound" ? 4 : 0;
   }
   if (V == 3 && variant == 4) {      // timing only, see MEMSRC
-    if (bundle_size == 2 && feat_dim == 16) return launch_render_tc3_t<2, 16, 3, 4, false, 0, 1, 1>(p, st);
-    if (bundle_size == 4 && feat_dim == 32) return launch_render_tc3_t<4, 32, 3, 2, false, 0, 1, 1>(p, st);
+    if (bundle_size == 2 && feat_dim == 16) return launch_render_tc3_t<2, 16, 3, 4, false, 1, 1>(p, st);
+    if (bundle_size == 4 && feat_dim == 32) return launch_render_tc3_t<4, 32, 3, 2, false, 1, 1>(p, st);
   }
   if (V == 3 && variant) {
     if (bundle_size == 2 && feat_dim == 16)

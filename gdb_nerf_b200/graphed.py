@@ -92,12 +92,14 @@ class GraphedTrainStep:
     run a backward pass on the default stream before (autograd creates each parameter's AccumulateGrad node on the stream of
     its first backward; the capture needs them on its own stream - construct the stepper first, it warms up by itself).
 
+    ``group`` / ``world``: the process group (and its size) the gradient all-reduce runs over; the default is the whole job.
+
         stepper = GraphedTrainStep(net, opt, example_batch, loss_fn, params)
         loss = stepper(batch)          # device scalar, overwritten by the next call
     """
 
     def __init__(self, net: torch.nn.Module, opt, example_batch: Mapping, loss_fn, params,
-                 clip_value: float = 40.0, allreduce=None, warmup: int = 3, group=None) -> None:
+                 clip_value: float = 40.0, allreduce=None, warmup: int = 3, group=None, world=None) -> None:
         if not net.training:
             raise ValueError("GraphedTrainStep captures the training step; call net.train() first")
         from .optim import FlatAdam
@@ -114,7 +116,7 @@ class GraphedTrainStep:
             loss = loss_fn(out)
             loss.backward()
             if fused:
-                opt.step(group=group)                 # all-reduce on the flat gradient + fused average / clip / Adam
+                opt.step(group=group, world=world)    # all-reduce on the flat gradient + fused average / clip / Adam
             else:
                 if allreduce is not None:
                     allreduce(self.params)

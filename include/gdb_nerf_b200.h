@@ -171,7 +171,10 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          int precision /* 0 = fp32 SIMT MLP (1e-4 class); 1 = fp16-operand tcgen05 MLP, fp32 accumulate (2e-3 class);
                                           2 = split-fp16 (hi+lo) tcgen05 MLP, three MMAs per K step, fp32 accumulate (1e-4 class);
                                           3 = the first-generation kernel of class 1 (kept for A/B measurements);
-                                          4 = the round-1 kernel of class 1 (serial gathers; kept for A/B, bit-identical to 1) */,
+                                          4 = the round-1 kernel of class 1 (serial gathers; kept for A/B, bit-identical to 1);
+                                          5 = 1; 6 = the fourth-generation kernel of class 1 (weighted-sum taps, unconditional
+                                          gathers, padded operand chunks: a measured variant, within fp32 rounding of 1 in front of
+                                          the fp16 operand rounding) */,
                          int out_channels_last /* 0: planar out_feat; 1: channels-last out_feat + out_dec; 2: as 1, and the first pad
                                                   channel of out_dec is written as 1.0 instead of 0: a constant-one input channel whose
                                                   centre-tap weights carry the bias of the decoder's first convolution (needs dec_stride > feat_dim + 11) */,
@@ -181,7 +184,7 @@ int gdb_render_fused_fwd(const float* rgba, const float* tex, const float* vol_c
                          int row_lo, int row_hi /* bundle-map rows [row_lo, row_hi) rendered by this call (the image-tile split of one
                                                    target view over several GPUs: every output buffer has the full size, only the
                                                    rows of the range are written); 0, Hb = everything; partial ranges need
-                                                   precision 1 or 4 */,
+                                                   precision 1, 4, 5 or 6 */,
                          const gdb_render_taps* taps, void* stream);
 
 /* K2 fused with the probability head it follows (cost_reg_net.py:62-63 -> depth_net.py:172,479-514): logits =

@@ -270,7 +270,7 @@ def main():
                     try:
                         from gdb_nerf_b200.graphed import GraphedTrainStep
                         opt_g = FlatAdam(net_g.parameters(), lr=5e-4)
-                        graphed = GraphedTrainStep(net_g, opt_g, batch, loss_fn, opt_g.params, group=grp)
+                        graphed = GraphedTrainStep(net_g, opt_g, batch, loss_fn, opt_g.params, group=grp, world=n)
                         for _ in range(3):
                             graphed(batch)
                         torch.cuda.synchronize()
@@ -297,8 +297,12 @@ def main():
                       "eager_ms_per_step": ms_eager, "graph_ms_per_step": ms_graph if okmin > 0 else None, "allreduce_ms": ms_ar if n > 1 else None,
                       "allreduce_plus_clip_adam_ms": ms_tail, "allreduce_bytes": nbytes})
 
-    if world > 1:
-        dist.destroy_process_group()
+    # no destroy_process_group(): with a captured graph that holds NCCL kernels the teardown of the communicator never returned
+    # (N = 2, round 2); every line is already on disk, leave at once
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
