@@ -52,6 +52,9 @@ SIGNATURES = {
     "gdb_depth_range_from_logits_fwd": (c_i, [c_f, c_i, c_i, c_f, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f,
                                               c_f, c_f]),
     "gdb_prob_head_depth_range_split_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "gdb_prob_head_depth_range_tma_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "gdb_prob_head_tma_scratch_floats": (c_i64, [c_i, c_i, c_i, c_i]),
+    "gdb_prob_head_tma_counters": (c_i64, [c_i, c_i, c_i]),
     "gdb_prob_head_split_scratch_floats": (c_i64, [c_i, c_i, c_i, c_i]),
     "gdb_prob_head_split_counters": (c_i64, [c_i, c_i, c_i]),
     "gdb_prob_head_depth_range_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_f, c_f, c_f]),

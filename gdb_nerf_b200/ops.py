@@ -6,6 +6,8 @@ Every operator refuses CPU tensors: there is no fallback implementation.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Dict, NamedTuple, Optional, Tuple
 
@@ -189,10 +191,11 @@ def _prob_head_chunks(D: int) -> int:
 
 
 def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_scale: float, inv_depth: bool,
-                          want_prob: bool = False, split: bool = True) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
+                          want_prob: bool = False, split: bool = True, tma: Optional[bool] = None) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
     """K2 fused with the probability head: ``y`` is the U-Net's last feature volume, (B,8,D,h,w)-shaped over channels-last
     (B,D,h,w,8) memory, ``weight`` the head's (1,8,3,3,3) Conv3d weight (padding 1, no bias).
-    -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w), prob (B,D,h,w) or None."""
+    -> depth (B,1,h,w), ci (B,2,h,w), vol_range (B,2,h,w), prob (B,D,h,w) or None.
+    ``tma``: the TMA-fed second-generation kernel (default; ``GDB_PH_TMA=0`` or ``tma=False`` selects the hand-staged split kernel)."""
     _dev(y, weight, depth_range)
     if not (_is_cl(y) and y.shape[1] == 8 and tuple(weight.shape) == (1, 8, 3, 3, 3)):
         raise _lib.GdbError("prob_head_depth_range needs a dense channels-last (B,8,D,h,w) volume and a (1,8,3,3,3) weight")
@@ -214,6 +217,17 @@ def prob_head_depth_range(y: Tensor, weight: Tensor, depth_range: Tensor, ci_sca
     prob = torch.empty((B, D, h, w), device=dev, dtype=torch.float32) if want_prob else None
     lib = _lib.load()
     nch = _prob_head_chunks(D) if (split and not want_prob) else 1
+    if tma is None:
+        tma = os.environ.get("GDB_PH_TMA", "1") != "0"
+    if tma and not want_prob and B * nch <= 65535:
+        # haloed planes by TMA (out-of-bounds zero fill = the padding), each plane read once, weights as constant operands
+        scratch = torch.empty(int(lib.gdb_prob_head_tma_scratch_floats(B, h, w, nch)), device=dev, dtype=torch.float32)
+        counters = torch.empty(int(lib.gdb_prob_head_tma_counters(B, h, w)), device=dev, dtype=torch.int32)
+        _lib.check(lib.gdb_prob_head_depth_range_tma_fwd(y.data_ptr(), wk.data_ptr(), depth_range.data_ptr(), rh, rw, B, Cc, D, h, w,
+                                                         nch, float(ci_scale), int(inv_depth), scratch.data_ptr(), counters.data_ptr(),
+                                                         depth.data_ptr(), ci.data_ptr(), vol.data_ptr(), _stream()),
+                   "gdb_prob_head_depth_range_tma_fwd")
+        return depth, ci, vol, None
     if nch > 1 and B * nch <= 65535:
         # depth axis split over nch CTAs per tile (on-line soft-max partials merged by the tile's last CTA)
         scratch = torch.empty(int(lib.gdb_prob_head_split_scratch_floats(B, h, w, nch)), device=dev, dtype=torch.float32)

@@ -60,6 +60,19 @@ def load_network(net: torch.nn.Module, model_dir: str, resume: bool = True, epoc
     return int(ckpt["epoch"]) + 1 if isinstance(ckpt, Mapping) and "epoch" in ckpt else 0
 
 
+_PINNED: Dict[Tuple, List[torch.Tensor]] = {}
+
+
+def _pinned(tag: Tuple, shape, dtype: torch.dtype) -> torch.Tensor:
+    """Page-locked host buffer from a process-wide pool keyed by (owner tag, shape, dtype): page-locking costs milliseconds per
+    buffer (and serialises between the ranks of a node), so a sweep re-uses the buffers of the sweeps before it."""
+    key = (tag, tuple(shape), dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = _PINNED[key] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    return buf
+
+
 def _record_stream(batch: Any, stream: torch.cuda.Stream) -> None:
     if isinstance(batch, Mapping):
         for k, v in batch.items():
@@ -81,24 +94,18 @@ class PinnedUploader:
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = slots
-        self._host: List[Dict[str, torch.Tensor]] = [dict() for _ in range(slots)]
+        torch.cuda.synchronize(self.device)     # the pooled staging buffers may still feed copies of an abandoned sweep
         self._free: List[Optional[torch.cuda.Event]] = [None] * slots
         self._turn = 0
 
     def _stage(self, slot: int, key: str, t: torch.Tensor) -> torch.Tensor:
-        buf = self._host[slot].get(key)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-            buf = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            self._host[slot][key] = buf
+        buf = _pinned(("up", str(self.device), slot, key), t.shape, t.dtype)
         buf.copy_(t)
         return buf
 
     def _stage_cat(self, slot: int, key: str, ts: Sequence[torch.Tensor]) -> torch.Tensor:
         shape = (sum(int(t.shape[0]) for t in ts),) + tuple(ts[0].shape[1:])
-        buf = self._host[slot].get(key)
-        if buf is None or tuple(buf.shape) != shape or buf.dtype != ts[0].dtype:
-            buf = torch.empty(shape, dtype=ts[0].dtype).pin_memory()
-            self._host[slot][key] = buf
+        buf = _pinned(("up", str(self.device), slot, key), shape, ts[0].dtype)
         torch.cat([t.cpu() for t in ts], 0, out=buf)
         return buf
 
@@ -167,7 +174,6 @@ def render_sweep(net: torch.nn.Module, batches: Sequence[Mapping] | Callable[[in
     up = PinnedUploader(device)
     compute = torch.cuda.current_stream(torch.device(device))
     ring = 3
-    out_host: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * ring for k in keys}
 
     def stage(call):
         items = [get(i) for i in call]
@@ -182,10 +188,7 @@ def render_sweep(net: torch.nn.Module, batches: Sequence[Mapping] | Callable[[in
         slot = c % ring
         res = {}
         for k in keys:
-            buf = out_host[k][slot]
-            if buf is None or buf.shape != ret[k].shape or buf.dtype != ret[k].dtype:
-                buf = torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory()
-                out_host[k][slot] = buf
+            buf = _pinned(("down", str(device), slot, k), ret[k].shape, ret[k].dtype)
             buf.copy_(ret[k], non_blocking=True)
             res[k] = buf
         done = torch.cuda.Event()

@@ -205,6 +205,18 @@ int gdb_prob_head_depth_range_split_fwd(const float* y_cl, const float* weight, 
                                         int C, int D, int h, int w, int nchunks, float ci_scale, int inv_depth, float* scratch,
                                         int* counters, float* depth, float* ci, float* vol_range, void* stream);
 
+/* Second generation of the split operator (same arguments, same results to fp32 summation order): the haloed depth planes
+ * arrive by TMA (cp.async.bulk.tensor.5d; the tensor map's out-of-bounds zero fill is the convolution's padding in x, y and
+ * depth), every plane is read from shared memory once and scattered into the three output planes it contributes to, and the
+ * 216 weights are constant operands (copied device-to-device into constant memory by every call: a memcpy node under stream
+ * capture; concurrent calls on different streams of one device must use the same weights).  Pixel tiles are 8 x 16:
+ * gdb_prob_head_tma_scratch_floats / _counters size the two work buffers.  Replaces cost_reg_net.py:62-63 + depth_net.py:479-514. */
+int64_t gdb_prob_head_tma_scratch_floats(int B, int h, int w, int nchunks);
+int64_t gdb_prob_head_tma_counters(int B, int h, int w);
+int gdb_prob_head_depth_range_tma_fwd(const float* y_cl, const float* weight, const float* depth_range, int rh, int rw, int B,
+                                      int C, int D, int h, int w, int nchunks, float ci_scale, int inv_depth, float* scratch,
+                                      int* counters, float* depth, float* ci, float* vol_range, void* stream);
+
 /* Output assembly, replaces network.py:175-182 minus the decoder CNN:
  * rgb = dec + pixel_shuffle(feat[:, :3b^2], b)  (reweighting: 0.5*(rgb + fine))
  * and the bilinear xb up-sampling of depth and opacity.

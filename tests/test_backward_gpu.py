@@ -370,6 +370,7 @@ def test_flat_adam_training_step_is_graph_capturable():
         loss_b = stepper(batch)
     torch.cuda.synchronize()
     opt_a = FlatAdam(net_a.parameters(), lr=5e-4)
+    before = opt_a.param_flat.clone()
     for _ in range(5):
         opt_a.zero_grad()
         loss_a = loss_fn(net_a(batch))
@@ -377,6 +378,10 @@ def test_flat_adam_training_step_is_graph_capturable():
         opt_a.step()
     torch.cuda.synchronize()
     assert float(opt_a.state[0]) == float(opt_b.state[0]) == 5.0
-    assert abs(float(loss_a) - float(loss_b)) <= 1e-3 * abs(float(loss_a))
-    rel = float((opt_a.param_flat - opt_b.param_flat).abs().max()) / float(opt_a.param_flat.abs().max())
-    assert rel <= 2e-3, rel                                                # atomics in the backward kernels: not bit-stable
+    assert abs(float(loss_a.detach()) - float(loss_b)) <= 1e-3 * abs(float(loss_a.detach()))
+    # atomics in the backward kernels are not bit-stable and Adam turns a gradient of either sign into a step of size lr, so
+    # single parameters with a gradient near zero may walk apart by up to 2 * steps * lr; what must agree is the bulk of the update
+    diff = (opt_a.param_flat - opt_b.param_flat).abs()
+    moved = (opt_a.param_flat - before).abs()
+    assert float(diff.mean()) <= 0.02 * float(moved.mean()), (float(diff.mean()), float(moved.mean()))
+    assert float(diff.max()) <= 2 * 5 * 5e-4 * 1.001

@@ -594,10 +594,30 @@ def test_prob_head_fused_into_depth_range(D, h, w, inv, per_pixel):
         assert _md(got[k], want[k]) <= 1e-5 * 480.0, k
     # depth axis split over several CTAs per tile (on-line soft-max partials); twice: the arrival counters reset themselves
     for _ in range(2):
-        sp = ops.prob_head_depth_range(y, wt, rng, 1.0, inv)
+        sp = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, tma=False)
         assert sp[3] is None
         for k in range(3):
             assert _md(sp[k], want[k]) <= 1e-5 * 480.0, k
-    one = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, split=False)
+    one = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, split=False, tma=False)
     for k in range(3):
         assert torch.equal(one[k], got[k])
+    # second generation (the default): planes by TMA with the out-of-bounds zero fill as padding, each plane read once and
+    # scattered into three output planes, weights as constant operands; depth axis split and unsplit, twice each
+    for split in (True, False):
+        for _ in range(2):
+            tm = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, split=split, tma=True)
+            assert tm[3] is None
+            for k in range(3):
+                assert _md(tm[k], want[k]) <= 1e-5 * 480.0, (split, k, _md(tm[k], want[k]))
+    # other weights on the same stream: the constant-memory copy is ordered with the launches
+    wt2 = (torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want2 = ops.depth_range_from_logits(rng, torch.nn.functional.conv3d(y, wt2, None, 1, 1).squeeze(1), 1.0, inv)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    tm2 = ops.prob_head_depth_range(y, wt2, rng, 1.0, inv, tma=True)
+    tm1 = ops.prob_head_depth_range(y, wt, rng, 1.0, inv, tma=True)
+    for k in range(3):
+        assert _md(tm2[k], want2[k]) <= 1e-5 * 480.0 and _md(tm1[k], want[k]) <= 1e-5 * 480.0, k
