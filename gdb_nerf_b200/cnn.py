@@ -72,7 +72,7 @@ def _wfolded(block: nn.Sequential, f_in: int):
 
 
 def can_wfold(x: torch.Tensor, f: int) -> bool:
-    return x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % f == 0 and x.permute(0, *range(2, x.dim()), 1).is_contiguous()
+    return x.is_cuda and x.dtype in (torch.float32, torch.float16) and x.shape[-1] % f == 0 and x.permute(0, *range(2, x.dim()), 1).is_contiguous()
 
 
 def run_block(block: nn.Sequential, x: torch.Tensor, wfold: int = 0) -> torch.Tensor:
@@ -243,7 +243,7 @@ def _deconv_skip(block: nn.Sequential, x: torch.Tensor, skip: torch.Tensor, wfol
         d = F.conv_transpose3d(x, w, None, tuple(conv.stride[:-1]) + (1,), conv.padding, tuple(conv.output_padding[:-1]) + (0,))
     else:
         d = F.conv_transpose3d(x, w, None, conv.stride, conv.padding, conv.output_padding)
-    if ops._is_cl(d) and ops._is_cl(skip) and d.shape[1] % 4 == 0:
+    if d.dtype == torch.float32 and ops._is_cl(d) and ops._is_cl(skip) and d.shape[1] % 4 == 0:
         return ops.bias_act_add(d, b, skip, relu=True)
     return skip + (d + b.view(1, -1, 1, 1, 1)).relu_()
 
