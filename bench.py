@@ -436,6 +436,31 @@ def run_ours(args, wl, cfg):
         latency = {"what": "Network.forward on ONE target view per call, inputs resident, wall clock per call, mean of 20",
                    "eager_ms": eager_ms, "cuda_graph_ms": (time.perf_counter() - t1) / 20 * 1e3}
         del runner
+        # and the benched batch itself back to back (no L2 flush between calls, wall clock): eager launches against one graph
+        # replay per step - how much of the step is launch gaps rather than kernels
+        try:
+            with torch.no_grad():
+                for _ in range(3):
+                    net(dev_batch)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            with torch.no_grad():
+                for _ in range(20):
+                    net(dev_batch)
+            torch.cuda.synchronize()
+            step_eager = (time.perf_counter() - t1) / 20 * 1e3
+            runner = GraphedForward(net, dev_batch)
+            for _ in range(3):
+                runner(dev_batch)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(20):
+                runner(dev_batch)
+            torch.cuda.synchronize()
+            latency["batch_step_back_to_back"] = {"views_per_step": B, "eager_ms": step_eager, "cuda_graph_ms": (time.perf_counter() - t1) / 20 * 1e3}
+            del runner
+        except Exception as exc:                         # never lose the headline to a side measurement
+            latency["batch_step_back_to_back"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
     barrier()
 
     # the reference's own CUDA forward on this GPU, same process (rank 0 of a single-GPU run only: it needs ~7 GB)
