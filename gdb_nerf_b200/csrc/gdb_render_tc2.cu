@@ -299,8 +299,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
       const float vw[4][4] = {{vw0.x, vw0.y, vw0.z, vw0.w}, {vw1.x, vw1.y, vw1.z, vw1.w}, {vw2.x, vw2.y, vw2.z, vw2.w}, {vw3.x, vw3.y, vw3.z, vw3.w}};
       const float vb[4] = {vbq.x, vbq.y, vbq.z, vbq.w};
+      // rows >= ns * G of a warp never hold a sample (slot-major rows: their slot index is >= max_samples; 30 of 32 rows are in
+      // use with 3 or 6 samples per bundle): the fetch iterations that would cover only such rows are skipped.  Their operand rows
+      // keep whatever the previous tile left there - rows are independent in every GEMM, nothing downstream reads them (the
+      // compositing sums run over rows < ns * G only) and their compositing weight is exactly 0.
+      const int nit = min(C::NIT, (ns * G + IPW - 1) / IPW);
 #pragma unroll 1
-      for (int it = 0; it < C::NIT; ++it) {
+      for (int it = 0; it < nit; ++it) {
         const int src_raw = it * IPW + gr;
         const bool ok = glane && src_raw < 32;
         const int src = min(src_raw, 31);
@@ -833,8 +838,9 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       // component-wise stash of the weighted colours: float index row * R + c * BB + j, in the warp's rows of X + FD
       static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows of X + FD");
       auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+      const int nit6 = min(BB, (ns * G * BB + 31) / 32);      // (row, ray) items of the rows that can hold a sample
 #pragma unroll 1
-      for (int it = 0; it < BB; ++it) {
+      for (int it = 0; it < nit6; ++it) {
         const int item = it * 32 + lane;
         const int r = item / BB, j = item - r * BB;
         const float4 ra = *reinterpret_cast<const float4*>(sS + (wq * 32 + r) * 16);
