@@ -154,15 +154,12 @@ __device__ __forceinline__ void unit3_fast(float& x, float& y, float& z) {
   const float inv = rsqrtf(fmaxf(x * x + y * y + z * z, 1e-24f));
   x *= inv; y *= inv; z *= inv;
 }
-// predicated 128-bit read-only load: no branch around it, so the compiler can keep a whole batch of gathers in flight behind
-// one another instead of one dependent group per basic block.  The result is UNDEFINED when the predicate is off (no zero
-// initialisation of the four destination registers: that was two CS2R per load, 4.6 % of the kernel's instructions): every
-// consumer either is guarded by the same condition (zero-weight voxel taps, the second mip level of a bi-linear sample) or
-// belongs to a row without a sample, whose operands and stash entries nothing reads and whose compositing weight is exactly 0.
+// predicated 128-bit read-only load (zero when the predicate is off): no branch around it, so the compiler can keep a
+// whole batch of gathers in flight behind one another instead of one dependent group per basic block
 __device__ __forceinline__ float4 ldg4_if(const float4* ptr, bool pred) {
-  float4 r;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}\n"
-      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
       : "l"(ptr), "r"((int)pred));
   return r;
 }
