@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       const float pxc = fmaf(ccx, cv[CV_K + 0] * ifb, fmaf(ccy, cv[CV_K + 1] * ifb, ccz * (cv[CV_K + 2] * ifb)));
       const float pyc = fmaf(ccx, cv[CV_K + 3] * ifb, fmaf(ccy, cv[CV_K + 4] * ifb, ccz * (cv[CV_K + 5] * ifb)));
       const float pzc = fmaxf(fmaf(ccx, cv[CV_K + 6], fmaf(ccy, cv[CV_K + 7], ccz * cv[CV_K + 8])), 1e-6f);
-      const float rz = fdiv(1.f, pzc);
+      const float rz = __frcp_rn(pzc);
       const float u01 = pxc * rz * inv_Wb, v01 = pyc * rz * inv_Hb;
       d_a0[v] = 0; d_a1[v] = 0; d_pk[v] = 0;
       d_fu0[v] = d_fv0[v] = d_fu1[v] = d_fv1[v] = d_fr[v] = 0.f;
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
           float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
           float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
-          const float rz = fdiv(1.f, iz);
+          const float rz = __frcp_rn(iz);
           float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
           const Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
           const float4* ib = reinterpret_cast<const float4*>(p.rgba) + (size_t)(b * V + v) * p.H * p.W;
