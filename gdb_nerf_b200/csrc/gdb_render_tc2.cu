@@ -1038,13 +1038,15 @@ static int launch_render_tc2(const RenderParams& p, cudaStream_t st) {
 }
 
 // gen = 2: the round-1 kernel (A/B reference, `precision = 4` of the C ABI); gen = 3: the batched-gather kernel (default).
-// The batching mode of the feature fetch (FB, see the kernel's header comment) defaults to 0; GDB_K3_FB = 1 / 2 select the
-// measured alternatives for the two benchmark shapes (V = 3).
+// The batching mode of the feature fetch (FB, see the kernel's header comment): measured best is one view at a time (FB = 0) for
+// 2x2 bundles (16 warps per SM at 128 registers: 0.95 / 1.07 ms at DTU with FB = 0 / 2) and all 8 V taps of an iteration in flight
+// (FB = 2) for 4x4 bundles (8 warps per SM at 255 registers: 2.36 / 2.24 ms at NeRF 800x800); GDB_K3_FB = 0 / 1 / 2 overrides
+// it for V = 3.
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st) {
-  static int fb_env = -1;
-  if (fb_env < 0) {
+  static int fb_env = -2;
+  if (fb_env == -2) {
     const char* e = getenv("GDB_K3_FB");
-    fb_env = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    fb_env = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
   }
   if (gen == 2) {
     if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 2, 0>(p, st);
@@ -1054,9 +1056,10 @@ int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, in
     if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 2, 0>(p, st);
     if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 2, 0>(p, st);
   } else {
-    if (V == 3 && fb_env != 0) {
-      if (bundle_size == 2 && feat_dim == 16) return fb_env == 1 ? launch_render_tc2<2, 16, 3, 4, 3, 1>(p, st) : launch_render_tc2<2, 16, 3, 4, 3, 2>(p, st);
-      if (bundle_size == 4 && feat_dim == 32) return fb_env == 1 ? launch_render_tc2<4, 32, 3, 2, 3, 1>(p, st) : launch_render_tc2<4, 32, 3, 2, 3, 2>(p, st);
+    if (V == 3) {
+      const int fb = fb_env >= 0 ? fb_env : (bundle_size == 4 ? 2 : 0);
+      if (bundle_size == 2 && feat_dim == 16 && fb) return fb == 1 ? launch_render_tc2<2, 16, 3, 4, 3, 1>(p, st) : launch_render_tc2<2, 16, 3, 4, 3, 2>(p, st);
+      if (bundle_size == 4 && feat_dim == 32 && fb) return fb == 1 ? launch_render_tc2<4, 32, 3, 2, 3, 1>(p, st) : launch_render_tc2<4, 32, 3, 2, 3, 2>(p, st);
     }
     if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 3, 0>(p, st);
     if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 3, 0>(p, st);
