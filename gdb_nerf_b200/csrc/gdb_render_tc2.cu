@@ -1063,7 +1063,11 @@ int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, in
     }
     if (bundle_size == 2 && feat_dim == 16 && V == 2) return launch_render_tc2<2, 16, 2, 4, 3, 0>(p, st);
     if (bundle_size == 2 && feat_dim == 16 && V == 3) return launch_render_tc2<2, 16, 3, 4, 3, 0>(p, st);
-    if (bundle_size == 2 && feat_dim == 16 && V == 4) return launch_render_tc2<2, 16, 4, 2, 3, 0>(p, st);
+    if (bundle_size == 2 && feat_dim == 16 && V == 4) {
+      static int ng_env = -1;
+      if (ng_env < 0) { const char* e = getenv("GDB_K3_NG_V4"); ng_env = (e && e[0] == '2') ? 2 : 3; }
+      return ng_env == 2 ? launch_render_tc2<2, 16, 4, 2, 3, 0>(p, st) : launch_render_tc2<2, 16, 4, 3, 3, 0>(p, st);
+    }
     if (bundle_size == 4 && feat_dim == 32 && V == 2) return launch_render_tc2<4, 32, 2, 2, 3, 0>(p, st);
     if (bundle_size == 4 && feat_dim == 32 && V == 3) return launch_render_tc2<4, 32, 3, 2, 3, 0>(p, st);
     if (bundle_size == 4 && feat_dim == 32 && V == 4) return launch_render_tc2<4, 32, 4, 1, 3, 0>(p, st);

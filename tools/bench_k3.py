@@ -16,6 +16,7 @@ ap.add_argument("--precisions", default="", help="comma-separated list, e.g. 4,1
 ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--workload", default="dtu")
+ap.add_argument("--V", type=int, default=3, help="source views (2, 3 or 4)")
 ap.add_argument("--lib", default="", help="alternative build of the library (A/B measurements)")
 ap.add_argument("--folded", action="store_true", help="volume in the depth-folded (B,Hb,Wb,D,12) layout of the 2-D cost-regularisation head")
 ap.add_argument("--noisy-depth", action="store_true", help="per-bundle white-noise depth (adversarial: no coherence between neighbouring bundles) "
@@ -26,7 +27,7 @@ if args.lib:
     from gdb_nerf_b200 import _lib as _L
     _L.LIB_PATH = os.path.abspath(args.lib)
 w = WORKLOADS[args.workload]; cfg = make_cfg(w["recipe"]); b = cfg.nerf.bundle_size
-H, W, V, B = w["H"], w["W"], 3, args.B
+H, W, V, B = w["H"], w["W"], args.V, args.B
 Hb, Wb = H // b, W // b
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
@@ -66,4 +67,4 @@ for prec in plist:
         e.record(); torch.cuda.synchronize()
         if i >= 2: ts.append(s.elapsed_time(e))
     ms = sum(ts) / len(ts)
-    print(f"{args.workload} precision {prec} (GDB_K3_FB={os.environ.get('GDB_K3_FB', '-')}): {ms:.4f} ms per launch ({B} views) = {ms / B * 1e3:.1f} us/view, min {min(ts):.4f}", flush=True)
+    print(f"{args.workload} V={V} precision {prec} (GDB_K3_FB={os.environ.get('GDB_K3_FB', '-')}): {ms:.4f} ms per launch ({B} views) = {ms / B * 1e3:.1f} us/view, min {min(ts):.4f}", flush=True)
