@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgdbnerf_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["gdb_costvolume.cu", "gdb_probhead_tma.cu", "gdb_sampling.cu", "gdb_prepare.cu", "gdb_render.cu", "gdb_render_tc.cu", "gdb_render_tc2.cu", "gdb_render_tc3.cu", "gdb_glue.cu", "gdb_costvolume_bwd.cu", "gdb_render_bwd.cu", "gdb_coarse.cu", "gdb_optim.cu"]
+SOURCES = ["gdb_costvolume.cu", "gdb_probhead_tma.cu", "gdb_sampling.cu", "gdb_prepare.cu", "gdb_render.cu", "gdb_render_tc.cu", "gdb_render_tc2.cu", "gdb_render_tc3.cu", "gdb_render_tc4.cu", "gdb_glue.cu", "gdb_costvolume_bwd.cu", "gdb_render_bwd.cu", "gdb_coarse.cu", "gdb_optim.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

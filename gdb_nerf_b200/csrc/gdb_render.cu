@@ -496,7 +496,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               "gdb_render_fused_fwd: row range [%d, %d) outside the %d bundle rows", row_lo, row_hi, H / bundle_size);
   GDB_REQUIRE((row_lo == 0 && row_hi == H / bundle_size) || precision == 1 || (precision >= 4 && precision <= 6), GDB_E_UNSUPPORTED,
               "gdb_render_fused_fwd: a partial row range needs precision 1, 4, 5 or 6 (got %d)", precision);
-  GDB_REQUIRE(!((precision == 1 || precision == 5 || precision == 6) && out_channels_last) || (aligned16(out_feat) && aligned16(out_dec)), GDB_E_ALIGN,
+  GDB_REQUIRE(!((precision == 1 || precision == 2 || precision == 5 || precision == 6) && out_channels_last) || (aligned16(out_feat) && aligned16(out_dec)), GDB_E_ALIGN,
               "gdb_render_fused_fwd: channels-last outputs must be 16-byte aligned");
   GDB_REQUIRE(aligned16(rgba) && aligned16(tex) && aligned16(vol_cl) && aligned16(mlp), GDB_E_ALIGN,
               "gdb_render_fused_fwd: rgba/tex/vol/mlp must be 16-byte aligned");
@@ -540,6 +540,7 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
   cudaStream_t st = as_stream(stream);
   if (precision == 6) return render_tc3_dispatch(p, bundle_size, feat_dim, V, st);
   if (precision == 1 || precision == 4 || precision == 5) return render_tc2_dispatch(p, bundle_size, feat_dim, V, precision == 4 ? 2 : 3, st);
+  if (precision == 2 && render_tc4_covers(p, bundle_size, feat_dim, V)) return render_tc4_dispatch(p, bundle_size, feat_dim, V, st);
   if (precision >= 2) return render_tc_dispatch(p, bundle_size, feat_dim, V, precision == 2, st);
 #define GDB_R(BSZ, FD, VV) \
   if (bundle_size == BSZ && feat_dim == FD && V == VV) return launch_render<BSZ, FD, VV>(p, st);

@@ -124,5 +124,9 @@ int render_tc_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int
 int render_tc2_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, int gen, cudaStream_t st);
 // fourth-generation tensor-core kernel (fp16 operands, the default of precision 1), gdb_render_tc3.cu
 int render_tc3_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st);
+// split-fp16 (fp32-class) arithmetic in the third-generation layout, gdb_render_tc4.cu: the production kernel of precision 2 where it
+// covers the call (2x2 bundles, three source views, no parity taps); the first-generation split kernel handles the rest
+bool render_tc4_covers(const RenderParams& p, int bundle_size, int feat_dim, int V);
+int render_tc4_dispatch(const RenderParams& p, int bundle_size, int feat_dim, int V, cudaStream_t st);
 
 }  // namespace gdb

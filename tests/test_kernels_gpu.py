@@ -561,10 +561,26 @@ def test_render_fused_split_precision_tensor_core(golden, prefix):
     # and it agrees with the SIMT fp32 kernel to a few fp32 ulps of the activations
     assert _md(sp["sigma"], ref32["sigma"]) <= 2e-5
     assert _md(sp["feat"], ref32["feat"]) <= 2e-5
-    split = ops.render_fused(*args, precision=2, out_channels_last=True)
+    # without the parity taps the production kernel of this arithmetic runs: for 2x2 bundles and three source views that is the
+    # split-fp16 kernel in the third-generation layout (gdb_render_tc4.cu: `mean` folded into extra MMAs, var[16:19] in the spare
+    # K slots of [x_v | 1]), elsewhere the first-generation split kernel itself.  Same class, not the same summation order.
     R = 3 * b * b
-    assert torch.equal(split["fine"].permute(0, 3, 1, 2), sp["feat"][:, :R])
-    assert torch.equal(split["dec_in"].permute(0, 3, 1, 2), sp["feat"][:, R:])
+    exact = not (b == 2 and feat_dim == 16 and V == 3)
+    for kw in (dict(), dict(out_channels_last=True), dict(out_channels_last=True, pad_dec=True, dec_one=True)):
+        prod = ops.render_fused(*args, precision=2, **kw)
+        torch.cuda.synchronize()
+        if kw:
+            fine, dec = prod["fine"].permute(0, 3, 1, 2), prod["dec_in"].permute(0, 3, 1, 2)[:, :sp["feat"].shape[1] - R]
+        else:
+            fine, dec = prod["feat"][:, :R], prod["feat"][:, R:]
+        if exact:
+            assert torch.equal(fine, sp["feat"][:, :R]) and torch.equal(dec, sp["feat"][:, R:])
+        else:
+            assert _md(fine, sp["feat"][:, :R]) <= 2e-5 and _md(dec, sp["feat"][:, R:]) <= 2e-5, (kw, _md(fine, sp["feat"][:, :R]), _md(dec, sp["feat"][:, R:]))
+            assert _md(fine, ref_feat[:, :R]) <= noise and _md(dec, ref_feat[:, R:]) <= noise
+        assert _md(prod["depth"].reshape(-1), golden.t(prefix + "bundle_depth")) <= 1e-4 * (spec["far"] - spec["near"])
+        assert _md(prod["depth"], sp["depth"]) <= 2e-6 * (spec["far"] - spec["near"])
+        assert _md(prod["opacity"].reshape(-1), golden.t(prefix + "bundle_opacity")) <= 1e-5
 
 
 @pytest.mark.parametrize("D,h,w,inv,per_pixel", [(64, 12, 40, True, False), (36, 9, 33, True, False), (8, 10, 70, False, True)])
