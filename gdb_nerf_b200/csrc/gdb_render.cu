@@ -14,6 +14,7 @@
 // waits on its gathers another runs its MLP.  The MLP weights (packed [K][N])
 // live in shared memory once per CTA; each lane keeps its activations in a
 // private shared-memory column ([row][lane], bank = lane: conflict-free).
+#include <mutex>
 #include "gdb_render_common.cuh"
 
 namespace gdb {
@@ -550,6 +551,51 @@ extern "C" int gdb_render_fused_fwd(const float* rgba, const float* tex, const f
               "gdb_render_fused_fwd: (bundle_size=%d, feat_dim=%d, V=%d) not instantiated; built: (2,16,2..4), (4,32,2..4)",
               bundle_size, feat_dim, V);
 }
+
+// ---------------------------------------------------------------- tile counters --
+// The persistent tensor-core kernels hand their tiles out dynamically: SMs do not run at one speed (measured: a static
+// stride leaves 8 % of the SM cycles idle at the end of the DTU launch), an atomic counter evens the finish line out.
+namespace gdb {
+constexpr int TILE_SLOTS_STREAM = 64, TILE_SLOTS_CAPTURE = 960;
+__device__ unsigned int g_tile_counters[TILE_SLOTS_STREAM + TILE_SLOTS_CAPTURE];
+
+unsigned int* acquire_tile_counter(cudaStream_t st) {
+  struct DevState {
+    unsigned int* base = nullptr;
+    cudaStream_t streams[TILE_SLOTS_STREAM];
+    int n_streams = 0, n_capture = 0;
+  };
+  static std::mutex mu;
+  static DevState devs[GDB_MAX_DEVICES];
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("GDB_K3_STATIC"); off = (e && e[0] == '1') ? 1 : 0; }     // A/B: static tile assignment
+  if (off || st == cudaStreamPerThread) return nullptr;     // the per-thread handle names a different stream in every host thread
+  std::lock_guard<std::mutex> lock(mu);
+  DevState& d = devs[current_device()];
+  if (!d.base && cudaGetSymbolAddress(reinterpret_cast<void**>(&d.base), g_tile_counters) != cudaSuccess) {
+    cudaGetLastError();
+    d.base = nullptr;
+    return nullptr;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  int slot = -1;
+  if (cs == cudaStreamCaptureStatusActive) {
+    if (d.n_capture >= TILE_SLOTS_CAPTURE) return nullptr;
+    slot = TILE_SLOTS_STREAM + d.n_capture++;
+  } else {
+    for (int i = 0; i < d.n_streams && slot < 0; ++i)
+      if (d.streams[i] == st) slot = i;
+    if (slot < 0) {
+      if (d.n_streams >= TILE_SLOTS_STREAM) return nullptr;
+      slot = d.n_streams;
+      d.streams[d.n_streams++] = st;
+    }
+  }
+  if (cudaMemsetAsync(d.base + slot, 0, sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d.base + slot;
+}
+}  // namespace gdb
 
 extern "C" int gdb_abi_version(void) { return GDB_ABI_VERSION; }
 extern "C" const char* gdb_last_error_string(void) { return err_buf(); }

@@ -32,7 +32,15 @@ struct RenderParams {
   int64_t vol_sb, vol_sz, vol_sy, vol_sx;   // float strides of vol over (batch, depth, row, column): layout 0 (B,D,Hb,Wb,.) or 1 (B,Hb,Wb,D,.)
   int B, H, W, Hb, Wb, D, max_samples, L, inv_depth, adaptive, out_cl;
   int pix_lo, pix_hi;  // range of bundle indices (row-major over the Hb x Wb bundle map) rendered in every view: the image-tile split
+  unsigned int* tile_counter;   // tensor-core kernels: tiles beyond a tile slot's first are handed out by this counter (zero at launch);
+                                // nullptr = every tile slot strides through the tiles (static assignment)
 };
+
+// A zeroed tile counter for one launch on `st` (gdb_render.cu), or nullptr when none is available (the kernel then falls back
+// to the static assignment).  The counters live in a __device__ array of the library (nothing is allocated): one per stream
+// that ever launched (launches on a stream are ordered, so its counter is never shared by two kernels in flight), a fresh
+// one for every launch recorded during a stream capture (a graph replay may overlap launches on the capturing stream).
+unsigned int* acquire_tile_counter(cudaStream_t st);
 
 template <int N>
 __device__ __forceinline__ void axpy_row(float (&acc)[N], const float* __restrict__ wrow, float x) {

@@ -42,6 +42,17 @@ namespace gdb {
 //    * compositing and the output stores run on float4 quads (lane = (bundle, channel quad), STG.128 into the channels-last
 //      decoder input), the fine colours are stashed component-wise so that a lane sums and stores one float4 of a bundle,
 //    * the colour pass reads its per-row parameters from shared memory (two LDS.128) instead of 5 + V shuffles.
+// sum_k relu(g[k]) w[k] over 32 accumulator columns in the four chains k mod 4, two chains per packed FFMA2 (bit-identical
+// to the scalar chains); w is 16-byte aligned in shared memory
+__device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w, unsigned long long& a01, unsigned long long& a23) {
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const ulonglong2 ww = *reinterpret_cast<const ulonglong2*>(w + k);
+    a01 = fma2(pack2(fmaxf(g[k + 0], 0.f), fmaxf(g[k + 1], 0.f)), ww.x, a01);
+    a23 = fma2(pack2(fmaxf(g[k + 2], 0.f), fmaxf(g[k + 3], 0.f)), ww.y, a23);
+  }
+}
+
 template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
@@ -120,8 +131,20 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   float4 rng_next = make_float4(1.f, 2.f, 1.f, 2.f);
   if (GEN == 3 && (int)(blockIdx.x * NG + g) < tiles) rng_next = load_ranges(blockIdx.x * NG + g);
 
+  // Tile assignment.  Every tile slot starts with tile blockIdx.x * NG + g; the following ones come from an atomic counter when
+  // the launch carries one (p.tile_counter, zero at launch: SMs do not run at one speed - with a static stride 8 % of the SM
+  // cycles of a DTU launch were idle at the end, 0.96 -> 0.89 ms), else from the static stride.  Row 0 of the group draws the
+  // next tile at the top of the current one; the group reads it behind the barrier in front of GEMM 1.
+  __shared__ int next_tile_s[NG];
+  const bool dyn = GEN == 3 && p.tile_counter != nullptr;
+  int tn = 0;
 #pragma unroll 1
-  for (int tile = blockIdx.x * NG + g; tile < tiles; tile += gridDim.x * NG) {
+  for (int tile = blockIdx.x * NG + g; tile < tiles; tile = tn) {
+    if (dyn) {
+      if (row == 0) next_tile_s[g] = (int)(gridDim.x * NG + atomicAdd(p.tile_counter, 1u));
+    } else {
+      tn = tile + gridDim.x * NG;
+    }
     const int b = tile / tiles_pv;                         // uniform over the group
     if (b != cur_b) {                                      // stage this view's camera block
       group_sync(g);
@@ -220,7 +243,9 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     float d_fu0[V], d_fv0[V], d_fu1[V], d_fv1[V], d_fr[V], d_dir[V][4];
     float tdx = cwx - ox, tdy = cwy - oy, tdz = cwz - oz;      // unit vector target camera -> sample (view independent)
     unit3_fast(tdx, tdy, tdz);
-#pragma unroll
+    // GEN 3 hands the descriptors over through shared memory at once: the loop stays rolled (530 fewer instructions of
+    // straight-line code per tile for the instruction cache: 0.962 -> 0.938 ms at DTU)
+#pragma unroll(GEN == 3 ? 1 : V)
     for (int v = 0; v < V; ++v) {
       const float* cv = head + CAM_HEAD + CAM_VIEW * v;
       // centre of the bundle's points in the source camera frame (bundle_sampler.py:340; the mean commutes with the rigid map)
@@ -278,9 +303,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
     }
     if constexpr (GEN == 3) {
-      // the depth ranges of my next tile, in flight underneath this tile
-      const int tn = tile + gridDim.x * NG;
-      if (tn < tiles) rng_next = load_ranges(tn);
+      // the depth ranges of my next tile, in flight underneath this tile (dynamic assignment: behind GEMM 1's barrier)
+      if (!dyn && tn < tiles) rng_next = load_ranges(tn);
     }
 
     // ================= P2: mip-mapped feature fetch, lane = (row, quad) =================
@@ -529,6 +553,10 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     tc_fence_before();
     fence_async_smem();
     group_sync(g);
+    if (dyn) {
+      tn = next_tile_s[g];
+      if (tn < tiles) rng_next = load_ranges(tn);
+    }
     if (row == 0) {
       tc_fence_after();
 #pragma unroll 1
@@ -548,6 +576,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float gv[32];
         tmem_ld32(tmem_row + v * 32, gv);
         float s0 = vec[C::X_SCAL + 0], s1 = 0.f, s2_ = 0.f, s3 = 0.f;     // four independent chains (FMA latency)
+#ifdef GDB_X_FMA2
+        {
+          unsigned long long a01 = pack2(s0, 0.f), a23 = pack2(0.f, 0.f);
+          relu_dot32(gv, vec + C::X_AGG_W, a01, a23);
+          unpack2(a01, s0, s1); unpack2(a23, s2_, s3);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           s0 = fmaf(fmaxf(gv[k + 0], 0.f), vec[C::X_AGG_W + k + 0], s0);
@@ -555,6 +590,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           s2_ = fmaf(fmaxf(gv[k + 2], 0.f), vec[C::X_AGG_W + k + 2], s2_);
           s3 = fmaf(fmaxf(gv[k + 3], 0.f), vec[C::X_AGG_W + k + 3], s3);
         }
+#endif
         float s = fmaxf((s0 + s1) + (s2_ + s3), 0.f);
 #pragma unroll
         for (int u = 0; u < V; ++u)
@@ -580,8 +616,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         for (int u = 1; u < V; ++u)
           if (u == v) a = aw[u];
         a *= rsum;
+#ifdef GDB_X_FMA2
+        const unsigned long long aa = pack2(a, a);
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) fma2_acc(im[k], im[k + 1], fmaxf(gv[k], 0.f), fmaxf(gv[k + 1], 0.f), aa);
+#else
 #pragma unroll
         for (int k = 0; k < 32; ++k) im[k] = fmaf(fmaxf(gv[k], 0.f), a, im[k]);
+#endif
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
@@ -671,6 +713,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         for (int half = 0; half < 2; ++half) {
           float hid[32];
           tmem_ld32(tmem_row + i * 64 + half * 32, hid);
+#ifdef GDB_X_FMA2
+          {
+            unsigned long long a01 = pack2(q0, q1), a23 = pack2(q2, q3);
+            relu_dot32(hid, vec + C::X_W2_W + half * 32, a01, a23);
+            unpack2(a01, q0, q1); unpack2(a23, q2, q3);
+          }
+#else
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             q0 = fmaf(fmaxf(hid[k + 0], 0.f), vec[C::X_W2_W + half * 32 + k + 0], q0);
@@ -678,6 +727,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             q2 = fmaf(fmaxf(hid[k + 2], 0.f), vec[C::X_W2_W + half * 32 + k + 2], q2);
             q3 = fmaf(fmaxf(hid[k + 3], 0.f), vec[C::X_W2_W + half * 32 + k + 3], q3);
           }
+#endif
         }
         const float s2 = fmaxf((q0 + q1) + (q2 + q3), 0.f);
 #pragma unroll
@@ -1028,7 +1078,11 @@ static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   (void)NB;
   long ctas = (tiles + NG - 1) / NG;
   if (ctas > sm_count()) ctas = sm_count();
-  kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(p);
+  // dynamic tile assignment where it was measured to pay: 2x2 bundles (DTU 0.96 -> 0.89 ms; the 4x4 tiles of NeRF-synthetic,
+  // twice as long and in 54 rounds instead of 28, lose 0.4 % to the extra barrier-side traffic)
+  RenderParams q = p;
+  q.tile_counter = (GEN == 3 && BS == 2 && ctas == sm_count()) ? acquire_tile_counter(st) : nullptr;
+  kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(q);
   return cuda_check("gdb_render_fused_fwd(tc2)");
 }
 template <int BS, int FEAT_DIM, int V, int NG, int GEN, int FB>

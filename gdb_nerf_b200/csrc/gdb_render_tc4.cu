@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
   const bool glane = lane < IPW * QL;
   const bool last_quad = gq == QL - 1;
   const float4* tex4 = reinterpret_cast<const float4*>(p.tex);
-  const float inv_Wb = 1.f / (float)p.Wb, inv_Hb = 1.f / (float)p.Hb, two_W = 2.f / (float)p.W, two_H = 2.f / (float)p.H;
+  const float two_W = 2.f / (float)p.W, two_H = 2.f / (float)p.H;
 
   auto load_ranges = [&](int t) -> float4 {
     const int tb = t / tiles_pv;
@@ -238,8 +238,18 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
   float4 rng_next = make_float4(1.f, 2.f, 1.f, 2.f);
   if ((int)(blockIdx.x * NG + g) < tiles) rng_next = load_ranges(blockIdx.x * NG + g);
 
+  // tile assignment as in gdb_render_tc2.cu: the first tile of a slot is static, the following ones come from the launch's atomic
+  // counter (p.tile_counter) when there is one
+  __shared__ int next_tile_s[NG];
+  const bool dyn = p.tile_counter != nullptr;
+  int tn = 0;
 #pragma unroll 1
-  for (int tile = blockIdx.x * NG + g; tile < tiles; tile += gridDim.x * NG) {
+  for (int tile = blockIdx.x * NG + g; tile < tiles; tile = tn) {
+    if (dyn) {
+      if (row == 0) next_tile_s[g] = (int)(gridDim.x * NG + atomicAdd(p.tile_counter, 1u));
+    } else {
+      tn = tile + gridDim.x * NG;
+    }
     const int b = tile / tiles_pv;
     if (b != cur_b) {
       group_sync(g);
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
     // ====================== P1: per-view fetch descriptors (thread = row) ======================
     float tdx = cwx - ox, tdy = cwy - oy, tdz = cwz - oz;
     unit3_fast(tdx, tdy, tdz);
-#pragma unroll
+#pragma unroll 1      // rolled: less straight-line code per tile for the instruction cache (1.707 -> 1.692 ms at DTU)
     for (int v = 0; v < V; ++v) {
       const float* cv = head + CAM_HEAD + CAM_VIEW * v;
       const float ccx = fmaf(cwx, cv[CV_E + 0], fmaf(cwy, cv[CV_E + 1], fmaf(cwz, cv[CV_E + 2], cv[CV_E + 3])));
@@ -331,8 +341,10 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
       const float pxc = fmaf(ccx, cv[CV_K + 0] * ifb, fmaf(ccy, cv[CV_K + 1] * ifb, ccz * (cv[CV_K + 2] * ifb)));
       const float pyc = fmaf(ccx, cv[CV_K + 3] * ifb, fmaf(ccy, cv[CV_K + 4] * ifb, ccz * (cv[CV_K + 5] * ifb)));
       const float pzc = fmaxf(fmaf(ccx, cv[CV_K + 6], fmaf(ccy, cv[CV_K + 7], ccz * cv[CV_K + 8])), 1e-6f);
-      const float rz = __frcp_rn(pzc);
-      const float u01 = pxc * rz * inv_Wb, v01 = pyc * rz * inv_Hb;
+      // the texture coordinate with the reference's two true divisions (the fp16-operand kernel multiplies by reciprocals: one ulp
+      // of u is 3e-5 texels at LLFF, which white-noise features turn into 2e-5 of a fetched feature - noise for that class,
+      // a fifth of the budget of this one)
+      const float u01 = pxc / pzc / (float)p.Wb, v01 = pyc / pzc / (float)p.Hb;
       int d_a0 = 0, d_a1 = 0;
       uint32_t d_pk = 0;
       float d_fu0 = 0.f, d_fv0 = 0.f, d_fu1 = 0.f, d_fv1 = 0.f, d_fr = 0.f, dd0 = 0.f, dd1 = 0.f, dd2 = 0.f, dd3 = 0.f;
@@ -362,10 +374,7 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
       *reinterpret_cast<float4*>(dp + 2048) = make_float4(d_fu0, d_fv0, d_fu1, d_fv1);
       *reinterpret_cast<float4*>(dp + 4096) = make_float4(dd0, dd1, dd2, dd3);
     }
-    {
-      const int tn = tile + gridDim.x * NG;
-      if (tn < tiles) rng_next = load_ranges(tn);
-    }
+    if (!dyn && tn < tiles) rng_next = load_ranges(tn);      // the depth ranges of my next tile, in flight underneath this one
 
     // ================= P2: mip-mapped feature fetch, lane = (row, quad) =================
     // writes (both planes) FD_v = [featrgb_v | dir_v], X_v = [x_v | 1 | var16..18] and S = var[0:16]
@@ -512,6 +521,10 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
     tc_fence_before();
     fence_async_smem();
     group_sync(g);
+    if (dyn) {
+      tn = next_tile_s[g];
+      if (tn < tiles) rng_next = load_ranges(tn);
+    }
     if (row == 0) {
       tc_fence_after();
 #pragma unroll 1
@@ -904,7 +917,9 @@ static int launch_render_tc4(const RenderParams& p, cudaStream_t st) {
   const long tiles = (long)p.B * ((p.pix_hi - p.pix_lo + 4 * G - 1) / (4 * G));
   long ctas = (tiles + C::NG - 1) / C::NG;
   if (ctas > sm_count()) ctas = sm_count();
-  kern<<<(int)ctas, 128 * C::NG, C::SMEM, st>>>(p);
+  RenderParams q = p;
+  q.tile_counter = ctas == sm_count() ? acquire_tile_counter(st) : nullptr;
+  kern<<<(int)ctas, 128 * C::NG, C::SMEM, st>>>(q);
   return cuda_check("gdb_render_fused_fwd(tc4)");
 }
 

@@ -34,6 +34,19 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+#ifdef GDB_X_SPINHINT
+  // experiment: let the hardware park the warp for up to GDB_X_SPINHINT ns per probe instead of re-issuing the probe
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"(mbar),
+      "r"(parity), "r"((uint32_t)GDB_X_SPINHINT)
+      : "memory");
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"

@@ -117,7 +117,7 @@ def test_full_size_sampling_properties_and_counts():
     assert torch.equal(idx, torch.repeat_interleave(torch.arange(NB), counts))
 
 
-@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("dtu", 2), ("nerf", 0), ("nerf", 1), ("nerf", 2), ("llff", 1)])
+@pytest.mark.parametrize("workload,precision", [("dtu", 0), ("dtu", 1), ("dtu", 2), ("nerf", 0), ("nerf", 1), ("nerf", 2), ("llff", 1), ("llff", 2)])
 def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
     """BASELINE.json sizes (DTU 512x640 2x2 bundles, NeRF-synthetic 800x800 4x4 bundles): parity with the oracle on
     identical inputs plus size-independent properties.  precision 1 = tensor-core MLP (2e-3 class)."""
@@ -152,6 +152,57 @@ def test_full_size_render_against_oracle_and_view_symmetry(workload, precision):
                              cfg.nerf.max_num_samples, cfg.nerf.global_num_depth, cfg.nerf.max_mipmap_level, False, True)
     assert _md(out["feat"], truth["bundle_feat"]) <= tol
     assert _md(out["depth"], truth["bundle_depth"]) <= tol * (w["far"] - w["near"])
+
+
+@pytest.mark.parametrize("precision", [1, 2])
+def test_dynamic_tile_assignment_on_concurrent_streams_and_graph_replays(precision):
+    """The tensor-core kernels of 2x2 bundles draw their tiles from an atomic counter of the library: one counter per stream
+    (launches on a stream are ordered), a fresh one per launch recorded in a stream capture.  Launches in flight on several
+    streams, and a graph replay overlapping eager launches, must never share a counter - a shared one would skip tiles and
+    leave `torch.empty` garbage in the outputs.  Every result equals the serial one bit for bit (tiles are independent)."""
+    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs("dtu")
+    b = cfg.nerf.bundle_size
+    cam = ops.camera_block(rig["tar_exts"].to(DEV), rig["tar_ints"].to(DEV), rig["src_exts"].to(DEV), rig["src_ints"].to(DEV),
+                           rig["near_far"].to(DEV), b, cfg.nerf.global_num_depth, False)
+    src = ops.prepare_sources(data["feat"].to(DEV), data["rgb"].to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(data["vol"].to(DEV), 8)
+    dr, vr, packed = data["depth_range"].to(DEV), data["vol_range"].to(DEV), ops.pack_mlp(mlp, feat_dim, device=DEV)
+
+    def run():
+        return ops.render_fused(src, vol_cl, dr, vr, cam, packed, 1, 3, w["H"], w["W"], b, cfg.nerf.max_num_samples, False, True,
+                                precision=precision)
+
+    def same(a, bb):
+        return all(torch.equal(a[k], bb[k]) for k in ("feat", "depth", "opacity"))
+
+    ref = run()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    for _ in range(4):
+        for s in streams:
+            with torch.cuda.stream(s):
+                outs.append(run())
+    torch.cuda.synchronize()
+    assert all(same(o, ref) for o in outs)
+    # a captured launch replayed on the current stream while eager launches run on another one
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        run()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        gout = run()
+    for _ in range(3):
+        for v in gout.values():
+            if torch.is_tensor(v):
+                v.fill_(float("nan"))
+        torch.cuda.synchronize()
+        graph.replay()
+        with torch.cuda.stream(side):        # the capturing stream's own counter is not the graph's
+            eager = run()
+        torch.cuda.synchronize()
+        assert same(gout, ref) and same(eager, ref)
 
 
 @pytest.mark.parametrize("workload,hw", [("dtu", (64, 96)), ("nerf", (128, 160))])
