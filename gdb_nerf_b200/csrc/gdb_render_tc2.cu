@@ -53,11 +53,21 @@ __device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w,
   }
 }
 
+//
+// Measured variants kept behind compile-time flags (tools/build_variant.sh; profiles/r02_k3_experiments_s3.log; ms per 8 views,
+// DTU / LLFF / NeRF-synthetic against 0.882 / 1.655 / 2.27 of the default build in the same call):
+//   -DGDB_X_SPINHINT=ns  suspend-time hint on the mbarrier probe (the probe loop is 5.6 % of the issued instructions): no effect
+//   -DGDB_X_FMA2         packed FFMA2 in the ReLU-dot epilogues: 124 bytes of spills at 128 registers, 0.998 at DTU (+3.7 %), -0.7 % at NeRF
+//   -DGDB_K3_CHPAD=64    operand chunks 2048 + 64 bytes apart (removes the two-way conflicts of the fetch lanes' 8-byte stores):
+//                        0.894 / 1.676 (+1.3 %), 2.229 (-0.3 %)
+//   -DGDB_X_UNCOND       plain gathers instead of predicated ones with zero-initialised destinations: 0.906 / 1.708 (+2.5 / +3 %)
+//   -DGDB_X_ROLLR        the two rounds of GEMM 4 as one rolled loop: 0.936 / 1.774 (+6 %)
 template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
   using ML = typename C::ML;
   constexpr int BB = C::BB, F = C::F, FP = C::FP, R = C::R, CT = C::CT, QL = C::QL, IPW = C::IPW;
+  constexpr int CHB = C::CHB;                  // bytes between consecutive operand chunks
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   float* vec = reinterpret_cast<float*>(smem + C::VEC_OFF);
@@ -296,10 +306,10 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         // the descriptor of (row, view) travels through the row's own 3 x 16 bytes of the X_v operand region: the fetch
         // lanes of the row read it there and overwrite it with the operand afterwards
         static_assert(C::XCH >= 3, "three 16-byte slots per (row, view)");
-        unsigned char* dp = sX + (v * C::XCH) * 2048 + row * 16;
+        unsigned char* dp = sX + (v * C::XCH) * CHB + row * 16;
         *reinterpret_cast<uint4*>(dp) = make_uint4((uint32_t)d_a0[v], (uint32_t)d_a1[v], d_pk[v], __float_as_uint(d_fr[v]));
-        *reinterpret_cast<float4*>(dp + 2048) = make_float4(d_fu0[v], d_fv0[v], d_fu1[v], d_fv1[v]);
-        *reinterpret_cast<float4*>(dp + 4096) = make_float4(d_dir[v][0], d_dir[v][1], d_dir[v][2], d_dir[v][3]);
+        *reinterpret_cast<float4*>(dp + CHB) = make_float4(d_fu0[v], d_fv0[v], d_fu1[v], d_fv1[v]);
+        *reinterpret_cast<float4*>(dp + 2 * CHB) = make_float4(d_dir[v][0], d_dir[v][1], d_dir[v][2], d_dir[v][3]);
       }
     }
     if constexpr (GEN == 3) {
@@ -345,10 +355,17 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           const int dx = (int)((pk >> (28 + level)) & 1) * QL;
           const bool pr = ok && (pk >> 31) && (level == 0 || ((pk >> 30) & 1));
           const float4* b0 = tq + a;
+#ifdef GDB_X_UNCOND
+          // experiment: every address is valid whatever the predicate (zero descriptors of rows without a sample point at texel 0,
+          // level 1 exists even when unused) and every consumer selects on the same flags: plain loads, no zero initialisation
+          (void)pr;
+          t[0] = __ldg(b0); t[1] = __ldg(b0 + dx); t[2] = __ldg(b0 + dy); t[3] = __ldg(b0 + (dy + dx));
+#else
           t[0] = ldg4_if(b0, pr);
           t[1] = ldg4_if(b0 + dx, pr);
           t[2] = ldg4_if(b0 + dy, pr);
           t[3] = ldg4_if(b0 + (dy + dx), pr);
+#endif
         };
         auto mix = [&](float4& f, const float4(&t)[4], const uint4 q0, const float4 q1) {      // level-1 blend (tri-linear part)
           if ((q0.z >> 30) & 1) {
@@ -362,40 +379,40 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           float4 t0[V][4], t1[V][4];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB);
             taps4(q0, 0, t0[v]);
             taps4(q0, 1, t1[v]);
           }
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
-            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB);
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * CHB);
             f[v] = bilerp4(t0[v][0], t0[v][1], t0[v][2], t0[v][3], q1.x, q1.y);
             mix(f[v], t1[v], q0, q1);
           }
         } else if constexpr (FB == 1) {     // level 0 of all views, then level 1 of all views
           float4 t[V][4];
 #pragma unroll
-          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048), 0, t[v]);
+          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB), 0, t[v]);
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * CHB);
             f[v] = bilerp4(t[v][0], t[v][1], t[v][2], t[v][3], q1.x, q1.y);
           }
 #pragma unroll
-          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048), 1, t[v]);
+          for (int v = 0; v < V; ++v) taps4(*reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB), 1, t[v]);
 #pragma unroll
           for (int v = 0; v < V; ++v)
-            mix(f[v], t[v], *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048),
-                *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048));
+            mix(f[v], t[v], *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB),
+                *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * CHB));
         } else {                             // both levels of one view at a time
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             float4 t0[4], t1[4];
-            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * 2048);
+            const uint4 q0 = *reinterpret_cast<const uint4*>(dsc + (v * C::XCH) * CHB);
             taps4(q0, 0, t0);
             taps4(q0, 1, t1);
-            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * 2048);
+            const float4 q1 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 1) * CHB);
             f[v] = bilerp4(t0[0], t0[1], t0[2], t0[3], q1.x, q1.y);
             mix(f[v], t1, q0, q1);
           }
@@ -403,8 +420,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float xq[V][4];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const uint32_t pk = *reinterpret_cast<const uint32_t*>(dsc + (v * C::XCH) * 2048 + 8);
-          const float4 q2 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 2) * 2048);
+          const uint32_t pk = *reinterpret_cast<const uint32_t*>(dsc + (v * C::XCH) * CHB + 8);
+          const float4 q2 = *reinterpret_cast<const float4*>(dsc + (v * C::XCH + 2) * CHB);
           const float dir[4] = {q2.x, q2.y, q2.z, q2.w};
           const bool act = ok && (pk >> 31);
           if (TAPS && p.tap_rfd && act) {
@@ -424,8 +441,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           }
           __syncwarp();                     // every lane of the row has read the descriptor that the operand now replaces
           if (ok) {
-            unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * 2048 + orow16;
-            unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * 2048 + orow16;
+            unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * CHB + orow16;
+            unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * CHB + orow16;
             if (last_quad) {
               *reinterpret_cast<uint4*>(fdp) = make_uint4(pack_h2(fe[0], fe[1]), pack_h2(fe[2], dir[0]), pack_h2(dir[1], dir[2]), pack_h2(dir[3], 0.f));
               *reinterpret_cast<uint4*>(xp) = make_uint4(pack_h2(xq[v][0], xq[v][1]), pack_h2(xq[v][2], act ? 1.f : 0.f), 0u, 0u);
@@ -451,8 +468,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
             mean[e] = mu;
           }
           const int kv = gq, km = QL + gq;      // quad positions of var / mean inside S
-          *reinterpret_cast<uint2*>(sS + (kv >> 1) * 2048 + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
-          *reinterpret_cast<uint2*>(sS + (km >> 1) * 2048 + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
+          *reinterpret_cast<uint2*>(sS + (kv >> 1) * CHB + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
+          *reinterpret_cast<uint2*>(sS + (km >> 1) * CHB + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
         }
       }
     } else
@@ -516,8 +533,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           xq[v][e] = act ? fe[e] + fmaxf(t, 0.f) : 0.f;
         }
         if (ok) {
-          unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * 2048 + orow16;
-          unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * 2048 + orow16;
+          unsigned char* fdp = sFD + (v * C::FDCH + (gq >> 1)) * CHB + orow16;
+          unsigned char* xp = sX + (v * C::XCH + (gq >> 1)) * CHB + orow16;
           if (last_quad) {
             // featrgb's pad channel is K slot F: dir_v follows in FD, the constant one in X
             *reinterpret_cast<uint4*>(fdp) = make_uint4(pack_h2(f.x, f.y), pack_h2(f.z, dir[0]), pack_h2(dir[1], dir[2]), pack_h2(dir[3], 0.f));
@@ -544,8 +561,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           mean[e] = mu;
         }
         const int kv = gq, km = QL + gq;      // quad positions of var / mean inside S
-        *reinterpret_cast<uint2*>(sS + (kv >> 1) * 2048 + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
-        *reinterpret_cast<uint2*>(sS + (km >> 1) * 2048 + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
+        *reinterpret_cast<uint2*>(sS + (kv >> 1) * CHB + orow16 + (kv & 1) * 8) = make_uint2(pack_h2(var[0], var[1]), pack_h2(var[2], var[3]));
+        *reinterpret_cast<uint2*>(sS + (km >> 1) * CHB + orow16 + (km & 1) * 8) = make_uint2(pack_h2(mean[0], mean[1]), pack_h2(mean[2], mean[3]));
       }
     }
 
@@ -561,8 +578,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       tc_fence_after();
 #pragma unroll 1
       for (int v = 0; v < V; ++v) {
-        mma_chunks(tmem_group + v * 32, aS, C::SCH, zero_chunk, w_base + C::W_GS, 32, 0);
-        mma_chunks(tmem_group + v * 32, aX + v * C::XCH * 2048, C::XCH, zero_chunk, w_base + C::W_GX, 32, 1);
+        mma_chunks(tmem_group + v * 32, aS, C::SCH, zero_chunk, w_base + C::W_GS, 32, 0, CHB);
+        mma_chunks(tmem_group + v * 32, aX + v * C::XCH * CHB, C::XCH, zero_chunk, w_base + C::W_GX, 32, 1, CHB);
       }
       umma_commit(mbar);
     }
@@ -627,7 +644,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(im[ch * 8 + 0], im[ch * 8 + 1]), pack_h2(im[ch * 8 + 2], im[ch * 8 + 3]),
+        *reinterpret_cast<uint4*>(sS + ch * CHB + row * 16) = make_uint4(pack_h2(im[ch * 8 + 0], im[ch * 8 + 1]), pack_h2(im[ch * 8 + 2], im[ch * 8 + 3]),
                                                                           pack_h2(im[ch * 8 + 4], im[ch * 8 + 5]), pack_h2(im[ch * 8 + 6], im[ch * 8 + 7]));
     }
     // ================= GEMM 2: fc =================
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      mma_chunks(tmem_group, aS, 4, zero_chunk, w_base + C::W_FC, 16, 0);
+      mma_chunks(tmem_group, aS, 4, zero_chunk, w_base + C::W_FC, 16, 0, CHB);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -647,10 +664,10 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
 #pragma unroll
       for (int k = 0; k < 16; ++k) img[k] = fmaxf(img[k] + vec[C::X_FC_B + k], 0.f);
       // X[8] <- vox, S[0..1] <- img (their previous contents were consumed by GEMMs 1 and 2)
-      *reinterpret_cast<uint4*>(sX + 8 * 2048 + row * 16) = voxh;
+      *reinterpret_cast<uint4*>(sX + 8 * CHB + row * 16) = voxh;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
-        *reinterpret_cast<uint4*>(sS + ch * 2048 + row * 16) = make_uint4(pack_h2(img[ch * 8 + 0], img[ch * 8 + 1]), pack_h2(img[ch * 8 + 2], img[ch * 8 + 3]),
+        *reinterpret_cast<uint4*>(sS + ch * CHB + row * 16) = make_uint4(pack_h2(img[ch * 8 + 0], img[ch * 8 + 1]), pack_h2(img[ch * 8 + 2], img[ch * 8 + 3]),
                                                                           pack_h2(img[ch * 8 + 4], img[ch * 8 + 5]), pack_h2(img[ch * 8 + 6], img[ch * 8 + 7]));
     }
     // ================= GEMM 3: lr0 on [vox | img | 1] =================
@@ -659,8 +676,8 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     group_sync(g);
     if (row == 0) {
       tc_fence_after();
-      mma_step(tmem_group, aX + 8 * 2048, aS, w_base + C::W_LR0, 64, 0);
-      mma_step(tmem_group, aS + 2048, one_chunk, w_base + C::W_LR0 + 2 * 64 * 16, 64, 1);
+      mma_step(tmem_group, aX + 8 * CHB, aS, w_base + C::W_LR0, 64, 0);
+      mma_step(tmem_group, aS + CHB, one_chunk, w_base + C::W_LR0 + 2 * 64 * 16, 64, 1);
       umma_commit(mbar);
     }
     mbar_wait(mbar, parity); parity ^= 1;
@@ -671,13 +688,17 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       tmem_ld32(tmem_row + half * 32, h);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sX + (half * 4 + ch) * 2048 + row * 16) =
+        *reinterpret_cast<uint4*>(sX + (half * 4 + ch) * CHB + row * 16) =
             make_uint4(pack_h2(fmaxf(h[ch * 8 + 0], 0.f), fmaxf(h[ch * 8 + 1], 0.f)), pack_h2(fmaxf(h[ch * 8 + 2], 0.f), fmaxf(h[ch * 8 + 3], 0.f)),
                        pack_h2(fmaxf(h[ch * 8 + 4], 0.f), fmaxf(h[ch * 8 + 5], 0.f)), pack_h2(fmaxf(h[ch * 8 + 6], 0.f), fmaxf(h[ch * 8 + 7], 0.f)));
     }
     // ================= GEMM 4: [sigma | feat_head] and weight.0, view by view through NB 64-column buffers =================
     float sigma = 0.f, fh[8], wv[V];
+#ifdef GDB_X_ROLLR
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int r = 0; r < C::ROUNDS; ++r) {
       const int v0 = C::round_start(r), nv = C::round_n(r);
       tc_fence_before();
@@ -685,14 +706,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       group_sync(g);
       if (row == 0) {
         tc_fence_after();
-        if (r == 0) mma_chunks(tmem_group + (C::NB - 1) * 64, aX, 8, zero_chunk, w_base + C::W_SH, 16, 0);
+        if (r == 0) mma_chunks(tmem_group + (C::NB - 1) * 64, aX, 8, zero_chunk, w_base + C::W_SH, 16, 0, CHB);
 #pragma unroll 1
         for (int i = 0; i < nv; ++i) {
           const uint32_t d = tmem_group + i * 64;
-          mma_chunks(d, aX, 8, zero_chunk, w_base + C::W_0S, 64, 0);                                   // h
-          mma_step(d, aX + 8 * 2048, aS, w_base + C::W_0S + 8 * 64 * 16, 64, 1);                        // vox | img[0:8]
-          mma_step(d, aS + 2048, one_chunk, w_base + C::W_0S + 10 * 64 * 16, 64, 1);                    // img[8:16] | 1
-          mma_chunks(d, aFD + (v0 + i) * C::FDCH * 2048, C::FDCH, zero_chunk, w_base + C::W_0V, 64, 1); // featrgb_v | dir_v
+          mma_chunks(d, aX, 8, zero_chunk, w_base + C::W_0S, 64, 0, CHB);                                   // h
+          mma_step(d, aX + 8 * CHB, aS, w_base + C::W_0S + 8 * 64 * 16, 64, 1);                        // vox | img[0:8]
+          mma_step(d, aS + CHB, one_chunk, w_base + C::W_0S + 10 * 64 * 16, 64, 1);                    // img[8:16] | 1
+          mma_chunks(d, aFD + (v0 + i) * C::FDCH * CHB, C::FDCH, zero_chunk, w_base + C::W_0V, 64, 1, CHB); // featrgb_v | dir_v
         }
         umma_commit(mbar);
       }
@@ -765,7 +786,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     if (TAPS && p.tap_sigma && active) p.tap_sigma[srow] = sigma;
     if (TAPS && p.tap_w && active) p.tap_w[srow] = wgt;
 
-    auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+    auto stash_f = [&](int t) { return reinterpret_cast<float4*>(gsm + ((t * 4) >> 9) * CHB + wq * 512 + ((t * 4) & 511)); };
     const size_t ostr = p.out_cl ? 1 : (size_t)HW;
     float* tf = (TAPS && p.tap_feat && active) ? p.tap_feat + srow * CT : nullptr;
 
@@ -783,7 +804,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const uint4 q = *reinterpret_cast<const uint4*>(sFD + (v * C::FDCH + ch) * 2048 + row * 16);
+          const uint4 q = *reinterpret_cast<const uint4*>(sFD + (v * C::FDCH + ch) * CHB + row * 16);
           const float2 f0 = h2_to_f2(q.x), f1 = h2_to_f2(q.y), f2 = h2_to_f2(q.z), f3 = h2_to_f2(q.w);
           acc[0] = fmaf(f0.x, wv[v], acc[0]); acc[1] = fmaf(f0.y, wv[v], acc[1]);
           acc[2] = fmaf(f1.x, wv[v], acc[2]); acc[3] = fmaf(f1.y, wv[v], acc[3]);
@@ -880,23 +901,23 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float w4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int v = 0; v < V; ++v) w4[v] = wv[v];
-        *reinterpret_cast<float4*>(sS + 2048 + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+        *reinterpret_cast<float4*>(sS + CHB + row * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
       }
       if (TAPS)
-        *reinterpret_cast<uint4*>(sS + 4096 + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
+        *reinterpret_cast<uint4*>(sS + 2 * CHB + row * 16) = make_uint4(active ? 1u : 0u, (uint32_t)(srow & 0xffffffff), (uint32_t)((uint64_t)srow >> 32), 0u);
       __syncwarp();
       // component-wise stash of the weighted colours: float index row * R + c * BB + j, in the warp's rows of X + FD
       static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows of X + FD");
-      auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + ((t * 4) >> 9) * 2048 + wq * 512 + ((t * 4) & 511)); };
+      auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + ((t * 4) >> 9) * CHB + wq * 512 + ((t * 4) & 511)); };
       const int nit6 = min(BB, (ns * G * BB + 31) / 32);      // (row, ray) items of the rows that can hold a sample
 #pragma unroll 1
       for (int it = 0; it < nit6; ++it) {
         const int item = it * 32 + lane;
         const int r = item / BB, j = item - r * BB;
         const float4 ra = *reinterpret_cast<const float4*>(sS + (wq * 32 + r) * 16);
-        const float4 rb = *reinterpret_cast<const float4*>(sS + 2048 + (wq * 32 + r) * 16);
+        const float4 rb = *reinterpret_cast<const float4*>(sS + CHB + (wq * 32 + r) * 16);
         uint4 rc = make_uint4(0u, 0u, 0u, 0u);
-        if (TAPS) rc = *reinterpret_cast<const uint4*>(sS + 4096 + (wq * 32 + r) * 16);
+        if (TAPS) rc = *reinterpret_cast<const uint4*>(sS + 2 * CHB + (wq * 32 + r) * 16);
         const float zr = ra.x, wr = ra.w;
         // production build: a row without compositing weight contributes w * colour = 0 whatever it gathers - not fetched
         const bool actr = TAPS ? rc.x != 0 : wr != 0.f;
@@ -924,10 +945,14 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
           const Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
           const float4* ib = reinterpret_cast<const float4*>(p.rgba) + (size_t)(b * V + v) * p.H * p.W;
+#ifdef GDB_X_UNCOND
+          t[v][0] = __ldg(ib + bl4.o00); t[v][1] = __ldg(ib + bl4.o10); t[v][2] = __ldg(ib + bl4.o01); t[v][3] = __ldg(ib + bl4.o11);
+#else
           t[v][0] = ldg4_if(ib + bl4.o00, actr);
           t[v][1] = ldg4_if(ib + bl4.o10, actr);
           t[v][2] = ldg4_if(ib + bl4.o01, actr);
           t[v][3] = ldg4_if(ib + bl4.o11, actr);
+#endif
           tw[v][0] = bl4.w00; tw[v][1] = bl4.w10; tw[v][2] = bl4.w01; tw[v][3] = bl4.w11;
         }
         float cr = 0.f, cg = 0.f, cb = 0.f;
@@ -975,7 +1000,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       }
       __syncwarp();           // stash reads complete before the next tile's descriptors overwrite X
     } else {
-    auto stash = [&](int t) { return reinterpret_cast<float4*>(gsm + (t >> 5) * 2048 + wq * 512 + (t & 31) * 16); };
+    auto stash = [&](int t) { return reinterpret_cast<float4*>(gsm + (t >> 5) * CHB + wq * 512 + (t & 31) * 16); };
 #pragma unroll 1
     for (int it = 0; it < BB; ++it) {
       const int item = it * 32 + lane;

@@ -55,10 +55,14 @@ struct Tc2Cfg {
   static constexpr int VEC_OFF = ((W_END + 127) / 128) * 128;
   static constexpr int GROUP_OFF = ((VEC_OFF + X_END * 4 + 127) / 128) * 128;
   // per-group regions (bytes from the group base); S lies after X so that chunk pairs (X[8], S[0]) have a positive stride
+#ifndef GDB_K3_CHPAD
+#define GDB_K3_CHPAD 0
+#endif
+  static constexpr int CHB = 2048 + GDB_K3_CHPAD;      // bytes between consecutive operand chunks (the UMMA leading-dimension offset is free)
   static constexpr int A_X = 0;
-  static constexpr int A_FD = A_X + CH_X * 2048;
-  static constexpr int A_S = A_FD + CH_FD * 2048;
-  static constexpr int A_END = A_S + CH_S * 2048;
+  static constexpr int A_FD = A_X + CH_X * CHB;
+  static constexpr int A_S = A_FD + CH_FD * CHB;
+  static constexpr int A_END = ((A_S + CH_S * CHB + 127) / 128) * 128;
   static constexpr int CAM_OFF = A_END + 128;          // mbarrier at A_END
   static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
   static constexpr int ZERO_OFF = GROUP_OFF + NG * GROUP_BYTES;   // constant chunks after every group
@@ -141,10 +145,10 @@ __device__ __forceinline__ void mma_step(uint32_t d_tmem, uint32_t a0, uint32_t 
 }
 // `nch` consecutive chunks starting at `a` (odd counts pair the last chunk with the zero chunk)
 __device__ __forceinline__ void mma_chunks(uint32_t d_tmem, uint32_t a, int nch, uint32_t zero_chunk, uint32_t b_addr, int N,
-                                           uint32_t accumulate) {
+                                           uint32_t accumulate, int chb = 2048) {
   for (int ks = 0; 2 * ks < nch; ++ks) {
-    const uint32_t a0 = a + ks * 4096;
-    const uint32_t a1 = (2 * ks + 1 < nch) ? a0 + 2048 : zero_chunk;
+    const uint32_t a0 = a + ks * 2 * chb;
+    const uint32_t a1 = (2 * ks + 1 < nch) ? a0 + chb : zero_chunk;
     mma_step(d_tmem, a0, a1, b_addr + ks * 2 * (N * 16), N, (ks > 0 || accumulate) ? 1u : 0u);
   }
 }
