@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
   int tn = 0;
 #pragma unroll 1
   for (int tile = blockIdx.x * NG + g; tile < tiles; tile = tn) {
+    unsigned int drawn = 0;                                // the atomic's result is not touched before GEMM 1: its latency hides under P0-P2
     if (dyn) {
-      if (row == 0) next_tile_s[g] = (int)(gridDim.x * NG + atomicAdd(p.tile_counter, 1u));
+      if (row == 0) drawn = atomicAdd(p.tile_counter, 1u);
     } else {
       tn = tile + gridDim.x * NG;
     }
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     }
 
     // ================= GEMM 1: global_fc, G_v = [var|mean] W_gs + [x_v|1] W_gx =================
+    if (dyn && row == 0) next_tile_s[g] = (int)(gridDim.x * NG + drawn);
     tc_fence_before();
     fence_async_smem();
     group_sync(g);
@@ -910,7 +912,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       static_assert(32 * R * 4 <= 512 * (C::CH_X + C::CH_FD), "colour stash must fit in the warp's rows of X + FD");
       auto cst = [&](int t) { return reinterpret_cast<float*>(gsm + ((t * 4) >> 9) * CHB + wq * 512 + ((t * 4) & 511)); };
       const int nit6 = min(BB, (ns * G * BB + 31) / 32);      // (row, ray) items of the rows that can hold a sample
-#pragma unroll 1
+#pragma unroll 1      // (2 or 4 items per trip change nothing at 4x4 bundles: profiles/r02_k3_experiments_s3.log)
       for (int it = 0; it < nit6; ++it) {
         const int item = it * 32 + lane;
         const int r = item / BB, j = item - r * BB;
@@ -1106,7 +1108,9 @@ static int launch_render_tc2_t(const RenderParams& p, cudaStream_t st) {
   // dynamic tile assignment where it was measured to pay: 2x2 bundles (DTU 0.96 -> 0.89 ms; the 4x4 tiles of NeRF-synthetic,
   // twice as long and in 54 rounds instead of 28, lose 0.4 % to the extra barrier-side traffic)
   RenderParams q = p;
-  q.tile_counter = (GEN == 3 && BS == 2 && ctas == sm_count()) ? acquire_tile_counter(st) : nullptr;
+  static int dyn4 = -1;
+  if (dyn4 < 0) { const char* e = getenv("GDB_K3_DYN4"); dyn4 = (e && e[0] == '1') ? 1 : 0; }     // A/B: the counter for 4x4 bundles too
+  q.tile_counter = (GEN == 3 && (BS == 2 || dyn4) && ctas == sm_count()) ? acquire_tile_counter(st) : nullptr;
   kern<<<(int)ctas, 128 * NG, C::SMEM, st>>>(q);
   return cuda_check("gdb_render_fused_fwd(tc2)");
 }

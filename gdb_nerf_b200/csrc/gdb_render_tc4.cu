@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
   int tn = 0;
 #pragma unroll 1
   for (int tile = blockIdx.x * NG + g; tile < tiles; tile = tn) {
+    unsigned int drawn = 0;                                // the atomic's result is not touched before GEMM 1: its latency hides under P0-P2
     if (dyn) {
-      if (row == 0) next_tile_s[g] = (int)(gridDim.x * NG + atomicAdd(p.tile_counter, 1u));
+      if (row == 0) drawn = atomicAdd(p.tile_counter, 1u);
     } else {
       tn = tile + gridDim.x * NG;
     }
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
     }
 
     // ================= GEMM 1: global_fc, G_v = var W_var + [x_v|1|var tail] W_gx + sum_u x_u (W_mean / V) =================
+    if (dyn && row == 0) next_tile_s[g] = (int)(gridDim.x * NG + drawn);
     tc_fence_before();
     fence_async_smem();
     group_sync(g);
