@@ -572,13 +572,18 @@ unsigned int* acquire_tile_counter(cudaStream_t st) {
   if (off || st == cudaStreamPerThread) return nullptr;     // the per-thread handle names a different stream in every host thread
   std::lock_guard<std::mutex> lock(mu);
   DevState& d = devs[current_device()];
-  if (!d.base && cudaGetSymbolAddress(reinterpret_cast<void**>(&d.base), g_tile_counters) != cudaSuccess) {
-    cudaGetLastError();
-    d.base = nullptr;
-    return nullptr;
-  }
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (!d.base) {
+    // the symbol is resolved outside captures only (a first-use module lookup is not something to do inside a global-mode capture);
+    // a launch captured before any eager one simply keeps the static stride
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&d.base), g_tile_counters) != cudaSuccess) {
+      cudaGetLastError();
+      d.base = nullptr;
+      return nullptr;
+    }
+  }
   int slot = -1;
   if (cs == cudaStreamCaptureStatusActive) {
     if (d.n_capture >= TILE_SLOTS_CAPTURE) return nullptr;

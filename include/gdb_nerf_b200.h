@@ -151,7 +151,14 @@ int gdb_prepare_sources(const float* feat, int feat_channels_last, const float* 
  * Optional taps (any may be null; offsets required if any is non-null): the
  * reference's intermediates in its packed sample order -
  * rgbs_feat_dir (V,S,3b^2+F+4), vox_feat (S,8), sigma (S), feat (S,3b^2+F+8),
- * weights (S).  S_total is the row count of those tensors.                    */
+ * weights (S).  S_total is the row count of those tensors.
+ *
+ * Work distribution of the tensor-core kernels (precision 1 / 2, 2x2 bundles): persistent CTAs take their tiles from an atomic
+ * counter that lives in a __device__ array of the library (nothing is allocated): one counter per stream that ever launched
+ * (launches on a stream are ordered), a fresh one for every launch recorded during a stream capture; the call enqueues a
+ * 4-byte cudaMemsetAsync in front of the kernel (a memset node inside a graph).  With no counter to hand out (more than 64
+ * streams, 960 captured launches, cudaStreamPerThread, GDB_K3_STATIC=1) the CTAs stride through the tiles: same results, bit
+ * for bit, either way.                                                        */
 typedef struct gdb_render_taps {
   const int32_t* offsets;
   int64_t S_total;
