@@ -240,6 +240,28 @@ def test_view_counts_two_and_four(workload, hw, V):
     assert _md(var, tv) <= 1e-4
 
 
+@pytest.mark.parametrize("V", [2, 4])
+def test_full_size_view_counts_on_the_dynamic_tile_path(V):
+    """Two and four source views at the full DTU size: more tiles than tile slots, so the 2x2 tensor-core kernels (four
+    tile slots per SM with two views, three with four) draw tiles from the atomic counter.  Checked against the fp32 SIMT
+    kernel, which has no counter: a skipped or repeated tile would leave garbage / stale rows far outside the class."""
+    cfg, w, rig, data, mlp, feat_dim = _full_size_inputs("dtu", V=V)
+    b = cfg.nerf.bundle_size
+    cam = ops.camera_block(rig["tar_exts"].to(DEV), rig["tar_ints"].to(DEV), rig["src_exts"].to(DEV), rig["src_ints"].to(DEV),
+                           rig["near_far"].to(DEV), b, cfg.nerf.global_num_depth, False)
+    src = ops.prepare_sources(data["feat"].to(DEV), data["rgb"].to(DEV), b, cfg.nerf.max_mipmap_level)
+    vol_cl = ops.to_channels_last(data["vol"].to(DEV), 8)
+    args = (src, vol_cl, data["depth_range"].to(DEV), data["vol_range"].to(DEV), cam, ops.pack_mlp(mlp, feat_dim, device=DEV),
+            1, V, w["H"], w["W"], b, cfg.nerf.max_num_samples, False, True)
+    ref = ops.render_fused(*args, precision=0)
+    for _ in range(2):                                    # the second launch re-uses the stream's counter
+        out = ops.render_fused(*args, precision=1)
+        assert _md(out["feat"], ref["feat"]) <= 2e-3
+        assert _md(out["feat"][:, :3 * b * b], ref["feat"][:, :3 * b * b]) <= 1e-4
+        assert _md(out["depth"], ref["depth"]) <= 1e-4 * (w["far"] - w["near"])
+        assert _md(out["opacity"], torch.ones_like(out["opacity"])) <= 1e-5
+
+
 def test_full_size_warp_variance_against_oracle():
     w = WORKLOADS["dtu"]
     cfg = make_cfg(w["recipe"])
