@@ -279,6 +279,13 @@ __device__ __forceinline__ U4 ldg256(const float* p) {
 __device__ __forceinline__ void stcs256(float* p, const U4& r) {
   asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(r.a), "l"(r.b), "l"(r.c), "l"(r.d) : "memory");
 }
+__device__ __forceinline__ u64 shfl_down64(u64 v, int delta) {
+  const unsigned lo = __shfl_down_sync(0xffffffffu, (unsigned)v, delta), hi = __shfl_down_sync(0xffffffffu, (unsigned)(v >> 32), delta);
+  return (u64)lo | ((u64)hi << 32);
+}
+__device__ __forceinline__ U4 shfl_down256(const U4& v, int delta) {
+  return U4{shfl_down64(v.a, delta), shfl_down64(v.b, delta), shfl_down64(v.c, delta), shfl_down64(v.d, delta)};
+}
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ U4 u4_mul(const U4& v, u64 w) { return U4{mul2(v.a, w), mul2(v.b, w), mul2(v.c, w), mul2(v.d, w)}; }
@@ -287,14 +294,23 @@ __device__ __forceinline__ U4 u4_add(const U4& x, const U4& y) { return U4{add2(
 __device__ __forceinline__ U4 u4_sub(const U4& x, const U4& y) { return U4{sub2(x.a, y.a), sub2(x.b, y.b), sub2(x.c, y.c), sub2(x.d, y.d)}; }
 __device__ __forceinline__ U4 u4_sqacc(const U4& x, const U4& acc) { return U4{fma2(x.a, x.a, acc.a), fma2(x.b, x.b, acc.b), fma2(x.c, x.c, acc.c), fma2(x.d, x.d, acc.d)}; }
 
-template <int C, int V, int OUT_CL>      // 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
+//
+// Measured variants, GDB_K1_VARIANT = bit mask (read per call; tools/bench_k1.py):
+// bit 1 (NOSHFL): every lane projects its pixel into ALL V views itself instead of receiving the views of the other lanes of its
+// pixel by 6 shuffles per view - more issue slots (an issue utilisation of 42-47 % has room), fewer trips through the LSU.
+// bit 0 (XS): the x-adjacent pixel of a lane sits LPP lanes further on; where its left
+// column is my right column (same clamped rows, neighbour's c0 == my c1 - the rule wherever source and target pitch agree),
+// my two right-column taps ARE the neighbour's two left-column taps and arrive by shuffle (8 SHFL per 256-bit tap) instead
+// of by load; the other lanes load them as before (predicated).  Same values, same operation order: bit-identical.
+template <int C, int V, int OUT_CL, int VAR>      // 1: (B,D,Ht,Wt,C); 2: (B,Ht,Wt,D,C) depth folded into the channels
 __global__ void __launch_bounds__(256)
 warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
                       int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
                       float* __restrict__ out) {
+  constexpr bool XS = (VAR & 1) != 0, NOSHFL = (VAR & 2) != 0 || C == 8;
   constexpr int LPP = C / 8;                   // lanes per pixel
   constexpr int PIX = 256 / LPP;               // pixels per CTA
-  constexpr int VPL = (V + LPP - 1) / LPP;     // projections per lane
+  constexpr int VPL = NOSHFL ? V : (V + LPP - 1) / LPP;     // projections per lane
   __shared__ float sproj[V * 12];
 
   const int b = blockIdx.z;
@@ -312,7 +328,7 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
   float rx[VPL], ry[VPL], rz[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
-    const float* P = sproj + min(q + k * LPP, V - 1) * 12;
+    const float* P = sproj + (NOSHFL ? k : min(q + k * LPP, V - 1)) * 12;
     rx[k] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
     ry[k] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
     rz[k] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
@@ -330,14 +346,14 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
     const float depth = inv_depth ? fdiv(1.f, dv) : dv;
     WarpTap mine[VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) mine[k] = warp_tap(sproj + min(q + k * LPP, V - 1) * 12, rx[k], ry[k], rz[k], depth, Ws, Hs);
+    for (int k = 0; k < VPL; ++k) mine[k] = warp_tap(sproj + (NOSHFL ? k : min(q + k * LPP, V - 1)) * 12, rx[k], ry[k], rz[k], depth, Ws, Hs);
     U4 val[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int src = group_base + v % LPP;
-      const WarpTap m = mine[v / LPP];
+      const WarpTap m = mine[NOSHFL ? v : v / LPP];
       WarpTap t;
-      if (LPP > 1) {
+      if (!NOSHFL) {
         t.xx = __shfl_sync(0xffffffffu, m.xx, src);
         t.yy = __shfl_sync(0xffffffffu, m.yy, src);
         t.wx0 = __shfl_sync(0xffffffffu, m.wx0, src);
@@ -351,8 +367,21 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
       const int c0 = t.xx & 0xffff, c1 = t.xx >> 16;
       const float* vb = fbase + v * view_stride;
       // dead pixels of the last tile read pixel (0, 0)'s taps: in bounds, never stored
-      const U4 t00 = ldg256(vb + (size_t)(r0 + c0) * C), t10 = ldg256(vb + (size_t)(r0 + c1) * C);
-      const U4 t01 = ldg256(vb + (size_t)(r1 + c0) * C), t11 = ldg256(vb + (size_t)(r1 + c1) * C);
+      const U4 t00 = ldg256(vb + (size_t)(r0 + c0) * C), t01 = ldg256(vb + (size_t)(r1 + c0) * C);
+      U4 t10, t11;
+      if constexpr (XS) {
+        const int nxx = __shfl_down_sync(0xffffffffu, t.xx, LPP), nyy = __shfl_down_sync(0xffffffffu, t.yy, LPP);
+        const bool shared = (int)(threadIdx.x & 31) + LPP < 32 && nyy == t.yy && (nxx & 0xffff) == c1;
+        t10 = shfl_down256(t00, LPP);
+        t11 = shfl_down256(t01, LPP);
+        if (!shared) {
+          t10 = ldg256(vb + (size_t)(r0 + c1) * C);
+          t11 = ldg256(vb + (size_t)(r1 + c1) * C);
+        }
+      } else {
+        t10 = ldg256(vb + (size_t)(r0 + c1) * C);
+        t11 = ldg256(vb + (size_t)(r1 + c1) * C);
+      }
       const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
       U4 acc = u4_mul(t00, pack2(w00, w00));
       acc = u4_fma(t10, pack2(w10, w10), acc);
@@ -381,6 +410,11 @@ static bool warp_variance_v1() {
   if (v < 0) { const char* e = getenv("GDB_K1_V1"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+// GDB_K1_VARIANT = 0..3 selects the measured variants of the second-generation kernel (VAR above; read per call)
+static int warp_variance_variant() {
+  const char* e = getenv("GDB_K1_VARIANT");
+  return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+}
 
 template <int C, int V>
 static int launch_warp_variance(const float* feat, const float* proj, const float* range, int rh, int rw, int B, int Hs,
@@ -396,10 +430,16 @@ static int launch_warp_variance(const float* feat, const float* proj, const floa
     DCH = D;
     while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
     dim3 grid8(tiles, (D + DCH - 1) / DCH, B);
-    if (out_cl == 2)
-      warp_variance8_kernel<C, V, 2><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
-    else
-      warp_variance8_kernel<C, V, 1><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out);
+    const int var = C >= 16 ? warp_variance_variant() : 0;
+#define GDB_WV8(VAR_)                                                                                                              \
+  if (var == VAR_) {                                                                                                               \
+    if (out_cl == 2)                                                                                                               \
+      warp_variance8_kernel<C, V, 2, (C >= 16 ? VAR_ : 0)><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out); \
+    else                                                                                                                           \
+      warp_variance8_kernel<C, V, 1, (C >= 16 ? VAR_ : 0)><<<grid8, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, DCH, inv_depth, out); \
+  }
+    GDB_WV8(0) GDB_WV8(1) GDB_WV8(2) GDB_WV8(3)
+#undef GDB_WV8
     return cuda_check("gdb_warp_variance_fwd");
   }
   dim3 grid(tiles, (D + DCH - 1) / DCH, B);
