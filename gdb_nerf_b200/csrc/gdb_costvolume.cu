@@ -404,16 +404,151 @@ warp_variance8_kernel(const float* __restrict__ feat, const float* __restrict__ 
   }
 }
 
+// K1, vertical-pair variant (GDB_K1_VARIANT=4, measured): thread = (two vertically adjacent target pixels, 8-channel slice).
+// ncu of the kernel above: the L1 data pipe is 88-91 % busy (profiles/r02_ncu_full_k1_variants.json), i.e. only fewer bytes
+// through L1 per output can make it faster.  Where source and target pitch agree, the top row of the lower pixel's 2x2
+// footprint IS the bottom row of the upper pixel's (same clamped columns, r0 of B == r1 of A): those two taps are taken from
+// registers, 6 loads instead of 8 per (pair, view, plane).  The pairing is vertical so that the lanes of a warp still walk
+// consecutive x: every load / store instruction covers the same contiguous bytes as in the kernel above.  Same values, same
+// operation order per pixel: bit-identical.  Pairs whose footprints do not line up load all 8 taps.
+template <int C, int V, int OUT_CL>
+__global__ void __launch_bounds__(256, 2)
+warp_variance8_vpair_kernel(const float* __restrict__ feat, const float* __restrict__ proj, const float* __restrict__ range,
+                            int rh, int rw, int Hs, int Ws, int D, int Ht, int Wt, int DCH, int inv_depth,
+                            float* __restrict__ out) {
+  constexpr int LPP = C / 8;                   // lanes per pixel pair
+  constexpr int PIXP = 256 / LPP;              // pixel pairs per CTA
+  constexpr int NK = 2 * V;                    // (pixel, view) projections of a pair: k = s * V + v
+  constexpr int VPL = (NK + LPP - 1) / LPP;    // projections per lane
+  __shared__ float sproj[V * 12];
+
+  const int b = blockIdx.z;
+  const int HW = Ht * Wt;
+  const int NP = ((Ht + 1) >> 1) * Wt;         // pairs per target view
+  const int q = threadIdx.x % LPP;
+  const int pp = blockIdx.x * PIXP + threadIdx.x / LPP;
+  const bool liveA = pp < NP;
+  const int px = liveA ? pp % Wt : 0, pyp = liveA ? pp / Wt : 0;
+  const int pyA = 2 * pyp, pyB = min(2 * pyp + 1, Ht - 1);
+  const bool liveB = liveA && 2 * pyp + 1 < Ht;
+  const int group_base = (threadIdx.x & 31) - q;
+
+  if (threadIdx.x < V * 12) sproj[threadIdx.x] = proj[(size_t)b * V * 12 + threadIdx.x];
+  __syncthreads();
+
+  const float fx = (float)px + 0.5f;
+  float rx[VPL], ry[VPL], rz[VPL];
+  int po[VPL];
+  bool sB[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int k = min(q + j * LPP, NK - 1);
+    sB[j] = k >= V;
+    po[j] = (k - (sB[j] ? V : 0)) * 12;
+    const float* P = sproj + po[j];
+    const float fy = (float)(sB[j] ? pyB : pyA) + 0.5f;
+    rx[j] = fmaf(P[0], fx, fmaf(P[1], fy, P[2]));
+    ry[j] = fmaf(P[4], fx, fmaf(P[5], fy, P[6]));
+    rz[j] = fmaf(P[8], fx, fmaf(P[9], fy, P[10]));
+  }
+  const int rxi = rw == 1 ? 0 : px, ryA = rh == 1 ? 0 : pyA, ryB = rh == 1 ? 0 : pyB;
+  const float nearA = range[((size_t)(b * 2 + 0) * rh + ryA) * rw + rxi], farA = range[((size_t)(b * 2 + 1) * rh + ryA) * rw + rxi];
+  const float nearB = range[((size_t)(b * 2 + 0) * rh + ryB) * rw + rxi], farB = range[((size_t)(b * 2 + 1) * rh + ryB) * rw + rxi];
+  const size_t view_stride = (size_t)Hs * Ws * C;
+  const float* fbase = feat + (size_t)b * V * view_stride + q * 8;
+  const int pixA = pyA * Wt + px, pixB = pyB * Wt + px;
+
+  const int d0 = blockIdx.y * DCH;
+  const int d1 = min(d0 + DCH, D);
+  for (int d = d0; d < d1; ++d) {
+    const float dvA = hypothesis(nearA, farA, d, D, inv_depth), dvB = hypothesis(nearB, farB, d, D, inv_depth);
+    const float depthA = inv_depth ? fdiv(1.f, dvA) : dvA, depthB = inv_depth ? fdiv(1.f, dvB) : dvB;
+    WarpTap mine[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) mine[j] = warp_tap(sproj + po[j], rx[j], ry[j], rz[j], sB[j] ? depthB : depthA, Ws, Hs);
+    U4 valA[V], valB[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      WarpTap tA, tB;
+      {
+        constexpr int dummy = 0; (void)dummy;
+        const int kA = v, kB = V + v;
+        const WarpTap mA = mine[kA / LPP], mB = mine[kB / LPP];
+        if (LPP > 1) {
+          const int sa = group_base + kA % LPP, sb = group_base + kB % LPP;
+          tA.xx = __shfl_sync(0xffffffffu, mA.xx, sa); tA.yy = __shfl_sync(0xffffffffu, mA.yy, sa);
+          tA.wx0 = __shfl_sync(0xffffffffu, mA.wx0, sa); tA.wx1 = __shfl_sync(0xffffffffu, mA.wx1, sa);
+          tA.wy0 = __shfl_sync(0xffffffffu, mA.wy0, sa); tA.wy1 = __shfl_sync(0xffffffffu, mA.wy1, sa);
+          tB.xx = __shfl_sync(0xffffffffu, mB.xx, sb); tB.yy = __shfl_sync(0xffffffffu, mB.yy, sb);
+          tB.wx0 = __shfl_sync(0xffffffffu, mB.wx0, sb); tB.wx1 = __shfl_sync(0xffffffffu, mB.wx1, sb);
+          tB.wy0 = __shfl_sync(0xffffffffu, mB.wy0, sb); tB.wy1 = __shfl_sync(0xffffffffu, mB.wy1, sb);
+        } else {
+          tA = mA; tB = mB;
+        }
+      }
+      const float* vb = fbase + v * view_stride;
+      const int rA0 = (tA.yy & 0xffff) * Ws, rA1 = (tA.yy >> 16) * Ws, cA0 = tA.xx & 0xffff, cA1 = tA.xx >> 16;
+      const int rB0 = (tB.yy & 0xffff) * Ws, rB1 = (tB.yy >> 16) * Ws, cB0 = tB.xx & 0xffff, cB1 = tB.xx >> 16;
+      // dead pixels read pixel (0, 0)'s (or the upper pixel's) taps: in bounds, never stored
+      const U4 a00 = ldg256(vb + (size_t)(rA0 + cA0) * C), a10 = ldg256(vb + (size_t)(rA0 + cA1) * C);
+      const U4 a01 = ldg256(vb + (size_t)(rA1 + cA0) * C), a11 = ldg256(vb + (size_t)(rA1 + cA1) * C);
+      const U4 b01 = ldg256(vb + (size_t)(rB1 + cB0) * C), b11 = ldg256(vb + (size_t)(rB1 + cB1) * C);
+      const bool shared = rB0 == rA1 && tB.xx == tA.xx;
+      {
+        const float w00 = tA.wx0 * tA.wy0, w10 = tA.wx1 * tA.wy0, w01 = tA.wx0 * tA.wy1, w11 = tA.wx1 * tA.wy1;
+        U4 acc = u4_mul(a00, pack2(w00, w00));
+        acc = u4_fma(a10, pack2(w10, w10), acc);
+        acc = u4_fma(a01, pack2(w01, w01), acc);
+        acc = u4_fma(a11, pack2(w11, w11), acc);
+        valA[v] = acc;
+      }
+      {
+        const float w00 = tB.wx0 * tB.wy0, w10 = tB.wx1 * tB.wy0, w01 = tB.wx0 * tB.wy1, w11 = tB.wx1 * tB.wy1;
+        U4 acc;
+        if (shared) {       // the upper pixel's bottom row is this pixel's top row
+          acc = u4_mul(a01, pack2(w00, w00));
+          acc = u4_fma(a11, pack2(w10, w10), acc);
+        } else {
+          const U4 b00 = ldg256(vb + (size_t)(rB0 + cB0) * C), b10 = ldg256(vb + (size_t)(rB0 + cB1) * C);
+          acc = u4_mul(b00, pack2(w00, w00));
+          acc = u4_fma(b10, pack2(w10, w10), acc);
+        }
+        acc = u4_fma(b01, pack2(w01, w01), acc);
+        acc = u4_fma(b11, pack2(w11, w11), acc);
+        valB[v] = acc;
+      }
+    }
+    const float invV = 1.f / (float)V;
+    const u64 iv = pack2(invV, invV);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const U4* val = s ? valB : valA;
+      U4 mean = val[0];
+#pragma unroll
+      for (int v = 1; v < V; ++v) mean = u4_add(mean, val[v]);
+      mean = u4_mul(mean, iv);
+      U4 var{0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int v = 0; v < V; ++v) var = u4_sqacc(u4_sub(val[v], mean), var);
+      var = u4_mul(var, iv);
+      const int pix = s ? pixB : pixA;
+      if (s ? liveB : liveA)
+        stcs256(out + (OUT_CL == 2 ? (((size_t)b * HW + pix) * D + d) : (((size_t)b * D + d) * HW + pix)) * C + q * 8, var);
+    }
+  }
+}
+
 // GDB_K1_V1=1 keeps the first-generation kernel (A/B measurements, tools/bench_k1.py)
 static bool warp_variance_v1() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GDB_K1_V1"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
-// GDB_K1_VARIANT = 0..3 selects the measured variants of the second-generation kernel (VAR above; read per call)
+// GDB_K1_VARIANT = 0..3 selects the measured variants of the second-generation kernel (VAR above), 4 the vertical-pair kernel
+// (read per call)
 static int warp_variance_variant() {
   const char* e = getenv("GDB_K1_VARIANT");
-  return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+  return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
 }
 
 template <int C, int V>
@@ -431,6 +566,17 @@ static int launch_warp_variance(const float* feat, const float* proj, const floa
     while (DCH > 2 && (long)tiles * ((D + DCH - 1) / DCH) * B < 4L * 4 * sm_count()) DCH = (DCH + 1) / 2;
     dim3 grid8(tiles, (D + DCH - 1) / DCH, B);
     const int var = C >= 16 ? warp_variance_variant() : 0;
+    if (var == 4) {
+      const int tp = (((Ht + 1) >> 1) * Wt + PIX8 - 1) / PIX8;
+      int dch = D;
+      while (dch > 2 && (long)tp * ((D + dch - 1) / dch) * B < 4L * 2 * sm_count()) dch = (dch + 1) / 2;
+      dim3 gridp(tp, (D + dch - 1) / dch, B);
+      if (out_cl == 2)
+        warp_variance8_vpair_kernel<C, V, 2><<<gridp, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, dch, inv_depth, out);
+      else
+        warp_variance8_vpair_kernel<C, V, 1><<<gridp, 256, 0, st>>>(feat, proj, range, rh, rw, Hs, Ws, D, Ht, Wt, dch, inv_depth, out);
+      return cuda_check("gdb_warp_variance_fwd");
+    }
 #define GDB_WV8(VAR_)                                                                                                              \
   if (var == VAR_) {                                                                                                               \
     if (out_cl == 2)                                                                                                               \

@@ -7,7 +7,9 @@ launches, and A/Bs the kernel variants the library selects by environment (read 
                          with that lane's left column
     GDB_K1_VARIANT=2     every lane projects its pixel into all views itself (no descriptor shuffles)
     GDB_K1_VARIANT=3     both
-all of them must be bit-identical to the default
+    GDB_K1_VARIANT=4     vertical pixel pairs per thread: the lower pixel's top footprint row taken from the upper pixel's registers
+                         where the two coincide (6 loads instead of 8 per pair and view)
+all of them must be bit-identical to the default (also checked on an odd-sized, ragged map)
 
     python tools/bench_k1.py [--workload dtu|llff|nerf] [--B 8] [--iters 20]
 """
@@ -42,7 +44,7 @@ for si, (scale, C, D) in enumerate(stages):
         rng = torch.stack((mid - half, mid + half)).unsqueeze(0).repeat(a.B, 1, 1, 1).to(dev)
     nbytes = feat.numel() * 4 + a.B * D * Hs * Ws * C * 4
     ref = None
-    for name, env in (("default", {}), ("xshare", {"GDB_K1_VARIANT": "1"}), ("noshfl", {"GDB_K1_VARIANT": "2"}), ("xshare+noshfl", {"GDB_K1_VARIANT": "3"})):
+    for name, env in (("default", {}), ("xshare", {"GDB_K1_VARIANT": "1"}), ("noshfl", {"GDB_K1_VARIANT": "2"}), ("xshare+noshfl", {"GDB_K1_VARIANT": "3"}), ("vpair", {"GDB_K1_VARIANT": "4"})):
         os.environ.pop("GDB_K1_VARIANT", None)
         os.environ.update(env)
         ts = []
@@ -58,3 +60,18 @@ for si, (scale, C, D) in enumerate(stages):
         print(f"K1 {a.workload} stage {si} (C={C} D={D} {Hs}x{Ws}, {a.B} views) {name}: {ms:.4f} ms (min {min(ts):.4f}) = "
               f"{nbytes / ms / 1e6:.0f} GB/s algorithmic{same}", flush=True)
     os.environ.pop("GDB_K1_VARIANT", None)
+
+# odd-sized ragged map, per-pixel ranges, every variant against the default
+Hs, Ws, C, D = 37, 53, 16, 5
+feat = (torch.randn(2, a.V, Hs, Ws, C, generator=g) * 0.5).to(dev)
+rig2 = camera_rig(2, a.V, Hs * 2, Ws * 2, near, far, focal * Hs * 2 / H, tilt=0.05)
+proj = ops.homography_mats(rig2["src_exts"].to(dev), rig2["src_ints"].to(dev), rig2["tar_exts"].to(dev), rig2["tar_ints"].to(dev), 0.5, 0.5)
+mid = near + (far - near) * (0.2 + 0.6 * torch.rand(2, 1, Hs, Ws, generator=g))
+rng = torch.cat((mid * 0.97, mid * 1.03), 1).to(dev)
+outs = []
+for v in range(5):
+    os.environ["GDB_K1_VARIANT"] = str(v)
+    outs.append([ops.warp_variance(feat, proj, rng, D, Hs, Ws, False, out_channels_last=True, depth_folded=f).clone() for f in (False, True)])
+os.environ.pop("GDB_K1_VARIANT", None)
+print("K1 odd-sized map (37x53, C=16, D=5): variants 1-4 bit-identical to default:",
+      [all(torch.equal(x, y) for x, y in zip(outs[v], outs[0])) for v in range(1, 5)], flush=True)
