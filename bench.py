@@ -578,7 +578,9 @@ def run_ours(args, wl, cfg):
             "gpu_launches": launches,
             "single_view_latency": latency,
             "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload]),
-            "roofline_warp_variance": roof("gdb_warp_variance_fwd", K1_BYTES_PER_VIEW[args.workload]),
+            "roofline_warp_variance": dict(roof("gdb_warp_variance_fwd", K1_BYTES_PER_VIEW[args.workload]) or {},
+                                           binding_pipe="L1 data pipe (l1tex__data_pipe_lsu_wavefronts 84-85 % of peak over elapsed, 88-91 % over "
+                                                        "active cycles: ncu --set full, profiles/r02_ncu_full_k1_variants.json), not HBM"),
             "roofline_mlp_tensor": roof_tensor("gdb_render_fused_fwd", K3_MLP_FLOP_PER_VIEW[args.workload]),
             "reference_cuda": ref_cuda,
             "mlp_variants": None if args.lean else {
