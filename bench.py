@@ -344,6 +344,37 @@ def run_ours(args, wl, cfg):
             for k, buf in out_host[i % NFLY].items():
                 buf.copy_(ret[k], non_blocking=True)
 
+    pipe = {}
+
+    def step_e2e_pipe(i):
+        """The same step as a copy pipeline around ONE compute stream: uploads on an upload stream, graph replays back to back on
+        a compute stream, downloads on a download stream, ordered by events; NFLY graph instances (= input / output buffer sets)
+        rotate.  Forwards of consecutive steps never interleave on the SMs (the three-stream scheme above lets them)."""
+        if not pipe:
+            pipe.update(cin=torch.cuda.Stream(device=dev), comp=torch.cuda.Stream(device=dev), cout=torch.cuda.Stream(device=dev),
+                        staged=[torch.cuda.Event() for _ in range(NFLY)], computed=[torch.cuda.Event() for _ in range(NFLY)],
+                        drained=[torch.cuda.Event() for _ in range(NFLY)])
+            for evs in (pipe["computed"], pipe["drained"]):
+                for ev in evs:
+                    ev.record(torch.cuda.current_stream(dev))
+        k = i % NFLY
+        r = runners[k]
+        with torch.no_grad():
+            with torch.cuda.stream(pipe["cin"]):
+                pipe["cin"].wait_event(pipe["computed"][k])       # the previous replay of this instance has read its inputs
+                r.stage(pinned)
+                pipe["staged"][k].record(pipe["cin"])
+            with torch.cuda.stream(pipe["comp"]):
+                pipe["comp"].wait_event(pipe["staged"][k])
+                pipe["comp"].wait_event(pipe["drained"][k])       # ... and its outputs have been copied out
+                ret, _, _ = r.replay()
+                pipe["computed"][k].record(pipe["comp"])
+            with torch.cuda.stream(pipe["cout"]):
+                pipe["cout"].wait_event(pipe["computed"][k])
+                for key, buf in out_host[k].items():
+                    buf.copy_(ret[key], non_blocking=True)
+                pipe["drained"][k].record(pipe["cout"])
+
     def time_e2e(step=None):
         step = step or step_e2e
         for i in range(2 * NFLY):
@@ -415,7 +446,7 @@ def run_ours(args, wl, cfg):
     ms_e2e = time_e2e()
     # ... and with the forward as a CUDA-graph replay (every rank decides alone whether its capture worked; the slowest path of
     # any rank is what the max over ranks reports)
-    ms_e2e_graph, graph_note = 0.0, "not attempted (--no-e2e-graph)"
+    ms_e2e_graph, ms_e2e_pipe, graph_note = 0.0, 0.0, "not attempted (--no-e2e-graph)"
     if not args.no_e2e_graph:
         try:
             from gdb_nerf_b200.graphed import GraphedForward
@@ -432,6 +463,8 @@ def run_ours(args, wl, cfg):
             dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
         if float(ok_all[0]) > 0:
             ms_e2e_graph = time_e2e(step_e2e_graph)
+            ms_e2e_pipe = time_e2e(step_e2e_pipe)
+        pipe.clear()
         runners.clear()
         torch.cuda.empty_cache()
     ms_e2e_p2 = 0.0
@@ -507,14 +540,17 @@ def run_ours(args, wl, cfg):
         ref_cuda = reference_cuda_probe(args.workload, cfg, dev)
     barrier()
 
-    t = torch.tensor([ms_dev, ms_e2e, alt[0][0] if alt else 0.0, alt[2][0] if alt else 0.0, ms_e2e_p2, ms_e2e_graph], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, alt[0][0] if alt else 0.0, alt[2][0] if alt else 0.0, ms_e2e_p2, ms_e2e_graph, ms_e2e_pipe], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_p0, ms_p2, ms_e2e_p2, ms_e2e_graph = (float(x) for x in t)
+    ms_dev, ms_e2e, ms_p0, ms_p2, ms_e2e_p2, ms_e2e_graph, ms_e2e_pipe = (float(x) for x in t)
     ms_e2e_eager = ms_e2e
-    use_graph = 0.0 < ms_e2e_graph < ms_e2e   # both paths are public API and both were timed: the faster one is the end-to-end figure
+    use_graph = 0.0 < ms_e2e_graph < ms_e2e   # all paths are public API and all were timed: the fastest one is the end-to-end figure
     if use_graph:
         ms_e2e = ms_e2e_graph
+    use_pipe = 0.0 < ms_e2e_pipe < ms_e2e
+    if use_pipe:
+        ms_e2e = ms_e2e_pipe
 
     if rank == 0:
         rays_per_step = world * B * H * W
@@ -570,11 +606,15 @@ def run_ours(args, wl, cfg):
                     "ms_per_step": ms_e2e / args.steps, "what": "pinned host batch (8-bit source images, cameras) -> H2D -> Network.forward -> D2H of ret['rgb'], "
                             "ret['nerf_depth'], ret['mvs_depth'] into pinned memory, every step; three steps in flight on three streams (copies overlap kernels); "
                             "wall clock over all steps",
-                    "forward": ("one CUDA-graph replay per step (gdb_nerf_b200.graphed.GraphedForward, one instance per step in flight)"
+                    "forward": ("copy pipeline around one compute stream: GraphedForward.stage on an upload stream, .replay back to back on a compute "
+                                "stream, the downloads on a third, ordered by events (three instances rotate)" if use_pipe else
+                                "one CUDA-graph replay per step (gdb_nerf_b200.graphed.GraphedForward, one instance per step in flight)"
                                 if use_graph else "eager operator calls (Network.forward)"),
                     "eager": {"value": rays_per_step * args.steps / (ms_e2e_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_eager / args.steps},
                     "cuda_graph": ({"value": rays_per_step * args.steps / (ms_e2e_graph * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_graph / args.steps}
-                                   if ms_e2e_graph > 0.0 else graph_note)},
+                                   if ms_e2e_graph > 0.0 else graph_note),
+                    "cuda_graph_copy_pipeline": ({"value": rays_per_step * args.steps / (ms_e2e_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_pipe / args.steps}
+                                                 if ms_e2e_pipe > 0.0 else graph_note)},
             "gpu_launches": launches,
             "single_view_latency": latency,
             "roofline": roof("gdb_render_fused_fwd", K3_BYTES_PER_VIEW[args.workload]),

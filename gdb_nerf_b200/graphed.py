@@ -73,12 +73,23 @@ class GraphedForward:
             self._out = net(self._batch)
 
     def __call__(self, batch: Mapping) -> Tuple[Dict[str, torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
+        self.stage(batch)
+        return self.replay()
+
+    def stage(self, batch: Mapping) -> None:
+        """Copies ``batch`` (host or device tensors) into the graph's static inputs on the CURRENT stream.  With ``replay`` this
+        lets a caller run uploads, replays and downloads of consecutive batches on three streams ordered by events (a copy
+        pipeline around ONE compute stream) instead of whole steps on several streams."""
         flat = _flatten(batch)
         for k, dst in self._static_in.items():
             src = flat[k]
             if src.shape != dst.shape:
                 raise ValueError(f"{k}: shape {tuple(src.shape)} differs from the captured {tuple(dst.shape)}")
             dst.copy_(src, non_blocking=True)
+
+    def replay(self) -> Tuple[Dict[str, torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
+        """Replays the captured forward on the current stream; the returned tensors are the graph's static outputs
+        (overwritten by the next replay of this instance)."""
         self.graph.replay()
         return self._out
 
