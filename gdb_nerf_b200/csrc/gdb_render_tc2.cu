@@ -62,6 +62,10 @@ __device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w,
 //                        0.894 / 1.676 (+1.3 %), 2.229 (-0.3 %)
 //   -DGDB_X_UNCOND       plain gathers instead of predicated ones with zero-initialised destinations: 0.906 / 1.708 (+2.5 / +3 %)
 //   -DGDB_X_ROLLR        the two rounds of GEMM 4 as one rolled loop: 0.936 / 1.774 (+6 %)
+//   -DGDB_X_LINPROJ      colour pass: pixel -> source-image projection of a (row, ray, view) as ONE 3x3 matrix per (target view,
+//                        source view) composed in double precision when the camera block is staged (image = z * Q (x, y, 1) + c:
+//                        9 FMAs per view instead of 12 + 18; not bit-identical to the default chain, same rounding class)
+//   -DGDB_X_RCPA         colour pass: MUFU.RCP alone (1 ulp) instead of the correctly rounded reciprocal
 template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
@@ -161,6 +165,33 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       group_sync(g);
       for (int i = row; i < CAM_HEAD + CAM_VIEW * V; i += 128) scam[i] = p.cam[(size_t)b * p.cam_stride + i];
       group_sync(g);
+#ifdef GDB_X_LINPROJ
+      if (row < V) {
+        // Q = K_v R_v M, c = K_v (R_v o + t_v): image coordinates of pixel (x, y) at ray depth z are z * Q (x, y, 1) + c
+        const float* cv = scam + CAM_HEAD + CAM_VIEW * row;
+        double A[9], Q[9], c3[3];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += (double)cv[CV_K + i * 3 + k] * (double)cv[CV_E + k * 4 + j];
+            A[i * 3 + j] = a;
+          }
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 3; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += A[i * 3 + k] * (double)scam[CAM_M + k * 3 + j];
+            Q[i * 3 + j] = a;
+          }
+          double a = 0.0;
+          for (int k = 0; k < 3; ++k) a += A[i * 3 + k] * (double)scam[CAM_O + k] + (double)cv[CV_K + i * 3 + k] * (double)cv[CV_E + k * 4 + 3];
+          c3[i] = a;
+        }
+        float* L = scam + C::LIN_FLOATS_OFF + row * 12;
+        for (int i = 0; i < 9; ++i) L[i] = (float)Q[i];
+        for (int i = 0; i < 3; ++i) L[9 + i] = (float)c3[i];
+      }
+      group_sync(g);
+#endif
       cur_b = b;
     }
     const int pix_warp0 = pix_lo + ((tile - b * tiles_pv) * 4 + wq) * G;       // first bundle of my warp
@@ -926,16 +957,24 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         const int64_t srow_r = TAPS ? (int64_t)(((uint64_t)rc.z << 32) | rc.y) : 0;
         const float wvr[4] = {rb.x, rb.y, rb.z, rb.w};
         const float x = ra.y + (float)(j % BS), y = ra.z + (float)(j / BS);
+#ifndef GDB_X_LINPROJ
         const float* M = head + CAM_M;
         const float dx = fmaf(x, M[0], fmaf(y, M[1], M[2]));
         const float dy = fmaf(x, M[3], fmaf(y, M[4], M[5]));
         const float dz = fmaf(x, M[6], fmaf(y, M[7], M[8]));
         const float wx = fmaf(dx, zr, ox), wy = fmaf(dy, zr, oy), wz = fmaf(dz, zr, oz);
+#endif
         // all 4 V taps of the (row, ray) in flight at once
         float4 t[V][4];
         float tw[V][4];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
+#ifdef GDB_X_LINPROJ
+          const float* L = scam + C::LIN_FLOATS_OFF + v * 12;
+          const float ix = fmaf(zr, fmaf(x, L[0], fmaf(y, L[1], L[2])), L[9]);
+          const float iy = fmaf(zr, fmaf(x, L[3], fmaf(y, L[4], L[5])), L[10]);
+          const float iz = fmaxf(fmaf(zr, fmaf(x, L[6], fmaf(y, L[7], L[8])), L[11]), 1e-6f);
+#else
           const float* cv = head + CAM_HEAD + CAM_VIEW * v;
           float cx = fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
           float cy = fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
@@ -943,7 +982,13 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
           float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
           float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+#endif
+#ifdef GDB_X_RCPA
+          float rz;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(iz));
+#else
           const float rz = __frcp_rn(iz);
+#endif
           float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
           const Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
           const float4* ib = reinterpret_cast<const float4*>(p.rgba) + (size_t)(b * V + v) * p.H * p.W;

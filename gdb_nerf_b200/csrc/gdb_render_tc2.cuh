@@ -64,7 +64,12 @@ struct Tc2Cfg {
   static constexpr int A_S = A_FD + CH_FD * CHB;
   static constexpr int A_END = ((A_S + CH_S * CHB + 127) / 128) * 128;
   static constexpr int CAM_OFF = A_END + 128;          // mbarrier at A_END
+#ifdef GDB_X_LINPROJ
+  static constexpr int LIN_FLOATS_OFF = ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 32;   // composed projections, floats from the camera block
+  static constexpr int GROUP_BYTES = CAM_OFF + LIN_FLOATS_OFF * 4 + (12 * V * 4 + 127) / 128 * 128;
+#else
   static constexpr int GROUP_BYTES = CAM_OFF + ((CAM_HEAD + CAM_VIEW * V) * 4 + 127) / 128 * 128;
+#endif
   static constexpr int ZERO_OFF = GROUP_OFF + NG * GROUP_BYTES;   // constant chunks after every group
   static constexpr int ONE_OFF = ZERO_OFF + 2048;
   static constexpr int SMEM = ONE_OFF + 2048;
