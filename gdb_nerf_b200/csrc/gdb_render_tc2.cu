@@ -53,6 +53,17 @@ __device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w,
   }
 }
 
+// single-MUFU reciprocal / square root (1-2 ulp, no range-check branch and no slow-path call behind them)
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#ifdef GDB_X_P1A
+#define GDB_P1_SQRT sqrt_approx
+#define GDB_P1_RCP rcp_approx
+#else
+#define GDB_P1_SQRT sqrtf
+#define GDB_P1_RCP __frcp_rn
+#endif
+
 //
 // Measured variants kept behind compile-time flags (tools/build_variant.sh; profiles/r02_k3_experiments_s3.log; ms per 8 views,
 // DTU / LLFF / NeRF-synthetic against 0.882 / 1.655 / 2.27 of the default build in the same call):
@@ -66,6 +77,7 @@ __device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w,
 //                        source view) composed in double precision when the camera block is staged (image = z * Q (x, y, 1) + c:
 //                        9 FMAs per view instead of 12 + 18; not bit-identical to the default chain, same rounding class)
 //   -DGDB_X_RCPA         colour pass: MUFU.RCP alone (1 ulp) instead of the correctly rounded reciprocal
+//   -DGDB_X_P1A          P0 / P1 (per row and view): single-MUFU square roots and reciprocal (ball radius, mip level, texture coordinate)
 template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
     float ball;
     {
       float ex = cwx - ox, ey = cwy - oy, ez = cwz - oz;
-      ball = sqrtf(ex * ex + ey * ey + ez * ez) * geo.unit_ball;
+      ball = GDB_P1_SQRT(ex * ex + ey * ey + ez * ez) * geo.unit_ball;
     }
 
     // ---- voxel feature (bundle_sampler.py:322-324), kept as one packed fp16 chunk until region X is free
@@ -295,17 +307,17 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
       const float ccy = fmaf(cwx, cv[CV_E + 4], fmaf(cwy, cv[CV_E + 5], fmaf(cwz, cv[CV_E + 6], cv[CV_E + 7])));
       const float ccz = fmaf(cwx, cv[CV_E + 8], fmaf(cwy, cv[CV_E + 9], fmaf(cwz, cv[CV_E + 10], cv[CV_E + 11])));
       // mip level (:343-348): only its fractional part reaches the output, approximate division is ample
-      const float dist = sqrtf(ccx * ccx + ccy * ccy + ccz * ccz);
+      const float dist = GDB_P1_SQRT(ccx * ccx + ccy * ccy + ccz * ccz);
       const float sec = __fdividef(dist, ccz);
       const float sec_sq = sec * sec;
       const float rb = __fdividef(dist, ball);
-      const float foot = __fdividef(sec_sq, sqrtf(fmaxf(rb * rb - 1.f, 1e-12f)) + sqrtf(fmaxf(sec_sq - 1.f, 1e-12f)));
+      const float foot = __fdividef(sec_sq, GDB_P1_SQRT(fmaxf(rb * rb - 1.f, 1e-12f)) + GDB_P1_SQRT(fmaxf(sec_sq - 1.f, 1e-12f)));
       const float lod = log2f(__fdividef(foot, cv[CV_PIXR]));
       constexpr float ifb = 1.f / (float)BS;                  // power of two: exact
       const float pxc = fmaf(ccx, cv[CV_K + 0] * ifb, fmaf(ccy, cv[CV_K + 1] * ifb, ccz * (cv[CV_K + 2] * ifb)));
       const float pyc = fmaf(ccx, cv[CV_K + 3] * ifb, fmaf(ccy, cv[CV_K + 4] * ifb, ccz * (cv[CV_K + 5] * ifb)));
       const float pzc = fmaxf(fmaf(ccx, cv[CV_K + 6], fmaf(ccy, cv[CV_K + 7], ccz * cv[CV_K + 8])), 1e-6f);
-      const float rz = __frcp_rn(pzc);
+      const float rz = GDB_P1_RCP(pzc);
       const float u01 = pxc * rz * inv_Wb, v01 = pyc * rz * inv_Hb;
       d_a0[v] = 0; d_a1[v] = 0; d_pk[v] = 0;
       d_fu0[v] = d_fv0[v] = d_fu1[v] = d_fv1[v] = d_fr[v] = 0.f;
@@ -984,8 +996,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
           float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
 #endif
 #ifdef GDB_X_RCPA
-          float rz;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(iz));
+          const float rz = rcp_approx(iz);
 #else
           const float rz = __frcp_rn(iz);
 #endif
@@ -1076,7 +1087,11 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
         float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
         float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+#ifdef GDB_X_RCPA
+        const float rz = rcp_approx(iz);
+#else
         const float rz = fdiv(1.f, iz);
+#endif
         float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (actr) {
