@@ -25,6 +25,22 @@
 //    gather iterations / rays / views of the epilogues are rolled: 7.3 k SASS instructions instead of 13.3 k in the first
 //    tcgen05 variant, whose top stall reason was instruction fetch.  The production instantiation (TAPS = false)
 //    carries none of the per-sample parity outputs.
+// Round 2, last session (profiles/r02_k3_rcpa.log): the correctly rounded reciprocal of the colour pass (__frcp_rn: MUFU.RCP, two
+// Newton steps, a range check and a CALL to a slow path) sat between the projection of a (row, ray) into a view and that view's
+// four gathers, so the twelve "branch-free" gathers of an item were in fact three dependent groups.  Defaults now:
+//   GDB_X_RCPA    colour pass: MUFU.RCP alone (1 ulp of a pixel coordinate, 6e-5 px at 800 px)
+//   GDB_X_P1A     P0 / P1 (per row and view): single-MUFU square roots / reciprocal (ball radius, mip level, texture coordinate)
+//   GDB_X_LINPROJ colour pass: pixel -> source-image projection as ONE 3x3 matrix + offset per (target view, source view),
+//                 composed in double precision when the camera block is staged: image = z * Q (x, y, 1) + c, 9 FMAs per
+//                 (row, ray, view) instead of 12 + 18
+// 0.885 -> 0.856 ms per 8 DTU views, 2.22 -> 1.93 ms at NeRF-synthetic 4x4, 1.66 -> 1.59 ms at LLFF; errors against the oracle
+// unchanged (fine rgb max 1.2e-5 / 1.7e-5).  -DGDB_X_EXACT restores the exact chain (A/B).  Both generations (precision 1 / 4)
+// follow the same flags and stay bit-identical to each other.
+#ifndef GDB_X_EXACT
+#define GDB_X_RCPA
+#define GDB_X_P1A
+#define GDB_X_LINPROJ
+#endif
 #include "gdb_render_tc2.cuh"
 
 namespace gdb {
@@ -53,9 +69,6 @@ __device__ __forceinline__ void relu_dot32(const float (&g)[32], const float* w,
   }
 }
 
-// single-MUFU reciprocal / square root (1-2 ulp, no range-check branch and no slow-path call behind them)
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #ifdef GDB_X_P1A
 #define GDB_P1_SQRT sqrt_approx
 #define GDB_P1_RCP rcp_approx
@@ -73,11 +86,8 @@ __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.appro
 //                        0.894 / 1.676 (+1.3 %), 2.229 (-0.3 %)
 //   -DGDB_X_UNCOND       plain gathers instead of predicated ones with zero-initialised destinations: 0.906 / 1.708 (+2.5 / +3 %)
 //   -DGDB_X_ROLLR        the two rounds of GEMM 4 as one rolled loop: 0.936 / 1.774 (+6 %)
-//   -DGDB_X_LINPROJ      colour pass: pixel -> source-image projection of a (row, ray, view) as ONE 3x3 matrix per (target view,
-//                        source view) composed in double precision when the camera block is staged (image = z * Q (x, y, 1) + c:
-//                        9 FMAs per view instead of 12 + 18; not bit-identical to the default chain, same rounding class)
-//   -DGDB_X_RCPA         colour pass: MUFU.RCP alone (1 ulp) instead of the correctly rounded reciprocal
-//   -DGDB_X_P1A          P0 / P1 (per row and view): single-MUFU square roots and reciprocal (ball radius, mip level, texture coordinate)
+//   -DGDB_X_EXACT        the exact reciprocal / square roots and the step-by-step projection chain of the colour pass (the default
+//                        until the last session of round 2): 0.885 / 1.66 / 2.22 against 0.856 / 1.59 / 1.93
 template <int BS, int FEAT_DIM, int V, int NG, bool TAPS, int GEN, int FB>
 __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderParams p) {
   using C = Tc2Cfg<BS, FEAT_DIM, V, NG>;
@@ -1072,14 +1082,22 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
 #pragma unroll
       for (int v = 0; v < V; ++v) wvr[v] = __shfl_sync(full, wv[v], r);
       const float x = x0r + (float)(j % BS), y = y0r + (float)(j / BS);
+#ifndef GDB_X_LINPROJ
       const float* M = head + CAM_M;
       const float dx = fmaf(x, M[0], fmaf(y, M[1], M[2]));
       const float dy = fmaf(x, M[3], fmaf(y, M[4], M[5]));
       const float dz = fmaf(x, M[6], fmaf(y, M[7], M[8]));
       const float wx = fmaf(dx, zr, ox), wy = fmaf(dy, zr, oy), wz = fmaf(dz, zr, oz);
+#endif
       float cr = 0.f, cg = 0.f, cb = 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
+#ifdef GDB_X_LINPROJ
+        const float* L = scam + C::LIN_FLOATS_OFF + v * 12;
+        const float ix = fmaf(zr, fmaf(x, L[0], fmaf(y, L[1], L[2])), L[9]);
+        const float iy = fmaf(zr, fmaf(x, L[3], fmaf(y, L[4], L[5])), L[10]);
+        const float iz = fmaxf(fmaf(zr, fmaf(x, L[6], fmaf(y, L[7], L[8])), L[11]), 1e-6f);
+#else
         const float* cv = head + CAM_HEAD + CAM_VIEW * v;
         float cx = fmaf(wx, cv[CV_E + 0], fmaf(wy, cv[CV_E + 1], fmaf(wz, cv[CV_E + 2], cv[CV_E + 3])));
         float cy = fmaf(wx, cv[CV_E + 4], fmaf(wy, cv[CV_E + 5], fmaf(wz, cv[CV_E + 6], cv[CV_E + 7])));
@@ -1087,6 +1105,7 @@ __global__ void __launch_bounds__(128 * NG, 1) render_tc2_kernel(const RenderPar
         float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
         float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
         float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+#endif
 #ifdef GDB_X_RCPA
         const float rz = rcp_approx(iz);
 #else

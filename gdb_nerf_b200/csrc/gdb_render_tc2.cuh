@@ -172,6 +172,9 @@ __device__ __forceinline__ float4 ldg4_if(const float4* ptr, bool pred) {
       : "l"(ptr), "r"((int)pred));
   return r;
 }
+// single-MUFU reciprocal / square root (1-2 ulp, no range-check branch and no slow-path call behind them)
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 
 }  // namespace gdb

@@ -846,7 +846,13 @@ __global__ void __launch_bounds__(256, 1) render_tc4_kernel(const RenderParams p
           float ix = fmaf(cx, cv[CV_K + 0], fmaf(cy, cv[CV_K + 1], cz * cv[CV_K + 2]));
           float iy = fmaf(cx, cv[CV_K + 3], fmaf(cy, cv[CV_K + 4], cz * cv[CV_K + 5]));
           float iz = fmaxf(fmaf(cx, cv[CV_K + 6], fmaf(cy, cv[CV_K + 7], cz * cv[CV_K + 8])), 1e-6f);
+#ifdef GDB_X_EXACT
           const float rz = __frcp_rn(iz);
+#else
+          // MUFU.RCP alone (1 ulp of a PIXEL coordinate of the colour tap; the texture coordinate of P1 keeps its true divisions):
+          // no range check / slow-path call between a view's projection and its gathers (gdb_render_tc2.cu, head of the file)
+          const float rz = rcp_approx(iz);
+#endif
           float gx = (ix * rz) * two_W - 1.f, gy = (iy * rz) * two_H - 1.f;
           const Bilin bl4 = bilin_border(gx, gy, p.W, p.H);
           const float4* ib = reinterpret_cast<const float4*>(p.rgba) + (size_t)(b * V + v) * p.H * p.W;
