@@ -356,7 +356,11 @@ def test_render_fused_batched_gather_kernel_bit_identical(golden, prefix):
         for k in new:
             assert torch.equal(new[k], old[k]), (k, kw.keys(), _md(new[k], old[k]))
             if k in ("rgbs_feat_dir", "vox_feat"):      # fp32 gathers: same taps, different summation order
-                assert _md(cur[k], old[k]) <= 2e-6 * (1.0 + float(old[k].abs().max())), (k, _md(cur[k], old[k]))
+                # the colour taps inside rgbs_feat_dir additionally come through two equivalent projection chains since the
+                # last session of round 2 (precision 1 / 4: composed matrix + MUFU.RCP, gdb_render_tc2.cu; precision 6: step by
+                # step + correctly rounded reciprocal): a few 1e-5 pixels of tap position, 4.8e-6 of colour measured
+                tol = (1e-5 if k == "rgbs_feat_dir" else 2e-6) * (1.0 + float(old[k].abs().max()))
+                assert _md(cur[k], old[k]) <= tol, (k, _md(cur[k], old[k]), tol)
             else:                                        # downstream of fp16 operand rounding (2^-11 relative steps)
                 tol = 1e-4 * (float(dr.max()) - float(dr.min())) if k == "depth" else 4e-4 * (1.0 + float(old[k].abs().max()))
                 assert _md(cur[k], old[k]) <= tol, (k, _md(cur[k], old[k]), tol)
