@@ -472,7 +472,7 @@ def _psnr(a, b):
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
 
 
-@pytest.mark.parametrize("workload", ["dtu"])
+@pytest.mark.parametrize("workload", ["dtu", "nerf", "llff"])
 def test_benched_math_mode_against_oracle(workload):
     """bench.py's configuration - TF32 cuDNN convolutions (PyTorch's default, also what the reference's own CUDA forward
     runs), cudnn.benchmark, fp16-operand MLP (precision 1), 8-bit source images converted on the device - at the benchmark's
